@@ -1,0 +1,240 @@
+// Device-resident Maximizer state and the fused per-iteration update (one CTA, no host sync).
+//
+// Restates AcceleratedGradientDescent.maximize's rank-0 update (reference src/dualip/optimizers/agd.py:163-187)
+// and calculate_step_size (optimizers/agd_utils.py:4-89) with the history ring and the Lipschitz ratios kept on
+// the device.  The reference recomputes all <=14 ratios every iteration (agd_utils.py:86-88); they only depend on
+// stored history entries, so caching them and computing the newest pair gives the same numbers.
+#include <math.h>
+#include <new>
+
+#include "common.cuh"
+
+using namespace dualip;
+
+struct dualip_agd {
+  int device = 0;
+  int m = 0;
+  int H = 15;
+  float* x = nullptr;
+  float* y = nullptr;
+  float* gh = nullptr;      // H x m ring of gradients
+  float* yh = nullptr;      // H x m ring of y iterates (the reference stores y, not x: agd.py:170-172)
+  float* ratios = nullptr;  // H-1 ring: ratio of pair (j, j+1) at slot j % (H-1)
+  long long* pushes = nullptr;  // number of history pushes so far
+  double* dstate = nullptr;     // [0] max_step_size (mutable: gamma decay), [1] initial_step_size
+  uint8_t* eqmask = nullptr;
+  double* log_obj = nullptr;
+  double* log_step = nullptr;
+  int log_cap = 0;
+};
+
+namespace dualip {
+
+__global__ void __launch_bounds__(1024) agd_step_kernel(float* __restrict__ x, float* __restrict__ y, float* __restrict__ gh,
+                                                        float* __restrict__ yh, float* __restrict__ ratios,
+                                                        long long* __restrict__ pushes, double* __restrict__ dstate,
+                                                        const uint8_t* __restrict__ eqmask, const float* __restrict__ grad,
+                                                        const dualip_scalars* __restrict__ scal, int m, int H, float beta,
+                                                        int decay_now, double decay_factor, double* log_obj,
+                                                        double* log_step, int iter_index) {
+  __shared__ double dscratch[32];
+  __shared__ double s_step;
+  const int tid = threadIdx.x;
+  const long long t = *pushes;  // index of the entry pushed now
+  const int slot = (int)(t % H);
+  const int prev = (int)((t + H - 1) % H);
+  // 1) push (grad, y) and measure the newest pair                      agd_utils.py:11-27, :30-41
+  double dg2 = 0.0, dy2 = 0.0;
+  for (int i = tid; i < m; i += blockDim.x) {
+    const float g = grad[i], yy = y[i];
+    gh[(size_t)slot * m + i] = g;
+    yh[(size_t)slot * m + i] = yy;
+    if (t > 0) {
+      const float dg = __fsub_rn(gh[(size_t)prev * m + i], g);
+      const float dy = __fsub_rn(yh[(size_t)prev * m + i], yy);
+      dg2 = fma((double)dg, (double)dg, dg2);
+      dy2 = fma((double)dy, (double)dy, dy2);
+    }
+  }
+  dg2 = block_sum(dg2, dscratch);
+  dy2 = block_sum(dy2, dscratch);
+  if (tid == 0) {
+    if (t > 0) ratios[(t - 1) % (H - 1)] = __fdiv_rn((float)sqrt(dg2), (float)sqrt(dy2));
+    // 2) step size                                                      agd_utils.py:44-62
+    const long long n_pairs = t < (long long)(H - 1) ? t : (long long)(H - 1);
+    const double max_step = dstate[0], init_step = dstate[1];
+    double step = init_step;
+    if (n_pairs >= H - 1) {
+      // Python max() over the list in chronological order: the first element wins unless a later one is greater
+      const long long j0 = t - (H - 1);
+      float lmax = ratios[j0 % (H - 1)];
+      for (long long j = j0 + 1; j < t; ++j) {
+        const float v = ratios[j % (H - 1)];
+        if (v > lmax) lmax = v;
+      }
+      if (!(isnan(lmax) || isinf(lmax))) {
+        const double cand = (lmax != 0.f) ? 1.0 / (double)lmax : max_step;
+        step = cand < max_step ? cand : max_step;
+      }
+    }
+    s_step = step;
+    if (log_obj) log_obj[iter_index] = scal ? scal->dual_objective : 0.0;
+    if (log_step) log_step[iter_index] = step;
+    if (decay_now) dstate[0] = step * decay_factor;  // agd.py:107
+    *pushes = t + 1;
+  }
+  __syncthreads();
+  // 3) ascent step, projection on the dual cone, momentum              agd.py:181-185, :13-21
+  const float step32 = (float)s_step;
+  const float omb = __fsub_rn(1.0f, beta);
+  for (int i = tid; i < m; i += blockDim.x) {
+    const float xi = x[i], yi = y[i];
+    float yn = __fadd_rn(xi, __fmul_rn(grad[i], step32));
+    if (!(eqmask && eqmask[i])) yn = fmaxf(yn, 0.f);
+    x[i] = __fadd_rn(__fmul_rn(yn, omb), __fmul_rn(yi, beta));
+    y[i] = yn;
+  }
+}
+
+}  // namespace dualip
+
+extern "C" {
+
+void dualip_agd_destroy(dualip_agd* a) {
+  if (!a) return;
+  DeviceGuard g(a->device);
+  cudaFree(a->x);
+  cudaFree(a->y);
+  cudaFree(a->gh);
+  cudaFree(a->yh);
+  cudaFree(a->ratios);
+  cudaFree(a->pushes);
+  cudaFree(a->dstate);
+  cudaFree(a->eqmask);
+  cudaFree(a->log_obj);
+  cudaFree(a->log_step);
+  delete a;
+}
+
+int dualip_agd_reserve_log(dualip_agd* a, int32_t capacity) {
+  if (!a || capacity < 0) {
+    set_error("bad argument");
+    return DUALIP_EINVAL;
+  }
+  if (capacity <= a->log_cap) return DUALIP_OK;
+  DeviceGuard g(a->device);
+  double *lo = nullptr, *ls = nullptr;
+  DUALIP_CUDA_TRY(cudaMalloc(&lo, sizeof(double) * capacity));
+  DUALIP_CUDA_TRY(cudaMalloc(&ls, sizeof(double) * capacity));
+  DUALIP_CUDA_TRY(cudaMemset(lo, 0, sizeof(double) * capacity));
+  DUALIP_CUDA_TRY(cudaMemset(ls, 0, sizeof(double) * capacity));
+  if (a->log_cap > 0) {
+    DUALIP_CUDA_TRY(cudaMemcpy(lo, a->log_obj, sizeof(double) * a->log_cap, cudaMemcpyDeviceToDevice));
+    DUALIP_CUDA_TRY(cudaMemcpy(ls, a->log_step, sizeof(double) * a->log_cap, cudaMemcpyDeviceToDevice));
+  }
+  cudaFree(a->log_obj);
+  cudaFree(a->log_step);
+  a->log_obj = lo;
+  a->log_step = ls;
+  a->log_cap = capacity;
+  return DUALIP_OK;
+}
+
+int dualip_agd_create(dualip_agd** out, int32_t m, int32_t device, const float* initial_dev,
+                      const uint8_t* equality_mask_dev, double initial_step_size, double max_step_size,
+                      int32_t history_len) {
+  if (!out || m <= 0 || history_len < 2) {
+    set_error("bad argument");
+    return DUALIP_EINVAL;
+  }
+  *out = nullptr;
+  DeviceGuard g(device);
+  if (!g.ok) {
+    set_error("cannot select CUDA device %d", device);
+    return DUALIP_ECUDA;
+  }
+  dualip_agd* a = new (std::nothrow) dualip_agd();
+  if (!a) return DUALIP_ENOMEM;
+  a->device = device;
+  a->m = m;
+  a->H = history_len;
+#define AGD_TRY(expr)                                                 \
+  do {                                                                \
+    cudaError_t _e = (expr);                                          \
+    if (_e != cudaSuccess) {                                          \
+      set_error("%s failed: %s", #expr, cudaGetErrorString(_e));      \
+      dualip_agd_destroy(a);                                          \
+      return DUALIP_ECUDA;                                            \
+    }                                                                 \
+  } while (0)
+  AGD_TRY(cudaMalloc(&a->x, sizeof(float) * (m + 4)));
+  AGD_TRY(cudaMalloc(&a->y, sizeof(float) * (m + 4)));
+  AGD_TRY(cudaMalloc(&a->gh, sizeof(float) * (size_t)m * a->H));
+  AGD_TRY(cudaMalloc(&a->yh, sizeof(float) * (size_t)m * a->H));
+  AGD_TRY(cudaMalloc(&a->ratios, sizeof(float) * a->H));
+  AGD_TRY(cudaMalloc(&a->pushes, sizeof(long long)));
+  AGD_TRY(cudaMalloc(&a->dstate, sizeof(double) * 2));
+  AGD_TRY(cudaMemset(a->pushes, 0, sizeof(long long)));
+  AGD_TRY(cudaMemset(a->ratios, 0, sizeof(float) * a->H));
+  if (initial_dev) {
+    AGD_TRY(cudaMemcpy(a->x, initial_dev, sizeof(float) * m, cudaMemcpyDeviceToDevice));
+    AGD_TRY(cudaMemcpy(a->y, initial_dev, sizeof(float) * m, cudaMemcpyDeviceToDevice));
+  } else {
+    AGD_TRY(cudaMemset(a->x, 0, sizeof(float) * m));
+    AGD_TRY(cudaMemset(a->y, 0, sizeof(float) * m));
+  }
+  const double ds[2] = {max_step_size, initial_step_size};
+  AGD_TRY(cudaMemcpy(a->dstate, ds, sizeof(ds), cudaMemcpyHostToDevice));
+  if (equality_mask_dev) {
+    AGD_TRY(cudaMalloc(&a->eqmask, m));
+    AGD_TRY(cudaMemcpy(a->eqmask, equality_mask_dev, m, cudaMemcpyDeviceToDevice));
+  }
+#undef AGD_TRY
+  *out = a;
+  return DUALIP_OK;
+}
+
+const float* dualip_agd_x(const dualip_agd* a) { return a ? a->x : nullptr; }
+const float* dualip_agd_y(const dualip_agd* a) { return a ? a->y : nullptr; }
+
+int dualip_agd_get(dualip_agd* a, float* x_out_dev, float* y_out_dev, void* stream) {
+  if (!a) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_out_dev) DUALIP_CUDA_TRY(cudaMemcpyAsync(x_out_dev, a->x, sizeof(float) * a->m, cudaMemcpyDeviceToDevice, st));
+  if (y_out_dev) DUALIP_CUDA_TRY(cudaMemcpyAsync(y_out_dev, a->y, sizeof(float) * a->m, cudaMemcpyDeviceToDevice, st));
+  return DUALIP_OK;
+}
+
+int dualip_agd_step(dualip_agd* a, const float* grad_dev, const dualip_scalars* scalars_dev, float beta,
+                    int32_t decay_now, double decay_factor, int32_t iter_index, void* stream) {
+  if (!a || !grad_dev) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  const bool log = iter_index >= 0 && iter_index < a->log_cap;
+  agd_step_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a->x, a->y, a->gh, a->yh, a->ratios, a->pushes, a->dstate, a->eqmask,
+                                                        grad_dev, scalars_dev, a->m, a->H, beta, decay_now, decay_factor,
+                                                        log ? a->log_obj : nullptr, log ? a->log_step : nullptr,
+                                                        log ? iter_index : 0);
+  DUALIP_CUDA_TRY(cudaGetLastError());
+  return DUALIP_OK;
+}
+
+int dualip_agd_read_log(dualip_agd* a, int32_t count, double* dual_obj_host, double* step_host, void* stream) {
+  if (!a || count < 0 || count > a->log_cap) {
+    set_error("bad log range");
+    return DUALIP_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (count > 0) {
+    if (dual_obj_host) DUALIP_CUDA_TRY(cudaMemcpyAsync(dual_obj_host, a->log_obj, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+    if (step_host) DUALIP_CUDA_TRY(cudaMemcpyAsync(step_host, a->log_step, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+  }
+  DUALIP_CUDA_TRY(cudaStreamSynchronize(st));
+  return DUALIP_OK;
+}
+
+}  // extern "C"

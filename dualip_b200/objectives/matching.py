@@ -1,0 +1,311 @@
+"""Matching objective: same class names, constructor signatures and `calculate` keywords as the reference
+(src/dualip/objectives/matching.py), with the body of `calculate` replaced by one call into the C-ABI
+(include/dualip_b200.h: dualip_matching_calc / dualip_matching_partial + dualip_matching_epilogue).
+
+CUDA-only: tensors must live on a CUDA device and be float32.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from dualip_b200 import _native
+from dualip_b200.objectives.base import BaseInputArgs, BaseObjective, ObjectiveResult
+from dualip_b200.projections.base import ProjectionEntry, project
+
+_IDX = {name: i for i, name in enumerate(_native.SCALAR_FIELDS)}
+
+
+@dataclass
+class MatchingInputArgs(BaseInputArgs):
+    """Input arguments of the matching objective (reference matching.py:12-22).
+
+    A and c are `torch.sparse_csc` tensors of shape (m, n) sharing one sparsity pattern; b_vec=None marks a local
+    shard whose partial results are reduced by the distributed wrapper."""
+
+    A: torch.Tensor
+    c: torch.Tensor
+    projection_map: dict[str, ProjectionEntry]
+    b_vec: torch.Tensor
+    equality_mask: torch.Tensor = None
+
+
+def _indices_to_device(indices, device) -> torch.Tensor:
+    if isinstance(indices, range):
+        if indices.step == 1:
+            return torch.arange(indices.start, indices.stop, dtype=torch.int64, device=device)
+        return torch.arange(indices.start, indices.stop, indices.step, dtype=torch.int64, device=device)
+    if isinstance(indices, torch.Tensor):
+        return indices.to(device=device, dtype=torch.int64)
+    return torch.as_tensor(np.asarray(indices, dtype=np.int64), device=device)
+
+
+def _build_class_table(ccol: torch.Tensor, n_cols: int, projection_map, batching: bool):
+    """Turns the reference's projection_map (dict of ProjectionEntry) into the C-ABI class table and a per-column
+    class id.  Returns (classes ctypes array, n_classes, col_class uint8 tensor or None when one entry covers all).
+
+    Also derives, per simplex entry, whether its 1-entry columns would sit in a bucket of padded length 1 in the
+    reference (matching.py:87-114 thresholds {1,2},{3,4},{5..8},...; batching=False: one bucket), because the
+    reference's top-2 shortcut is skipped there (simplex.py:166)."""
+    device = ccol.device
+    classes = []
+    col_class = None
+    entries = list(projection_map.items())
+    lengths = None
+    single_full = False
+    if len(entries) == 1:
+        ind = entries[0][1].indices
+        if isinstance(ind, range) and ind.start == 0 and ind.step == 1 and ind.stop == n_cols:
+            single_full = True
+        elif not isinstance(ind, range) and len(ind) == n_cols:
+            t = _indices_to_device(ind, device)
+            single_full = bool((t == torch.arange(n_cols, device=device)).all().item())
+    if not single_full:
+        # class 0 = identity for columns no entry names (the reference leaves them unprojected)
+        classes.append(_native.ProjClass(_native.PROJ_CLAMP, -np.inf, np.inf, 1.0, 1.0, 0))
+        col_class = torch.zeros(n_cols, dtype=torch.uint8, device=device)
+    for key, entry in entries:
+        op = project(entry.proj_type, **entry.proj_params)  # raises ValueError for unknown names, like the reference
+        cls = op.native_class()
+        idx = None if single_full else _indices_to_device(entry.indices, device)
+        if idx is not None and idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= n_cols):
+            raise IndexError(f"projection entry '{key}' names a column outside [0, {n_cols})")
+        if cls.kind != _native.PROJ_CLAMP:
+            if lengths is None:
+                lengths = ccol[1:] - ccol[:-1]
+            sel = lengths if idx is None else lengths[idx]
+            if sel.numel():
+                if batching:
+                    unpadded = bool(((sel == 1).any() & ~(sel == 2).any()).item())
+                else:
+                    unpadded = bool((sel.max() == 1).item())
+                if unpadded:
+                    cls.flags |= _native.PROJ_FLAG_D1_UNPADDED
+        if idx is not None:
+            if len(classes) >= 255:
+                raise ValueError("at most 254 projection entries are supported")
+            if idx.numel():
+                if bool((col_class[idx] != 0).any().item()):
+                    raise ValueError(
+                        f"projection entry '{key}' overlaps an earlier entry; dualip_b200 projects each column once"
+                    )
+                col_class[idx] = len(classes)
+        classes.append(cls)
+    arr = (_native.ProjClass * len(classes))(*classes)
+    return arr, len(classes), col_class
+
+
+class MatchingSolverDualObjectiveFunction(BaseObjective):
+    """Dual gradient, objective and regularisation penalty of a matching LP on one GPU.
+
+    Drop-in for the reference class of the same name (matching.py:37-188): same constructor, same `calculate`
+    keywords, same ObjectiveResult fields.  Construction builds the device-side pass table
+    (dualip_plan_create); `calculate` is one fused kernel launch."""
+
+    def __init__(self, matching_input_args: MatchingInputArgs, gamma: float, batching: bool = True):
+        A, c = matching_input_args.A, matching_input_args.c
+        if A.layout != torch.sparse_csc or c.layout != torch.sparse_csc:
+            raise ValueError("Both A and c must be CSC-format sparse tensors")
+        if not A.is_cuda:
+            raise RuntimeError("dualip_b200 objectives need CUDA tensors (no CPU fallback); move the inputs to a GPU")
+        if A.values().dtype != torch.float32 or c.values().dtype != torch.float32:
+            raise TypeError("dualip_b200 is float32-only")
+        if A.shape != c.shape or A.values().shape != c.values().shape:
+            raise ValueError("A and c must share the same sparsity pattern")
+        self.A, self.c = A, c
+        self.gamma = gamma
+        self.b_vec = matching_input_args.b_vec
+        self.projection_map = matching_input_args.projection_map
+        self.is_distributed = self.b_vec is None
+        self.equality_mask = matching_input_args.equality_mask
+        self.batching = batching
+        self.device = A.device
+        self.m, self.n = int(A.shape[0]), int(A.shape[1])
+        if self.b_vec is not None:
+            if self.b_vec.device != self.device or self.b_vec.dtype != torch.float32:
+                self.b_vec = self.b_vec.to(device=self.device, dtype=torch.float32)
+            self.b_vec = self.b_vec.contiguous()
+
+        ccol, row = A.ccol_indices(), A.row_indices()
+        if ccol.dtype != row.dtype or ccol.dtype not in (torch.int32, torch.int64):
+            raise TypeError("ccol_indices and row_indices must both be int32 or both int64")
+        # keep the borrowed value arrays alive for the lifetime of the plan
+        self._a_vals = A.values().contiguous()
+        self._c_vals = c.values().contiguous()
+        self.nnz = int(self._a_vals.numel())
+        classes, n_classes, col_class = _build_class_table(ccol, self.n, self.projection_map, batching)
+        self._classes = classes
+        desc = _native.CscDesc(
+            n_cols=self.n, nnz=self.nnz, n_rows=self.m, index_bits=32 if ccol.dtype == torch.int32 else 64,
+            ccol_dev=ccol.data_ptr(), row_dev=row.data_ptr() if self.nnz else 0,
+            a_dev=self._a_vals.data_ptr() if self.nnz else 0, c_dev=self._c_vals.data_ptr() if self.nnz else 0,
+            col_class_dev=col_class.data_ptr() if col_class is not None else None,
+            classes=ctypes.cast(classes, ctypes.POINTER(_native.ProjClass)), n_classes=n_classes,
+            device=self.device.index if self.device.index is not None else torch.cuda.current_device(),
+        )
+        handle = ctypes.c_void_p()
+        torch.cuda.synchronize(self.device)
+        _native.check(_native.lib().dualip_plan_create(ctypes.byref(handle), ctypes.byref(desc)), "dualip_plan_create")
+        self._plan = handle
+        self._scal = torch.zeros(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=self.device)
+        self._grad = torch.empty(self.m, dtype=torch.float32, device=self.device)
+        self._partial = torch.empty(self.m + 2, dtype=torch.float32, device=self.device)
+
+    def __del__(self):
+        plan = getattr(self, "_plan", None)
+        if plan:
+            try:
+                _native.lib().dualip_plan_destroy(plan)
+            except Exception:
+                pass
+            self._plan = None
+
+    # -- introspection -------------------------------------------------------------------------------------
+    def plan_info(self) -> dict:
+        buf = (ctypes.c_int64 * 10)()
+        _native.check(_native.lib().dualip_plan_info(self._plan, buf, 10))
+        names = ["n_passes", "n_long_cols", "n_ctas", "threads", "smem_bytes", "row_bits", "smem_mode", "run_len",
+                 "launches_per_calc", "owned_bytes"]
+        return dict(zip(names, list(buf)))
+
+    def algorithmic_bytes(self, save_primal: bool = False) -> int:
+        """B_alg of SURVEY.md §8(d): fp32 a + fp32 c + int32 row per nnz, int32 ccol per column, read lambda and b and
+        write grad per dual (+4 B/nnz when the primal is written)."""
+        return 12 * self.nnz + 4 * (self.n + 1) + 12 * self.m + (4 * self.nnz if save_primal else 0)
+
+    # -- raw launches (device pointers; used by the Maximizer's fused loop) ---------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def launch_calc(self, lam_ptr: int, gamma: float, grad_ptr: int, scal_ptr: int, x_ptr: Optional[int] = None,
+                    diag_ptr: Optional[int] = None) -> None:
+        b_ptr = self.b_vec.data_ptr() if self.b_vec is not None else None
+        rc = _native.lib().dualip_matching_calc(self._plan, lam_ptr, b_ptr, float(gamma), grad_ptr, scal_ptr, x_ptr,
+                                                diag_ptr, 0, self._stream())
+        _native.check(rc, "dualip_matching_calc")
+
+    def launch_partial(self, lam_ptr: int, gamma: float, partial_ptr: int, x_ptr: Optional[int] = None,
+                       diag_ptr: Optional[int] = None) -> None:
+        rc = _native.lib().dualip_matching_partial(self._plan, lam_ptr, float(gamma), partial_ptr, x_ptr, diag_ptr, 0,
+                                                   self._stream())
+        _native.check(rc, "dualip_matching_partial")
+
+    def _check_dual(self, dual_val: torch.Tensor) -> torch.Tensor:
+        if dual_val.device != self.device:
+            raise RuntimeError(f"dual_val is on {dual_val.device}, objective on {self.device}")
+        if dual_val.dtype != torch.float32:
+            raise TypeError("dual_val must be float32")
+        if dual_val.numel() != self.m:
+            raise ValueError(f"dual_val has {dual_val.numel()} entries, expected {self.m}")
+        return dual_val.contiguous()
+
+    # -- the reference-facing call -------------------------------------------------------------------------
+    def calculate(self, dual_val: torch.Tensor, gamma: float = None, save_primal: bool = False, **kwargs) -> ObjectiveResult:
+        """Same contract as reference matching.py:116-188.  `diagnostics=True` (extra keyword) additionally returns
+        the per-column projection branch / support size as `result.projection_diag` (uint8 per nnz position)."""
+        if gamma is not None and gamma != self.gamma:
+            self.gamma = gamma  # no O(E) rescaling pass: the kernel forms -(a*lambda + c)/gamma in registers
+        lam = self._check_dual(dual_val)
+        with torch.cuda.device(self.device):
+            grad = torch.empty(self.m, dtype=torch.float32, device=self.device)
+            scal = torch.empty(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=self.device)
+            x = torch.empty(self.nnz, dtype=torch.float32, device=self.device) if save_primal else None
+            diag = None
+            if kwargs.get("diagnostics"):
+                diag = torch.full((self.nnz,), 255, dtype=torch.uint8, device=self.device)
+            self.launch_calc(lam.data_ptr(), self.gamma, grad.data_ptr(), scal.data_ptr(),
+                             x.data_ptr() if x is not None else None, diag.data_ptr() if diag is not None else None)
+            s32 = scal.to(torch.float32)
+        if not self.is_distributed:
+            res = ObjectiveResult(
+                dual_gradient=grad,
+                dual_objective=s32[_IDX["dual_objective"]],
+                reg_penalty=s32[_IDX["reg_penalty"]],
+                dual_val_times_grad=s32[_IDX["dual_val_times_grad"]],
+                max_pos_slack=s32[_IDX["max_pos_slack"]],
+                sum_pos_slack=s32[_IDX["sum_pos_slack"]],
+            )
+        else:
+            # local-shard mode (matching.py:179-184): raw partial gradient, dual_objective = c.x
+            res = ObjectiveResult(
+                dual_gradient=grad,
+                dual_objective=s32[_IDX["primal_objective"]],
+                reg_penalty=s32[_IDX["reg_penalty"]],
+            )
+        if save_primal:
+            res.primal_var = x  # a fresh buffer (the reference aliases its scratch, matching.py:156,186)
+            res.primal_objective = s32[_IDX["primal_objective"]].clone()
+        if diag is not None:
+            res.projection_diag = diag
+        res.scalars64 = scal
+        return res
+
+
+def reduce_partials(partial: torch.Tensor) -> torch.Tensor:
+    """The one collective of the sharded path: SUM all-reduce of the packed [grad(m) | c.x | ||x||^2] vector
+    (replaces three dist.reduce + barrier, reference matching.py:272-277).  No-op without a process group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(partial, op=dist.ReduceOp.SUM)
+    return partial
+
+
+class MatchingSolverDualObjectiveFunctionDistributed(BaseObjective):
+    """Entity-sharded matching objective: one process per GPU, each with its column shard.
+
+    Same constructor as the reference (matching.py:218-245).  Per call: local fused kernel -> ONE all-reduce of
+    m+2 floats -> m-length tail on every rank.  Every rank returns the full result (a superset of the reference,
+    where only rank 0's is meaningful, matching.py:280-307), so the Maximizer can update redundantly and skip the
+    two broadcasts of agd.py:204-206."""
+
+    result_on_all_ranks = True
+
+    def __init__(self, local_matching_input_args: MatchingInputArgs, b_vec: torch.Tensor, gamma: float,
+                 host_device=None, batching: bool = True):
+        if local_matching_input_args.b_vec is not None:
+            raise ValueError("local_matching_input_args.b_vec must be None: b_vec is shared across ranks")
+        self.gamma = gamma
+        self.host_device = host_device
+        self.equality_mask = local_matching_input_args.equality_mask
+        self.local_objective = MatchingSolverDualObjectiveFunction(local_matching_input_args, gamma, batching)
+        self.device = self.local_objective.device
+        self.m = self.local_objective.m
+        self.b_vec = b_vec.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def launch_partial_and_reduce(self, lam_ptr: int, gamma: float, partial: torch.Tensor) -> None:
+        self.local_objective.launch_partial(lam_ptr, gamma, partial.data_ptr())
+        reduce_partials(partial)
+
+    def launch_epilogue(self, partial_ptr: int, lam_ptr: int, gamma: float, grad_ptr: int, scal_ptr: int) -> None:
+        rc = _native.lib().dualip_matching_epilogue(partial_ptr, self.m, lam_ptr, self.b_vec.data_ptr(), float(gamma),
+                                                    grad_ptr, scal_ptr, self.local_objective._stream())
+        _native.check(rc, "dualip_matching_epilogue")
+
+    def calculate(self, dual_val: torch.Tensor, gamma: float = None, save_primal: bool = False, rank: int = 0) -> ObjectiveResult:
+        if save_primal:
+            raise NotImplementedError("save_primal=True is not yet supported in distributed mode")  # matching.py:255-256
+        if gamma is not None and gamma != self.gamma:
+            self.gamma = gamma
+            self.local_objective.gamma = gamma
+        lam = self.local_objective._check_dual(dual_val)
+        with torch.cuda.device(self.device):
+            partial = torch.empty(self.m + 2, dtype=torch.float32, device=self.device)
+            grad = torch.empty(self.m, dtype=torch.float32, device=self.device)
+            scal = torch.empty(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=self.device)
+            self.launch_partial_and_reduce(lam.data_ptr(), self.gamma, partial)
+            self.launch_epilogue(partial.data_ptr(), lam.data_ptr(), self.gamma, grad.data_ptr(), scal.data_ptr())
+            s32 = scal.to(torch.float32)
+        res = ObjectiveResult(
+            dual_gradient=grad,
+            dual_objective=s32[_IDX["dual_objective"]],
+            reg_penalty=s32[_IDX["reg_penalty"]],
+            dual_val_times_grad=s32[_IDX["dual_val_times_grad"]],
+            max_pos_slack=s32[_IDX["max_pos_slack"]],
+            sum_pos_slack=s32[_IDX["sum_pos_slack"]],
+        )
+        res.scalars64 = scal
+        return res

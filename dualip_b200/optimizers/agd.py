@@ -1,0 +1,252 @@
+"""Maximizer: Nesterov-accelerated projected gradient ascent on the dual.
+
+Same class name, constructor and `maximize(f, initial_value, rank=0) -> SolverResult` as the reference
+(src/dualip/optimizers/agd.py:66-229).  Two loops:
+
+* fused (CUDA matching objectives): iterate, history ring, step-size rule and logs live on the device
+  (csrc/agd.cu); one iteration = the objective's kernel(s) + one update kernel, with no host synchronisation;
+* generic (any object with `calculate` / `equality_mask`): host-driven, the reference's semantics op for op.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+from dualip_b200 import _native
+from dualip_b200.objectives.base import BaseObjective
+from dualip_b200.optimizers.agd_utils import calculate_step_size
+from dualip_b200.types import ObjectiveResult, SolverResult
+
+_IDX = {name: i for i, name in enumerate(_native.SCALAR_FIELDS)}
+
+
+def project_on_nn_cone(y: torch.Tensor, equality_mask: torch.Tensor | None = None) -> torch.Tensor:
+    """Dual cone: lambda_r >= 0 on inequality rows, free on equality rows (reference agd.py:13-21)."""
+    clipped = y.clamp_min(0.0)
+    return clipped if equality_mask is None else torch.where(equality_mask, y, clipped)
+
+
+def format_objective_result_summary(iteration: int, objective_result: ObjectiveResult) -> str:
+    """One-line iteration summary with the reference's field names (agd.py:24-63)."""
+
+    def show(name, val):
+        if val is None:
+            return None
+        try:
+            if isinstance(val, torch.Tensor):
+                return f"{name}={val.item()}" if val.numel() == 1 else f"{name}.shape={tuple(val.shape)}"
+            return f"{name}={val}"
+        except Exception:
+            return f"{name}=<unprintable>"
+
+    try:
+        grad_norm = f"dual_grad_norm={float(objective_result.dual_gradient.norm().item())}"
+    except Exception:
+        grad_norm = "dual_grad_norm=<unprintable>"
+    parts = [f"iter={iteration}", show("dual_objective", objective_result.dual_objective), grad_norm]
+    for name in ("reg_penalty", "primal_objective", "primal_var", "dual_val_times_grad", "max_pos_slack", "sum_pos_slack"):
+        parts.append(show(name, getattr(objective_result, name, None)))
+    return " | ".join(p for p in parts if p is not None)
+
+
+class AcceleratedGradientDescent:
+    def __init__(
+        self,
+        max_iter: int,
+        gamma: float,
+        initial_step_size: float = 1e-5,
+        max_step_size: float = 0.1,
+        gamma_decay_type: str = None,
+        gamma_decay_params: dict = {},
+        save_primal: bool = False,
+        iteration_callback: Optional[Callable[[int, ObjectiveResult], None]] = None,
+    ):
+        self.initial_step_size = initial_step_size
+        self.max_step_size = max_step_size
+        self.max_iter = max_iter
+        self.beta_seq = self._compute_beta_seq(self.max_iter)
+        self.streams = None
+        self.gamma = gamma
+        self.gamma_decay_type = gamma_decay_type
+        self.gamma_decay_params = gamma_decay_params
+        self.save_primal = save_primal
+        self._user_callback = iteration_callback is not None
+        self.iteration_callback = iteration_callback if iteration_callback is not None else self._default_iteration_callback
+
+    def _compute_beta_seq(self, max_iter: int) -> torch.Tensor:
+        """beta_i = (1 - t_{i+1}) / t_{i+2}, t_{k} = (1 + sqrt(1 + 4 t_{k-1}^2))/2; t is stored in float32 and the
+        square root is taken in double, exactly like the reference (agd.py:93-100)."""
+        t = torch.zeros(max_iter + 2)
+        for k in range(1, max_iter + 2):
+            t[k] = (1 + math.sqrt(1 + 4 * (t[k - 1] ** 2))) / 2
+        return (1 - t[1 : max_iter + 1]) / t[2 : max_iter + 2]
+
+    def _update_gamma(self, itr: int, step_size: float):
+        """Step decay: every `decay_steps` iterations gamma *= decay_factor and the step cap becomes
+        step * decay_factor (reference agd.py:102-109)."""
+        if self.gamma_decay_type != "step":
+            raise ValueError(f"Unsupported gamma decay type: {self.gamma_decay_type}")
+        if itr % self.gamma_decay_params["decay_steps"] == 0:
+            factor = self.gamma_decay_params["decay_factor"]
+            self.gamma = self.gamma * factor
+            self.max_step_size = step_size * factor
+
+    def _default_iteration_callback(self, iteration: int, objective_result: ObjectiveResult) -> None:
+        try:
+            print(format_objective_result_summary(iteration, objective_result))
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------------
+    def maximize(self, f: BaseObjective, initial_value: torch.Tensor, rank: int = 0) -> SolverResult:
+        """Maximise the dual objective of `f` starting from `initial_value` (reference agd.py:121-229)."""
+        if self._fusable(f, initial_value):
+            return self._maximize_fused(f, initial_value, rank)
+        return self._maximize_generic(f, initial_value, rank)
+
+    @staticmethod
+    def _fusable(f, initial_value: torch.Tensor) -> bool:
+        from dualip_b200.objectives.matching import (
+            MatchingSolverDualObjectiveFunction,
+            MatchingSolverDualObjectiveFunctionDistributed,
+        )
+
+        if not (isinstance(initial_value, torch.Tensor) and initial_value.is_cuda and initial_value.dtype == torch.float32):
+            return False
+        if isinstance(f, MatchingSolverDualObjectiveFunctionDistributed):
+            return f.device == initial_value.device
+        return (isinstance(f, MatchingSolverDualObjectiveFunction) and not f.is_distributed
+                and f.device == initial_value.device)
+
+    # -- fused device-resident loop ------------------------------------------------------------------------
+    def _maximize_fused(self, f, initial_value: torch.Tensor, rank: int) -> SolverResult:
+        from dualip_b200.objectives.matching import MatchingSolverDualObjectiveFunctionDistributed
+
+        lib = _native.lib()
+        device = initial_value.device
+        m = initial_value.numel()
+        sharded = isinstance(f, MatchingSolverDualObjectiveFunctionDistributed)
+        if self.save_primal and sharded:
+            raise NotImplementedError("save_primal=True is not yet supported in distributed mode")
+        eq = f.equality_mask
+        eq_u8 = eq.to(device=device, dtype=torch.uint8).contiguous() if eq is not None else None
+        init = initial_value.detach().contiguous()
+        beta = self.beta_seq.tolist()
+        decay = self.gamma is not None and self.gamma_decay_type is not None
+        if decay and self.gamma_decay_type != "step":
+            raise ValueError(f"Unsupported gamma decay type: {self.gamma_decay_type}")
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            handle = ctypes.c_void_p()
+            torch.cuda.synchronize(device)
+            _native.check(lib.dualip_agd_create(ctypes.byref(handle), m, device.index, init.data_ptr(),
+                                                eq_u8.data_ptr() if eq_u8 is not None else None,
+                                                float(self.initial_step_size), float(self.max_step_size), 15),
+                          "dualip_agd_create")
+            try:
+                _native.check(lib.dualip_agd_reserve_log(handle, max(self.max_iter, 1)))
+                x_ptr = lib.dualip_agd_x(handle)
+                grad = torch.empty(m, dtype=torch.float32, device=device)
+                scal = torch.zeros(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=device)
+                partial = torch.empty(m + 2, dtype=torch.float32, device=device) if sharded else None
+                primal = None
+                for i in range(1, self.max_iter + 1):
+                    gamma_i = self.gamma if self.gamma is not None else f.gamma
+                    f.gamma = gamma_i
+                    last_primal = i == self.max_iter and self.save_primal
+                    if sharded:
+                        f.local_objective.gamma = gamma_i
+                        f.launch_partial_and_reduce(x_ptr, gamma_i, partial)
+                        f.launch_epilogue(partial.data_ptr(), x_ptr, gamma_i, grad.data_ptr(), scal.data_ptr())
+                    else:
+                        if last_primal:
+                            primal = torch.empty(f.nnz, dtype=torch.float32, device=device)
+                        f.launch_calc(x_ptr, gamma_i, grad.data_ptr(), scal.data_ptr(),
+                                      primal.data_ptr() if last_primal else None)
+                    if rank == 0:
+                        self.iteration_callback(i, self._view_result(grad, scal, primal if last_primal else None))
+                    decay_now, factor = 0, 1.0
+                    if decay and i % self.gamma_decay_params["decay_steps"] == 0:
+                        decay_now, factor = 1, float(self.gamma_decay_params["decay_factor"])
+                        self.gamma = self.gamma * factor
+                    _native.check(lib.dualip_agd_step(handle, grad.data_ptr(), scal.data_ptr(), float(beta[i - 1]),
+                                                      decay_now, factor, i - 1, stream), "dualip_agd_step")
+                n = self.max_iter
+                obj_log = (ctypes.c_double * max(n, 1))()
+                step_log = (ctypes.c_double * max(n, 1))()
+                _native.check(lib.dualip_agd_read_log(handle, n, obj_log, step_log, stream), "dualip_agd_read_log")
+                y = torch.empty(m, dtype=torch.float32, device=device)
+                _native.check(lib.dualip_agd_get(handle, None, y.data_ptr(), stream))
+                torch.cuda.synchronize(device)
+            finally:
+                lib.dualip_agd_destroy(handle)
+        dual_obj_log = [float(v) for v in obj_log[:n]]
+        step_size_log = [float(v) for v in step_log[:n]]
+        if decay and step_size_log:
+            # host mirror of the device-side cap (agd.py:107), for callers that inspect the optimizer afterwards
+            steps = self.gamma_decay_params["decay_steps"]
+            k = (n // steps) * steps
+            if k >= 1:
+                self.max_step_size = step_size_log[k - 1] * self.gamma_decay_params["decay_factor"]
+        final = self._view_result(grad, scal, primal, as_float32=True)
+        return SolverResult(dual_val=y, dual_objective=dual_obj_log[-1] if dual_obj_log else 0.0, objective_result=final,
+                            dual_objective_log=dual_obj_log, step_size_log=step_size_log)
+
+    @staticmethod
+    def _view_result(grad, scal, primal, as_float32: bool = False) -> ObjectiveResult:
+        s = scal.to(torch.float32) if as_float32 else scal
+        res = ObjectiveResult(
+            dual_gradient=grad,
+            dual_objective=s[_IDX["dual_objective"]],
+            reg_penalty=s[_IDX["reg_penalty"]],
+            dual_val_times_grad=s[_IDX["dual_val_times_grad"]],
+            max_pos_slack=s[_IDX["max_pos_slack"]],
+            sum_pos_slack=s[_IDX["sum_pos_slack"]],
+        )
+        if primal is not None:
+            res.primal_var = primal
+            res.primal_objective = s[_IDX["primal_objective"]]
+        return res
+
+    # -- generic host-driven loop (user objectives, CPU tensors) -------------------------------------------
+    def _maximize_generic(self, f, initial_value: torch.Tensor, rank: int) -> SolverResult:
+        grad_history, dual_history = [], []
+        dual_obj_log, step_size_log = [], []
+        x = initial_value.clone()
+        y = initial_value.clone()
+        equality_mask = f.equality_mask
+        everyone_updates = bool(getattr(f, "result_on_all_ranks", False))
+        distributed = dist.is_available() and dist.is_initialized()
+        dual_obj = 0.0
+        objective_result = None
+        for i in range(1, self.max_iter + 1):
+            kwargs = {"gamma": self.gamma} if self.gamma is not None else {}
+            if i == self.max_iter and self.save_primal:
+                kwargs["save_primal"] = self.save_primal
+            objective_result = f.calculate(dual_val=x, rank=rank, **kwargs)
+            if rank == 0 or everyone_updates:
+                if rank == 0:
+                    self.iteration_callback(i, objective_result)
+                dual_obj = objective_result.dual_objective.cpu().item()
+                dual_obj_log.append(dual_obj)
+                step_size = calculate_step_size(objective_result.dual_gradient, y, grad_history, dual_history,
+                                                initial_step_size=self.initial_step_size, max_step_size=self.max_step_size)
+                step_size_log.append(step_size)
+                y_new = project_on_nn_cone(x + objective_result.dual_gradient * step_size, equality_mask)
+                b_i = self.beta_seq[i - 1]
+                x = (y_new * (1.0 - b_i)) + (y * b_i)
+                y = y_new
+                if self.gamma is not None and self.gamma_decay_type is not None:
+                    self._update_gamma(i, step_size)
+            if distributed and not everyone_updates:
+                dist.broadcast(x, src=0)
+                dist.broadcast(y, src=0)
+        if rank == 0 or everyone_updates:
+            return SolverResult(dual_val=y, dual_objective=dual_obj, objective_result=objective_result,
+                                dual_objective_log=dual_obj_log, step_size_log=step_size_log)
+        return SolverResult(dual_val=y, dual_objective=0.0, objective_result=objective_result, dual_objective_log=[],
+                            step_size_log=[])

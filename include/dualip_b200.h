@@ -1,0 +1,171 @@
+/*
+ * dualip_b200 — C-ABI of the B200-native DuaLip dual-ascent hot path.
+ *
+ * The reference (linkedin/DuaLip v5.0.1) has no FFI: its seam is the Python
+ * protocol  f.calculate(dual_val, gamma, save_primal) -> ObjectiveResult
+ * (reference src/dualip/objectives/matching.py:116-188) called once per
+ * iteration by AcceleratedGradientDescent.maximize (optimizers/agd.py:150-160).
+ * The entry points below are what a binding for that seam calls.  Plain
+ * pointers and sizes only; no torch types.  All `*_dev` pointers are CUDA device
+ * pointers on the plan's device; every launch goes to the `stream` argument
+ * (a cudaStream_t passed as void*), performs no host synchronisation and no
+ * allocation, and is therefore CUDA-graph capturable (except the *_host calls).
+ *
+ * Return value: 0 on success, negative DUALIP_E* on failure; the message is
+ * available from dualip_last_error() (thread-local).
+ */
+#ifndef DUALIP_B200_H
+#define DUALIP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DUALIP_B200_ABI_VERSION 1
+
+/* error codes */
+#define DUALIP_OK 0
+#define DUALIP_EINVAL (-1)   /* bad argument / unsupported layout  (reference: ValueError)   */
+#define DUALIP_ECUDA (-2)    /* CUDA runtime error                                            */
+#define DUALIP_ENOMEM (-3)   /* allocation failure                                            */
+#define DUALIP_ERANGE (-4)   /* size outside what this build supports                         */
+
+/* projection kinds (reference src/dualip/projections/{box,cone,simplex}.py) */
+#define DUALIP_PROJ_CLAMP 0       /* box(lower,upper), cone(lower) / cone(upper) / cone(): x = min(max(v,lo),hi); +-inf = open */
+#define DUALIP_PROJ_SIMPLEX 1     /* "simplex":    {x>=0, sum x <= z}, batched Duchi with pre-clamp (simplex.py:126-236, :248-255) */
+#define DUALIP_PROJ_SIMPLEX_EQ 2  /* "simplex_eq": {x>=0, sum x  = z}, same routine without the feasibility branch (:267-274)      */
+
+/* flags of a projection class */
+#define DUALIP_PROJ_FLAG_D1_UNPADDED 1u /* 1-nnz columns of this class sit in a bucket whose padded length L is 1, so the
+                                           reference skips its top-2 shortcut for them (simplex.py:166 `if L > 1`)              */
+
+/* One row per distinct (proj_type, proj_params) of the reference's projection_map
+ * (projections/base.py:8-12).  Columns reference it through col_class[]. */
+typedef struct dualip_proj_class {
+  int32_t kind;   /* DUALIP_PROJ_*                                                     */
+  float lo;       /* CLAMP: lower bound or -INFINITY                                    */
+  float hi;       /* CLAMP: upper bound or +INFINITY                                    */
+  float z;        /* SIMPLEX*: radius, fl32(z)                                          */
+  float z_thr;    /* SIMPLEX : fl32(double(z) + 1e-6), the feasibility threshold (simplex.py:154) */
+  uint32_t flags; /* DUALIP_PROJ_FLAG_*                                                 */
+} dualip_proj_class;
+
+/* Description of one (local shard of a) matching LP: A and c are CSC with ONE shared
+ * sparsity pattern (reference MatchingInputArgs, matching.py:12-22). */
+typedef struct dualip_csc_desc {
+  int64_t n_cols;          /* entities (columns of A)                                   */
+  int64_t nnz;             /* stored entries E                                          */
+  int32_t n_rows;          /* dual dimension m                                          */
+  int32_t index_bits;      /* 32 or 64: width of ccol_dev[] and row_dev[] entries       */
+  const void* ccol_dev;    /* n_cols+1 column pointers, non-decreasing, ccol[0]=0       */
+  const void* row_dev;     /* nnz row indices in [0,m)  (copied, narrowed; not retained) */
+  const float* a_dev;      /* nnz values of A   (BORROWED: must outlive the plan)        */
+  const float* c_dev;      /* nnz values of c   (BORROWED: must outlive the plan)        */
+  const uint8_t* col_class_dev; /* n_cols class ids into classes[], or NULL = all columns class 0 */
+  const dualip_proj_class* classes; /* host array                                        */
+  int32_t n_classes;       /* 1..255                                                    */
+  int32_t device;          /* CUDA device ordinal                                       */
+} dualip_csc_desc;
+
+typedef struct dualip_plan dualip_plan;
+
+/* Scalars of one evaluation, all double (reference ObjectiveResult, types.py:32-41). */
+typedef struct dualip_scalars {
+  double dual_objective;      /* c.x + reg_penalty + lambda.(Ax-b)   (matching.py:33)   */
+  double primal_objective;    /* c.x                                  (matching.py:160)  */
+  double reg_penalty;         /* gamma/2 * ||x||^2                    (matching.py:157)  */
+  double dual_val_times_grad; /* lambda.(Ax-b)                        (matching.py:167)  */
+  double max_pos_slack;       /* max(max(Ax-b),0)                     (matching.py:168)  */
+  double sum_pos_slack;       /* sum relu(Ax-b)                       (matching.py:169)  */
+  double x_sq_norm;           /* ||x||^2                                                  */
+  double grad_sq_norm;        /* ||Ax-b||^2                                               */
+} dualip_scalars;
+
+/* calc flags */
+#define DUALIP_CALC_DEFAULT 0u
+
+int dualip_abi_version(void);
+const char* dualip_last_error(void);
+
+/* Build the device-side pass table for a shard (setup time; synchronises).  Replaces
+ * MatchingSolverDualObjectiveFunction.__init__ / _compute_buckets (matching.py:43-114). */
+int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* desc);
+void dualip_plan_destroy(dualip_plan* plan);
+
+/* Introspection: fills up to `cap` int64 values:
+ * [0] n_passes [1] n_long_cols [2] n_ctas [3] threads/cta [4] smem bytes/cta [5] row index bits
+ * [6] smem mode (0: lambda+grad in smem, 1: grad in smem, 2: neither) [7] passes per run
+ * [8] kernel launches per calc  [9] plan-owned device bytes */
+int dualip_plan_info(const dualip_plan* plan, int64_t* out, int cap);
+
+/* One evaluation of the dual at lambda on this shard, epilogue included (single device).
+ * Replaces calculate() (matching.py:116-188).
+ *   lambda_dev  m floats.            b_dev  m floats, or NULL (treated as 0: "local shard" mode, matching.py:56)
+ *   grad_out_dev m floats  = A x*(lambda) - b
+ *   scalars_out_dev          one dualip_scalars (device memory)
+ *   x_out_dev   nnz floats or NULL (save_primal; CSC value order, matching.py:185-187)
+ *   diag_out_dev nnz bytes or NULL: at the FIRST entry of every simplex column, branch|rho<<2 with
+ *               branch 0=feasible 1=top-2 shortcut 2=Duchi (rho = support size, saturated at 63); tests only. */
+int dualip_matching_calc(dualip_plan* plan, const float* lambda_dev, const float* b_dev, double gamma,
+                         float* grad_out_dev, dualip_scalars* scalars_out_dev, float* x_out_dev,
+                         uint8_t* diag_out_dev, uint32_t flags, void* stream);
+
+/* Sharded evaluation, step 1: this shard's partial sums, packed for ONE all-reduce:
+ * partial_out_dev[0..m) = sum_j a_rj x_rj over local columns, [m] = c.x, [m+1] = ||x||^2  (m+2 floats).
+ * Replaces the local calculate() + three dist.reduce calls (matching.py:261-274). */
+int dualip_matching_partial(dualip_plan* plan, const float* lambda_dev, double gamma, float* partial_out_dev,
+                            float* x_out_dev, uint8_t* diag_out_dev, uint32_t flags, void* stream);
+
+/* Sharded evaluation, step 2 (after the all-reduce; identical on every rank): m-length tail.
+ * Replaces matching.py:280-299.  No plan needed. */
+int dualip_matching_epilogue(const float* partial_sum_dev, int32_t m, const float* lambda_dev, const float* b_dev,
+                             double gamma, float* grad_out_dev, dualip_scalars* scalars_out_dev, void* stream);
+
+/* Host-buffer convenience used for the end-to-end measurement: copies lambda (and nothing else)
+ * host->device, evaluates, copies grad and scalars device->host, synchronises the stream.
+ * b_dev stays device-resident (it is part of the problem, like A and c). */
+int dualip_matching_calc_host(dualip_plan* plan, const float* lambda_host, const float* b_dev, double gamma,
+                              float* grad_out_host, dualip_scalars* scalars_out_host, void* stream);
+
+/* ---- device-resident Maximizer state (reference optimizers/agd.py:121-229, agd_utils.py:4-89) ---- */
+typedef struct dualip_agd dualip_agd;
+
+/* Creates optimizer state for an m-vector on `device`: x = y = initial (device pointer, or NULL for zeros),
+ * 15-deep history ring (agd_utils.py:71). */
+int dualip_agd_create(dualip_agd** out, int32_t m, int32_t device, const float* initial_dev,
+                      const uint8_t* equality_mask_dev /* m bytes or NULL */, double initial_step_size,
+                      double max_step_size, int32_t history_len /* 15 */);
+void dualip_agd_destroy(dualip_agd* agd);
+/* Device pointer of the current evaluation point x (m floats) / last projected iterate y. */
+const float* dualip_agd_x(const dualip_agd* agd);
+const float* dualip_agd_y(const dualip_agd* agd);
+/* Copies x and/or y (m floats each) into caller buffers on the same device (either may be NULL). */
+int dualip_agd_get(dualip_agd* agd, float* x_out_dev, float* y_out_dev, void* stream);
+/* One accelerated step from grad (m floats) evaluated at x, with momentum beta_i (agd.py:93-100):
+ * step size from the Lipschitz history (agd_utils.py:65-89), y_new = proj(x + step*grad), x = y_new(1-beta)+y*beta.
+ * If decay_now != 0: afterwards max_step_size = step*decay_factor (agd.py:102-109; gamma itself is host state).
+ * Writes (dual_objective from scalars_dev, step) to log slot `iter_index` if 0 <= iter_index < capacity.  No host sync. */
+int dualip_agd_step(dualip_agd* agd, const float* grad_dev, const dualip_scalars* scalars_dev, float beta,
+                    int32_t decay_now, double decay_factor, int32_t iter_index, void* stream);
+/* Copies log entries [0,count) to host: dual_objective and step size per iteration. Synchronises. */
+int dualip_agd_read_log(dualip_agd* agd, int32_t count, double* dual_obj_host, double* step_host, void* stream);
+int dualip_agd_reserve_log(dualip_agd* agd, int32_t capacity);
+
+/* ---- setup-time helper kernels ---- */
+/* In-place Jacobi row scaling (reference preprocessing/precondition.py:8-29): norms_out[r] = ||A_r||_2,
+ * a[e] /= norms[row[e]], b[r] /= norms[r].  index_bits as above. Synchronises. */
+int dualip_jacobi_precondition(float* a_dev, const void* row_dev, int32_t index_bits, int64_t nnz, float* b_dev,
+                               int32_t m, float* norms_out_dev, int32_t device, void* stream);
+
+/* ProjectionOperator.__call__ on a zero-padded dense block x[L][K] (row-major, one column per entity), the
+ * contract of reference projections/base.py:30-36 as used by utils/sparse_utils.py:207-211.  out must not alias x. */
+int dualip_project_block(const float* x_dev, float* out_dev, int64_t L, int64_t K, const dualip_proj_class* cls,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUALIP_B200_H */
