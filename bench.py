@@ -1,0 +1,456 @@
+#!/usr/bin/env python
+"""Benchmark of the dual-ascent hot path.  One JSON line on stdout (rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repository's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the oracle port on all host threads
+
+Metric (BASELINE.json): dual-ascent iterations/sec on the synthetic matching LP with 100M entities x 10k duals
+(sparsity 1e-3, ~1e9 nonzeros), simplex(z=1) on even entities and box[0,1] on odd ones, Jacobi row preconditioning,
+Nesterov AGD with initial_step_size 1e-3 / max_step_size 1e-1, gamma 1e-3.  A "step" is one full iteration:
+evaluate the dual at lambda (fused kernel, + one all-reduce when sharded), then the accelerated update.
+With N GPUs the SAME 100M-entity problem is sharded by contiguous entity ranges (strong scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (entities, duals, sparsity, mixed projection map?, jacobi?)
+    "c3": (100_000_000, 10_000, 1e-3, True, True),
+    "c2": (1_000_000, 1_000, 1e-2, False, False),
+    "c3_small": (10_000_000, 10_000, 1e-3, True, True),
+    "tiny": (200_000, 1_000, 1e-2, True, True),
+}
+GAMMA = 1e-3
+INITIAL_STEP, MAX_STEP = 1e-3, 1e-1  # reference benchmark/config.py:17-18
+SEED = 42  # reference benchmark/config.py:12
+L2_BYTES = 126 * 1024 * 1024
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            f = [t.strip() for t in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def mixed_projection_map(n_local: int, col_start: int, device):
+    """simplex(z=1) on even global entities, box[0,1] on odd ones (our choice of mixed map)."""
+    import torch
+
+    from dualip_b200.projections import create_projection_map
+
+    first_even = (col_start % 2)  # local index of the first even global column
+    even = torch.arange(first_even, n_local, 2, device=device)
+    odd = torch.arange(1 - first_even, n_local, 2, device=device)
+    pm = {}
+    pm.update(create_projection_map("simplex", {"z": 1.0}, n_local, indices=even))
+    pm.update(create_projection_map("box", {"lower": 0.0, "upper": 1.0}, n_local, indices=odd))
+    return pm
+
+
+def build_problem(args, rank, world, device):
+    """Generates this rank's entity shard on its GPU and returns (objective, b, info)."""
+    import torch
+    import torch.distributed as dist
+
+    from benchmark.synthetic import capacity_vector, generate_shard
+    from dualip_b200.objectives.matching import (
+        MatchingInputArgs,
+        MatchingSolverDualObjectiveFunction,
+        MatchingSolverDualObjectiveFunctionDistributed,
+    )
+    from dualip_b200.preprocessing.precondition import jacobi_precondition
+    from dualip_b200.projections import create_projection_map
+    from dualip_b200.utils.dist_utils import shard_sizes
+
+    n, m, sparsity, mixed, jacobi = args.entities, args.duals, args.sparsity, args.mixed, args.jacobi
+    sizes = shard_sizes(n, world)
+    col_start = sum(sizes[:rank])
+    col_end = col_start + sizes[rank]
+    t0 = time.time()
+    shard = generate_shard(n, m, sparsity, SEED, device, col_start, col_end)
+    load = shard.greedy_load
+    if world > 1:
+        dist.all_reduce(load)
+    b = capacity_vector(load, m, sparsity, SEED, device)
+    n_local = col_end - col_start
+    A = torch.sparse_csc_tensor(shard.ccol, shard.row, shard.a, size=(m, n_local))
+    C = torch.sparse_csc_tensor(shard.ccol, shard.row, shard.c, size=(m, n_local))
+    if jacobi:
+        jacobi_precondition(A, b, sharded=True)  # global row norms (one all-reduce of m doubles when sharded)
+    pm = mixed_projection_map(n_local, col_start, device) if mixed else create_projection_map("simplex", {"z": 1.0}, n_local)
+    torch.cuda.synchronize(device)
+    t_gen = time.time() - t0
+    t0 = time.time()
+    if world == 1:
+        obj = MatchingSolverDualObjectiveFunction(MatchingInputArgs(A, C, pm, b), gamma=GAMMA)
+        local = obj
+    else:
+        obj = MatchingSolverDualObjectiveFunctionDistributed(MatchingInputArgs(A, C, pm, None), b, GAMMA, host_device=device)
+        local = obj.local_objective
+    torch.cuda.synchronize(device)
+    t_plan = time.time() - t0
+    nnz_local = local.nnz
+    nnz_total = torch.tensor([nnz_local], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(nnz_total)
+    info = dict(nnz_local=nnz_local, nnz_total=int(nnz_total.item()), n_local=n_local, gen_s=round(t_gen, 2),
+                plan_s=round(t_plan, 2), plan=local.plan_info(), col_start=col_start, col_end=col_end)
+    return obj, local, b, shard, info
+
+
+def cpu_baseline_port(shard, b, args, n_sample_cols, threads, repeats=3):
+    """Times the C restatement (oracle/matching_oracle.c, OpenMP) on a column sample of this workload."""
+    import numpy as np
+    import torch
+
+    from oracle import c_oracle
+
+    n_s = min(n_sample_cols, shard.ccol.numel() - 1)
+    e_s = int(shard.ccol[n_s].item())
+    ccol = shard.ccol[: n_s + 1].cpu().numpy()
+    row = shard.row[:e_s].cpu().numpy()
+    a = shard.a[:e_s].cpu().numpy()
+    c = shard.c[:e_s].cpu().numpy()
+    m = args.duals
+    if args.mixed:
+        classes = [c_oracle.make_class("simplex", {"z": 1.0}), c_oracle.make_class("box", {"lower": 0.0, "upper": 1.0})]
+        col_class = ((np.arange(n_s) + shard.col_start) % 2).astype(np.uint8)
+    else:
+        classes, col_class = [c_oracle.make_class("simplex", {"z": 1.0})], None
+    lam = np.zeros(m, dtype=np.float32)
+    bh = b.cpu().numpy()
+    c_oracle.calculate(ccol, row, a, c, m, classes, lam, GAMMA, bh, col_class, want_x=False, want_diag=False, threads=threads)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        r = c_oracle.calculate(ccol, row, a, c, m, classes, lam, GAMMA, bh, col_class, want_x=False, want_diag=False, threads=threads)
+        times.append(time.perf_counter() - t0)
+        lam = np.maximum(lam + np.float32(INITIAL_STEP) * r["grad"], 0).astype(np.float32)
+    return min(times), e_s, n_s
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    from dualip_b200.optimizers.agd import AcceleratedGradientDescent, FusedAscentLoop
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    if args.gpus != world:
+        log(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+
+    obj, local, b, shard, info = build_problem(args, rank, world, device)
+    if rank == 0:
+        log(f"[bench] problem ready: {info}")
+    K, W = args.steps, args.warmup
+    m = args.duals
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident loop: W warm-up + K timed iterations ----
+    solver = AcceleratedGradientDescent(max_iter=W + K, gamma=GAMMA, initial_step_size=INITIAL_STEP, max_step_size=MAX_STEP,
+                                        iteration_callback=lambda i, r: None)
+    loop = FusedAscentLoop(solver, obj, torch.zeros(m, dtype=torch.float32, device=device), rank)
+    for i in range(1, W + 1):
+        loop.step(i)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(W + 1, W + K + 1):
+        loop.step(i)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    result = loop.finish()
+    lam_now = loop.current_dual()
+    loop.close()
+    launches_per_step = info["plan"]["launches_per_calc"] + 1 + (1 if world > 1 else 0)
+
+    # ---- dominant kernel alone, for the roofline (CUDA events on the launching stream) ----
+    grad = torch.empty(m, dtype=torch.float32, device=device)
+    scal = torch.zeros(8, dtype=torch.float64, device=device)
+    part = torch.empty(m + 2, dtype=torch.float32, device=device)
+    reps = max(5, min(K, 50))
+
+    def kernel_once():
+        if world == 1:
+            local.launch_calc(lam_now.data_ptr(), GAMMA, grad.data_ptr(), scal.data_ptr())
+        else:
+            local.launch_partial(lam_now.data_ptr(), GAMMA, part.data_ptr())
+
+    for _ in range(3):
+        kernel_once()
+    torch.cuda.synchronize(device)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(reps):
+        kernel_once()
+    k1.record()
+    torch.cuda.synchronize(device)
+    kernel_ms = k0.elapsed_time(k1) / reps
+    b_alg = local.algorithmic_bytes()
+    peak, peak_src = measured_peak_gbs()
+    achieved = b_alg / (kernel_ms * 1e-3) / 1e9
+
+    # ---- end to end through the public API with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        Ke = max(3, min(K, args.e2e_steps))
+        host_solver = AcceleratedGradientDescent(max_iter=Ke + 3, gamma=GAMMA, initial_step_size=INITIAL_STEP,
+                                                 max_step_size=MAX_STEP, iteration_callback=lambda i, r: None)
+        lam_host = torch.zeros(m, dtype=torch.float32).pin_memory()
+        # warm-up of the host path (pinned staging buffers, first-touch)
+        obj.calculate(lam_host, gamma=GAMMA)
+        barrier()
+        t0 = time.perf_counter()
+        host_solver.max_iter = Ke
+        host_solver.beta_seq = host_solver._compute_beta_seq(Ke)
+        host_solver.maximize(obj, lam_host, rank=0 if world == 1 else rank)
+        torch.cuda.synchronize(device)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        h2d, d2h = obj.host_io_bytes()
+        e2e = {"value": Ke / dt, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": Ke, "path": "AcceleratedGradientDescent.maximize with a pinned host dual vector: per iteration lambda "
+               "host->device, fused kernel(s), grad+scalars device->host, host-side update"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import c_oracle
+
+        threads = c_oracle.max_threads()
+        t_s, e_s, n_s = cpu_baseline_port(shard, b, args, args.cpu_sample_cols, threads)
+        it_s = 1.0 / (t_s * info["nnz_total"] / max(e_s, 1))
+        cpu = {"value": it_s, "unit": "iterations/s", "cores": threads, "kind": "port",
+               "sample": f"first {n_s} entities ({e_s} nnz) of the workload, best of 3 evaluations of the dual with the C/OpenMP "
+                         f"restatement; {t_s:.3f} s per evaluation = {e_s / t_s / 1e6:.1f} M nnz/s, scaled by nnz to the full problem",
+               "nnz_per_s": e_s / t_s}
+
+    if rank == 0:
+        it_per_s = K / (ms_total * 1e-3)
+        line = {
+            "metric": "dual-ascent iterations/sec", "value": it_per_s, "unit": "iterations/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synthetic matching LP {args.entities} entities x {args.duals} duals, sparsity {args.sparsity}, "
+                                   f"{'simplex(z=1) even / box[0,1] odd' if args.mixed else 'simplex(z=1)'}, "
+                                   f"{'Jacobi precond, ' if args.jacobi else ''}Nesterov AGD, gamma={GAMMA}",
+                       "workload_id": args.workload, "entities": args.entities, "duals": args.duals, "nnz": info["nnz_total"],
+                       "parallelism": f"entity-sharded x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush between iterations" % (b_alg / 1e9)
+                       if b_alg > 2 * L2_BYTES else "inputs fit in L2: numbers are L2-resident, not a roofline claim",
+                       "index_dtype": "int64 inputs, uint16 row ids in the plan"},
+            "entities_x_constraints_per_s": args.entities * args.duals * it_per_s,
+            "nnz_per_s": info["nnz_total"] * it_per_s,
+            "gpu_launches": launches_per_step * K,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "matching_pass_kernel", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes": b_alg, "peak_source": peak_src,
+                         "note": "rank-0 shard" if world > 1 else "whole problem"},
+            "final_dual_objective": result.dual_objective,
+            "setup": {"generate_s": info["gen_s"], "plan_s": info["plan_s"], "plan": info["plan"]},
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """CPU arm: the oracle port (C/OpenMP restatement of the reference's algorithm) on all host threads.
+
+    The reference itself is pure Python/PyTorch and is not present on the GPU box (it cannot travel), so this arm
+    times oracle/matching_oracle.c.  Each step is one dual-ascent iteration (evaluate + numpy update) on a bounded
+    column sample of the same workload; `value` is scaled by nnz to the full problem."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+
+    from benchmark.synthetic import capacity_vector, generate_shard
+    from oracle import c_oracle
+    from oracle import dualip_oracle as O
+
+    n, m = args.entities, args.duals
+    n_s = min(args.cpu_sample_cols, n)
+    gen_device = "cuda" if torch.cuda.is_available() else "cpu"
+    shard = generate_shard(n, m, args.sparsity, SEED, gen_device, 0, n_s)
+    b = capacity_vector(shard.greedy_load * (n / n_s), m, args.sparsity, SEED, gen_device).cpu().numpy()
+    ccol, row = shard.ccol.cpu().numpy(), shard.row.cpu().numpy()
+    a, c = shard.a.cpu().numpy(), shard.c.cpu().numpy()
+    if args.jacobi:
+        a, b, _ = O.jacobi_precondition(a, row, b, m)
+        a = a.astype(np.float32)
+        b = b.astype(np.float32)
+    e_s = row.size
+    e_full = e_s * (n / n_s)
+    if args.mixed:
+        classes = [c_oracle.make_class("simplex", {"z": 1.0}), c_oracle.make_class("box", {"lower": 0.0, "upper": 1.0})]
+        col_class = (np.arange(n_s) % 2).astype(np.uint8)
+    else:
+        classes, col_class = [c_oracle.make_class("simplex", {"z": 1.0})], None
+    threads = c_oracle.max_threads()
+    K, W = args.steps, args.warmup
+
+    def calc(lam, gamma):
+        r = c_oracle.calculate(ccol, row, a, c, m, classes, lam, gamma, b, col_class, want_x=False, want_diag=False, threads=threads)
+        return r["grad"], r["scal"][0]
+
+    state = {"i": 0, "t0": None}
+
+    def timed_calc(lam, gamma):
+        if state["i"] == W:
+            state["t0"] = time.perf_counter()
+        state["i"] += 1
+        return calc(lam, gamma)
+
+    O.agd_maximize(timed_calc, np.zeros(m, dtype=np.float32), W + K, GAMMA, INITIAL_STEP, MAX_STEP)
+    dt = time.perf_counter() - state["t0"]
+    it_s_sample = K / dt
+    it_s_full = it_s_sample * (e_s / e_full)
+    line = {
+        "impl": "reference", "metric": "dual-ascent iterations/sec", "value": it_s_full, "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 / it_s_full, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"synthetic matching LP {n} entities x {m} duals, sparsity {args.sparsity}", "workload_id": args.workload,
+                   "entities": n, "duals": m},
+        "cpu_baseline": {"value": it_s_full, "unit": "iterations/s", "cores": threads, "kind": "port",
+                         "sample": f"first {n_s} of {n} entities ({e_s} nnz): {it_s_sample:.3f} it/s on the sample = "
+                                   f"{e_s * it_s_sample / 1e6:.1f} M nnz/s, scaled by nnz to the full problem"},
+        "e2e": {"value": it_s_full, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c3")
+    ap.add_argument("--entities", type=int, default=None)
+    ap.add_argument("--duals", type=int, default=None)
+    ap.add_argument("--sparsity", type=float, default=None)
+    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--cpu-sample-cols", type=int, default=4_000_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    n, m, sp, mixed, jac = WORKLOADS[args.workload]
+    args.entities = args.entities or n
+    args.duals = args.duals or m
+    args.sparsity = args.sparsity or sp
+    args.mixed, args.jacobi = mixed, jac
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

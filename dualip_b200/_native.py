@@ -62,6 +62,9 @@ SIGNATURES = {
                                   C.c_void_p]),
     "dualip_agd_read_log": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dualip_agd_reserve_log": (C.c_int, [C.c_void_p, C.c_int32]),
+    "dualip_row_sq_norms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                                      C.c_void_p]),
+    "dualip_scale_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "dualip_project_block": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ProjClass), C.c_void_p]),
     "dualip_jacobi_precondition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
                                              C.c_void_p, C.c_int32, C.c_void_p]),

@@ -1,6 +1,7 @@
 // Setup-time kernels: Jacobi row preconditioning (reference src/dualip/preprocessing/precondition.py:8-29,
 // utils/sparse_utils.py:429-450).  One pass to accumulate row norms, one pass to scale.
 #include <math.h>
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -74,6 +75,52 @@ extern "C" int dualip_jacobi_precondition(float* a_dev, const void* row_dev, int
   DUALIP_CUDA_TRY(cudaStreamSynchronize(st));
   cudaFree(sq);
   cudaFree(rec);
+  return DUALIP_OK;
+}
+
+// Sharded variant of the above: (1) local squared row norms, (2) caller all-reduces them, (3) scale with 1/norm.
+extern "C" int dualip_row_sq_norms(const float* a_dev, const void* row_dev, int32_t index_bits, int64_t nnz, int32_t m,
+                                   double* sq_out_dev, int32_t device, void* stream) {
+  if (!a_dev || !row_dev || !sq_out_dev || m <= 0 || nnz < 0 || (index_bits != 32 && index_bits != 64)) {
+    set_error("bad argument");
+    return DUALIP_EINVAL;
+  }
+  DeviceGuard g(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  DUALIP_CUDA_TRY(cudaMemsetAsync(sq_out_dev, 0, sizeof(double) * m, st));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int tb = 256;
+  const int nb = (int)std::max<int64_t>(1, std::min<int64_t>((nnz + tb - 1) / tb, (int64_t)sms * 16));
+  if (nnz > 0) {
+    if (index_bits == 64)
+      row_sq_norm_kernel<long long><<<nb, tb, 0, st>>>(a_dev, (const long long*)row_dev, nnz, sq_out_dev);
+    else
+      row_sq_norm_kernel<int><<<nb, tb, 0, st>>>(a_dev, (const int*)row_dev, nnz, sq_out_dev);
+  }
+  DUALIP_CUDA_TRY(cudaGetLastError());
+  return DUALIP_OK;
+}
+
+extern "C" int dualip_scale_rows(float* a_dev, const void* row_dev, int32_t index_bits, int64_t nnz,
+                                 const float* scale_dev, int32_t device, void* stream) {
+  if (!a_dev || !row_dev || !scale_dev || nnz < 0 || (index_bits != 32 && index_bits != 64)) {
+    set_error("bad argument");
+    return DUALIP_EINVAL;
+  }
+  DeviceGuard g(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int tb = 256;
+  const int nb = (int)std::max<int64_t>(1, std::min<int64_t>((nnz + tb - 1) / tb, (int64_t)sms * 16));
+  if (nnz > 0) {
+    if (index_bits == 64)
+      scale_rows_kernel<long long><<<nb, tb, 0, st>>>(a_dev, (const long long*)row_dev, nnz, scale_dev);
+    else
+      scale_rows_kernel<int><<<nb, tb, 0, st>>>(a_dev, (const int*)row_dev, nnz, scale_dev);
+  }
+  DUALIP_CUDA_TRY(cudaGetLastError());
   return DUALIP_OK;
 }
 

@@ -204,12 +204,37 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
             raise ValueError(f"dual_val has {dual_val.numel()} entries, expected {self.m}")
         return dual_val.contiguous()
 
+    def _calculate_host(self, dual_val: torch.Tensor) -> ObjectiveResult:
+        """Host-buffer evaluation through dualip_matching_calc_host: lambda is copied host->device from pinned memory,
+        grad and the scalars come back device->host, and the stream is synchronised before returning CPU tensors."""
+        if dual_val.dtype != torch.float32 or dual_val.numel() != self.m:
+            raise ValueError(f"dual_val must be float32 with {self.m} entries")
+        if not hasattr(self, "_h_lam"):
+            self._h_lam = torch.empty(self.m, dtype=torch.float32).pin_memory()
+            self._h_grad = torch.empty(self.m, dtype=torch.float32).pin_memory()
+            self._h_scal = torch.empty(len(_native.SCALAR_FIELDS), dtype=torch.float64).pin_memory()
+        self._h_lam.copy_(dual_val.reshape(-1))
+        with torch.cuda.device(self.device):
+            rc = _native.lib().dualip_matching_calc_host(
+                self._plan, self._h_lam.data_ptr(), self.b_vec.data_ptr() if self.b_vec is not None else None,
+                float(self.gamma), self._h_grad.data_ptr(), self._h_scal.data_ptr(), self._stream())
+        _native.check(rc, "dualip_matching_calc_host")
+        return _host_result(self._h_grad.clone(), self._h_scal.clone(), self.is_distributed)
+
+    def host_io_bytes(self) -> tuple:
+        """(host->device, device->host) bytes per host-buffer evaluation."""
+        return 4 * self.m, 4 * self.m + 8 * len(_native.SCALAR_FIELDS)
+
     # -- the reference-facing call -------------------------------------------------------------------------
     def calculate(self, dual_val: torch.Tensor, gamma: float = None, save_primal: bool = False, **kwargs) -> ObjectiveResult:
         """Same contract as reference matching.py:116-188.  `diagnostics=True` (extra keyword) additionally returns
         the per-column projection branch / support size as `result.projection_diag` (uint8 per nnz position)."""
         if gamma is not None and gamma != self.gamma:
             self.gamma = gamma  # no O(E) rescaling pass: the kernel forms -(a*lambda + c)/gamma in registers
+        if isinstance(dual_val, torch.Tensor) and dual_val.device.type == "cpu":
+            if save_primal or kwargs.get("diagnostics"):
+                raise ValueError("save_primal / diagnostics need a device-resident dual_val")
+            return self._calculate_host(dual_val)
         lam = self._check_dual(dual_val)
         with torch.cuda.device(self.device):
             grad = torch.empty(self.m, dtype=torch.float32, device=self.device)
@@ -246,6 +271,24 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
         return res
 
 
+def _host_result(grad: torch.Tensor, scal: torch.Tensor, local_mode: bool) -> ObjectiveResult:
+    s32 = scal.to(torch.float32)
+    if local_mode:
+        res = ObjectiveResult(dual_gradient=grad, dual_objective=s32[_IDX["primal_objective"]],
+                              reg_penalty=s32[_IDX["reg_penalty"]])
+    else:
+        res = ObjectiveResult(
+            dual_gradient=grad,
+            dual_objective=s32[_IDX["dual_objective"]],
+            reg_penalty=s32[_IDX["reg_penalty"]],
+            dual_val_times_grad=s32[_IDX["dual_val_times_grad"]],
+            max_pos_slack=s32[_IDX["max_pos_slack"]],
+            sum_pos_slack=s32[_IDX["sum_pos_slack"]],
+        )
+    res.scalars64 = scal
+    return res
+
+
 def reduce_partials(partial: torch.Tensor) -> torch.Tensor:
     """The one collective of the sharded path: SUM all-reduce of the packed [grad(m) | c.x | ||x||^2] vector
     (replaces three dist.reduce + barrier, reference matching.py:272-277).  No-op without a process group."""
@@ -276,6 +319,9 @@ class MatchingSolverDualObjectiveFunctionDistributed(BaseObjective):
         self.m = self.local_objective.m
         self.b_vec = b_vec.to(device=self.device, dtype=torch.float32).contiguous()
 
+    def host_io_bytes(self) -> tuple:
+        return 4 * self.m, 4 * self.m + 8 * len(_native.SCALAR_FIELDS)
+
     def launch_partial_and_reduce(self, lam_ptr: int, gamma: float, partial: torch.Tensor) -> None:
         self.local_objective.launch_partial(lam_ptr, gamma, partial.data_ptr())
         reduce_partials(partial)
@@ -291,6 +337,16 @@ class MatchingSolverDualObjectiveFunctionDistributed(BaseObjective):
         if gamma is not None and gamma != self.gamma:
             self.gamma = gamma
             self.local_objective.gamma = gamma
+        host_io = isinstance(dual_val, torch.Tensor) and dual_val.device.type == "cpu"
+        if host_io:
+            if not hasattr(self, "_h_lam"):
+                self._h_lam = torch.empty(self.m, dtype=torch.float32).pin_memory()
+                self._h_grad = torch.empty(self.m, dtype=torch.float32).pin_memory()
+                self._h_scal = torch.empty(len(_native.SCALAR_FIELDS), dtype=torch.float64).pin_memory()
+                self._d_lam = torch.empty(self.m, dtype=torch.float32, device=self.device)
+            self._h_lam.copy_(dual_val.reshape(-1))
+            self._d_lam.copy_(self._h_lam, non_blocking=True)
+            dual_val = self._d_lam
         lam = self.local_objective._check_dual(dual_val)
         with torch.cuda.device(self.device):
             partial = torch.empty(self.m + 2, dtype=torch.float32, device=self.device)
@@ -298,6 +354,11 @@ class MatchingSolverDualObjectiveFunctionDistributed(BaseObjective):
             scal = torch.empty(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=self.device)
             self.launch_partial_and_reduce(lam.data_ptr(), self.gamma, partial)
             self.launch_epilogue(partial.data_ptr(), lam.data_ptr(), self.gamma, grad.data_ptr(), scal.data_ptr())
+            if host_io:
+                self._h_grad.copy_(grad, non_blocking=True)
+                self._h_scal.copy_(scal, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                return _host_result(self._h_grad.clone(), self._h_scal.clone(), False)
             s32 = scal.to(torch.float32)
         res = ObjectiveResult(
             dual_gradient=grad,

@@ -95,6 +95,9 @@ class AcceleratedGradientDescent:
             self.gamma = self.gamma * factor
             self.max_step_size = step_size * factor
 
+    def _user_callback_active(self) -> bool:
+        return True
+
     def _default_iteration_callback(self, iteration: int, objective_result: ObjectiveResult) -> None:
         try:
             print(format_objective_result_summary(iteration, objective_result))
@@ -124,77 +127,13 @@ class AcceleratedGradientDescent:
 
     # -- fused device-resident loop ------------------------------------------------------------------------
     def _maximize_fused(self, f, initial_value: torch.Tensor, rank: int) -> SolverResult:
-        from dualip_b200.objectives.matching import MatchingSolverDualObjectiveFunctionDistributed
-
-        lib = _native.lib()
-        device = initial_value.device
-        m = initial_value.numel()
-        sharded = isinstance(f, MatchingSolverDualObjectiveFunctionDistributed)
-        if self.save_primal and sharded:
-            raise NotImplementedError("save_primal=True is not yet supported in distributed mode")
-        eq = f.equality_mask
-        eq_u8 = eq.to(device=device, dtype=torch.uint8).contiguous() if eq is not None else None
-        init = initial_value.detach().contiguous()
-        beta = self.beta_seq.tolist()
-        decay = self.gamma is not None and self.gamma_decay_type is not None
-        if decay and self.gamma_decay_type != "step":
-            raise ValueError(f"Unsupported gamma decay type: {self.gamma_decay_type}")
-        with torch.cuda.device(device):
-            stream = torch.cuda.current_stream(device).cuda_stream
-            handle = ctypes.c_void_p()
-            torch.cuda.synchronize(device)
-            _native.check(lib.dualip_agd_create(ctypes.byref(handle), m, device.index, init.data_ptr(),
-                                                eq_u8.data_ptr() if eq_u8 is not None else None,
-                                                float(self.initial_step_size), float(self.max_step_size), 15),
-                          "dualip_agd_create")
-            try:
-                _native.check(lib.dualip_agd_reserve_log(handle, max(self.max_iter, 1)))
-                x_ptr = lib.dualip_agd_x(handle)
-                grad = torch.empty(m, dtype=torch.float32, device=device)
-                scal = torch.zeros(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=device)
-                partial = torch.empty(m + 2, dtype=torch.float32, device=device) if sharded else None
-                primal = None
-                for i in range(1, self.max_iter + 1):
-                    gamma_i = self.gamma if self.gamma is not None else f.gamma
-                    f.gamma = gamma_i
-                    last_primal = i == self.max_iter and self.save_primal
-                    if sharded:
-                        f.local_objective.gamma = gamma_i
-                        f.launch_partial_and_reduce(x_ptr, gamma_i, partial)
-                        f.launch_epilogue(partial.data_ptr(), x_ptr, gamma_i, grad.data_ptr(), scal.data_ptr())
-                    else:
-                        if last_primal:
-                            primal = torch.empty(f.nnz, dtype=torch.float32, device=device)
-                        f.launch_calc(x_ptr, gamma_i, grad.data_ptr(), scal.data_ptr(),
-                                      primal.data_ptr() if last_primal else None)
-                    if rank == 0:
-                        self.iteration_callback(i, self._view_result(grad, scal, primal if last_primal else None))
-                    decay_now, factor = 0, 1.0
-                    if decay and i % self.gamma_decay_params["decay_steps"] == 0:
-                        decay_now, factor = 1, float(self.gamma_decay_params["decay_factor"])
-                        self.gamma = self.gamma * factor
-                    _native.check(lib.dualip_agd_step(handle, grad.data_ptr(), scal.data_ptr(), float(beta[i - 1]),
-                                                      decay_now, factor, i - 1, stream), "dualip_agd_step")
-                n = self.max_iter
-                obj_log = (ctypes.c_double * max(n, 1))()
-                step_log = (ctypes.c_double * max(n, 1))()
-                _native.check(lib.dualip_agd_read_log(handle, n, obj_log, step_log, stream), "dualip_agd_read_log")
-                y = torch.empty(m, dtype=torch.float32, device=device)
-                _native.check(lib.dualip_agd_get(handle, None, y.data_ptr(), stream))
-                torch.cuda.synchronize(device)
-            finally:
-                lib.dualip_agd_destroy(handle)
-        dual_obj_log = [float(v) for v in obj_log[:n]]
-        step_size_log = [float(v) for v in step_log[:n]]
-        if decay and step_size_log:
-            # host mirror of the device-side cap (agd.py:107), for callers that inspect the optimizer afterwards
-            steps = self.gamma_decay_params["decay_steps"]
-            k = (n // steps) * steps
-            if k >= 1:
-                self.max_step_size = step_size_log[k - 1] * self.gamma_decay_params["decay_factor"]
-        final = self._view_result(grad, scal, primal, as_float32=True)
-        return SolverResult(dual_val=y, dual_objective=dual_obj_log[-1] if dual_obj_log else 0.0, objective_result=final,
-                            dual_objective_log=dual_obj_log, step_size_log=step_size_log)
+        loop = FusedAscentLoop(self, f, initial_value, rank)
+        try:
+            for i in range(1, self.max_iter + 1):
+                loop.step(i)
+            return loop.finish()
+        finally:
+            loop.close()
 
     @staticmethod
     def _view_result(grad, scal, primal, as_float32: bool = False) -> ObjectiveResult:
@@ -250,3 +189,103 @@ class AcceleratedGradientDescent:
                                 dual_objective_log=dual_obj_log, step_size_log=step_size_log)
         return SolverResult(dual_val=y, dual_objective=0.0, objective_result=objective_result, dual_objective_log=[],
                             step_size_log=[])
+
+
+class FusedAscentLoop:
+    """Device-resident state of one `maximize` call on a CUDA matching objective.
+
+    `step(i)` enqueues iteration i (1-based) on the current stream: the objective's kernel(s) at the evaluation point
+    x held by the native optimizer state, then dualip_agd_step.  Nothing synchronises until `finish()`.  bench.py
+    drives this class directly so that it can bracket exactly K iterations with CUDA events."""
+
+    def __init__(self, solver: AcceleratedGradientDescent, f, initial_value: torch.Tensor, rank: int = 0):
+        from dualip_b200.objectives.matching import MatchingSolverDualObjectiveFunctionDistributed
+
+        self.solver, self.f, self.rank = solver, f, rank
+        self.lib = _native.lib()
+        self.device = initial_value.device
+        self.m = initial_value.numel()
+        self.sharded = isinstance(f, MatchingSolverDualObjectiveFunctionDistributed)
+        if solver.save_primal and self.sharded:
+            raise NotImplementedError("save_primal=True is not yet supported in distributed mode")
+        self.decay = solver.gamma is not None and solver.gamma_decay_type is not None
+        if self.decay and solver.gamma_decay_type != "step":
+            raise ValueError(f"Unsupported gamma decay type: {solver.gamma_decay_type}")
+        eq = f.equality_mask
+        self._eq_u8 = eq.to(device=self.device, dtype=torch.uint8).contiguous() if eq is not None else None
+        init = initial_value.detach().contiguous()
+        self.beta = solver.beta_seq.tolist()
+        self.handle = ctypes.c_void_p()
+        self.steps_done = 0
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            _native.check(self.lib.dualip_agd_create(
+                ctypes.byref(self.handle), self.m, self.device.index, init.data_ptr(),
+                self._eq_u8.data_ptr() if self._eq_u8 is not None else None, float(solver.initial_step_size),
+                float(solver.max_step_size), 15), "dualip_agd_create")
+            _native.check(self.lib.dualip_agd_reserve_log(self.handle, max(solver.max_iter, 1)))
+            self.x_ptr = self.lib.dualip_agd_x(self.handle)
+            self.grad = torch.empty(self.m, dtype=torch.float32, device=self.device)
+            self.scal = torch.zeros(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=self.device)
+            self.partial = torch.empty(self.m + 2, dtype=torch.float32, device=self.device) if self.sharded else None
+        self.primal = None
+
+    def step(self, i: int) -> None:
+        solver, f = self.solver, self.f
+        gamma_i = solver.gamma if solver.gamma is not None else f.gamma
+        f.gamma = gamma_i
+        last_primal = i == solver.max_iter and solver.save_primal
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            if self.sharded:
+                f.local_objective.gamma = gamma_i
+                f.launch_partial_and_reduce(self.x_ptr, gamma_i, self.partial)
+                f.launch_epilogue(self.partial.data_ptr(), self.x_ptr, gamma_i, self.grad.data_ptr(), self.scal.data_ptr())
+            else:
+                if last_primal:
+                    self.primal = torch.empty(f.nnz, dtype=torch.float32, device=self.device)
+                f.launch_calc(self.x_ptr, gamma_i, self.grad.data_ptr(), self.scal.data_ptr(),
+                              self.primal.data_ptr() if last_primal else None)
+            if self.rank == 0 and solver._user_callback_active():
+                solver.iteration_callback(i, solver._view_result(self.grad, self.scal, self.primal if last_primal else None))
+            decay_now, factor = 0, 1.0
+            if self.decay and i % solver.gamma_decay_params["decay_steps"] == 0:
+                decay_now, factor = 1, float(solver.gamma_decay_params["decay_factor"])
+                solver.gamma = solver.gamma * factor
+            _native.check(self.lib.dualip_agd_step(self.handle, self.grad.data_ptr(), self.scal.data_ptr(),
+                                                   float(self.beta[i - 1]), decay_now, factor, i - 1, stream),
+                          "dualip_agd_step")
+        self.steps_done = max(self.steps_done, i)
+
+    def current_dual(self) -> torch.Tensor:
+        y = torch.empty(self.m, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.dualip_agd_get(self.handle, None, y.data_ptr(),
+                                                  torch.cuda.current_stream(self.device).cuda_stream))
+        return y
+
+    def finish(self) -> SolverResult:
+        solver, n = self.solver, self.steps_done
+        obj_log = (ctypes.c_double * max(n, 1))()
+        step_log = (ctypes.c_double * max(n, 1))()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _native.check(self.lib.dualip_agd_read_log(self.handle, n, obj_log, step_log, stream), "dualip_agd_read_log")
+            y = self.current_dual()
+            torch.cuda.synchronize(self.device)
+        dual_obj_log = [float(v) for v in obj_log[:n]]
+        step_size_log = [float(v) for v in step_log[:n]]
+        if self.decay and step_size_log:
+            # host mirror of the device-side step cap (agd.py:107), for callers that inspect the optimizer afterwards
+            steps = solver.gamma_decay_params["decay_steps"]
+            k = (n // steps) * steps
+            if k >= 1:
+                solver.max_step_size = step_size_log[k - 1] * solver.gamma_decay_params["decay_factor"]
+        final = solver._view_result(self.grad, self.scal, self.primal, as_float32=True)
+        return SolverResult(dual_val=y, dual_objective=dual_obj_log[-1] if dual_obj_log else 0.0, objective_result=final,
+                            dual_objective_log=dual_obj_log, step_size_log=step_size_log)
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.dualip_agd_destroy(self.handle)
+            self.handle = ctypes.c_void_p()

@@ -7,8 +7,11 @@ import torch
 from dualip_b200 import _native
 
 
-def jacobi_precondition(A: torch.Tensor, b: torch.Tensor, norms_save_path: str = None):
-    """A <- diag(1/||A_r||_2) A and b <- b/||A_r||_2 in place; returns the row norms."""
+def jacobi_precondition(A: torch.Tensor, b: torch.Tensor, norms_save_path: str = None, sharded: bool = False):
+    """A <- diag(1/||A_r||_2) A and b <- b/||A_r||_2 in place; returns the row norms.
+
+    sharded=True: A is this rank's column shard; squared row norms are summed over the process group first, so
+    every rank scales with the norms of the full matrix (b is replicated and scaled identically everywhere)."""
     if A.layout != torch.sparse_csc:
         raise ValueError("Expected M to be a CSC-format sparse tensor")
     vals, row = A.values(), A.row_indices()
@@ -19,6 +22,25 @@ def jacobi_precondition(A: torch.Tensor, b: torch.Tensor, norms_save_path: str =
     if not vals.is_contiguous() or not b.is_contiguous():
         raise ValueError("A.values() and b must be contiguous for in-place scaling")
     m = int(A.shape[0])
+    if sharded:
+        import torch.distributed as dist
+
+        bits = 32 if row.dtype == torch.int32 else 64
+        sq = torch.empty(m, dtype=torch.float64, device=vals.device)
+        with torch.cuda.device(vals.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _native.check(_native.lib().dualip_row_sq_norms(vals.data_ptr(), row.data_ptr(), bits, vals.numel(), m,
+                                                            sq.data_ptr(), vals.device.index, stream))
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(sq)
+            norms = sq.to(torch.float32).sqrt()
+            rec = 1 / norms
+            _native.check(_native.lib().dualip_scale_rows(vals.data_ptr(), row.data_ptr(), bits, vals.numel(),
+                                                          rec.data_ptr(), vals.device.index, stream))
+            b.mul_(rec)
+        if norms_save_path:
+            torch.save(norms, Path(norms_save_path))
+        return norms
     norms = torch.empty(m, dtype=torch.float32, device=vals.device)
     with torch.cuda.device(vals.device):
         rc = _native.lib().dualip_jacobi_precondition(

@@ -160,6 +160,13 @@ int dualip_agd_reserve_log(dualip_agd* agd, int32_t capacity);
 int dualip_jacobi_precondition(float* a_dev, const void* row_dev, int32_t index_bits, int64_t nnz, float* b_dev,
                                int32_t m, float* norms_out_dev, int32_t device, void* stream);
 
+/* Sharded Jacobi scaling: local squared row norms (double, m), to be all-reduced by the caller, then
+ * a[e] *= scale[row[e]] with scale = 1/sqrt(sum).  Asynchronous on `stream`. */
+int dualip_row_sq_norms(const float* a_dev, const void* row_dev, int32_t index_bits, int64_t nnz, int32_t m,
+                        double* sq_out_dev, int32_t device, void* stream);
+int dualip_scale_rows(float* a_dev, const void* row_dev, int32_t index_bits, int64_t nnz, const float* scale_dev,
+                      int32_t device, void* stream);
+
 /* ProjectionOperator.__call__ on a zero-padded dense block x[L][K] (row-major, one column per entity), the
  * contract of reference projections/base.py:30-36 as used by utils/sparse_utils.py:207-211.  out must not alias x. */
 int dualip_project_block(const float* x_dev, float* out_dev, int64_t L, int64_t K, const dualip_proj_class* cls,
