@@ -1,22 +1,25 @@
 // Fused dual-ascent evaluation for block-structured matching LPs on sm_100a.
 //
-// One launch of matching_pass_kernel replaces the ~15 eager ATen passes of the reference's
+// One launch of matching_slab_kernel replaces the ~15 eager ATen passes of the reference's
 // MatchingSolverDualObjectiveFunction.calculate (reference src/dualip/objectives/matching.py:116-188):
 //   v = a*(-lambda[row]/gamma) + (-c/gamma)        matching.py:136-142, utils/sparse_utils.py:54-85,26-51
 //   x = Proj_column(v)                              sparse_utils.py:133-220 -> projections/{box,cone,simplex}.py
 //   grad[row] += a*x ; cx += c*x ; xx += x*x        matching.py:153-160, sparse_utils.py:223-243
 //   grad -= b ; dual_obj = cx + gamma/2*xx + lambda.grad ; slacks      matching.py:25-34,164-178
 //
-// Layout ("pass table"): the nonzeros of consecutive short columns (1..32 entries) are packed greedily
-// into passes of <= 32 nonzeros that begin and end on column boundaries.  A warp handles one pass with
-// one lane per nonzero: loads of a, c, row are fully coalesced, every per-column reduction is a
-// segmented warp scan, and nothing per nonzero ever touches shared memory except the lambda gather
-// and the gradient scatter.  ccol is never read by the hot kernel: a pass entry is
-// {first nnz, end-of-column bit mask}.  Columns with more than 32 entries go to a warp-per-column kernel.
-#include <cub/device/device_scan.cuh>
+// HBM layout ("slabs", a sliced-ELL format sorted by projection class and column length): at plan time the
+// columns are stably sorted by (class, nnz) and cut into slabs of 32 columns of EQUAL length d; a slab stores
+// its values transposed, a_t[(off + k)*32 + lane] = k-th entry of column `lane`.  A warp owns a slab and a lane
+// owns a column: every load of a, c, row is one fully coalesced 128-byte (64-byte for uint16 rows) request, all
+// per-column reductions are plain sequential register arithmetic (no shuffles), and lanes never diverge on
+// column length or projection type.  The only shared-memory traffic per nonzero is the lambda gather and the
+// gradient scatter.  Columns longer than kMaxThreadDeg go to a warp-per-column kernel.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
 #include <algorithm>
 #include <new>
 #include <type_traits>
+#include <vector>
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -36,27 +39,27 @@ void set_error(const char* fmt, ...) {
   g_last_error = buf;
 }
 
-constexpr int kPassWidth = 32;        // nonzeros per pass = lanes per warp
-constexpr int kChunkCols = 2048;      // columns walked by one builder thread; passes never straddle chunks
-constexpr int kPrefetch = 4;          // passes in flight per warp
+constexpr int kSlabW = 32;            // columns per slab = lanes per warp
+constexpr int kMaxThreadDeg = 1024;   // longest column handled one-lane-per-column
+constexpr int kDegBits = 11;          // key = class << kDegBits | degree
+constexpr uint32_t kKeyEmpty = (255u << kDegBits) | 2047u;
+constexpr uint32_t kKeyLong = (255u << kDegBits) | 2046u;
+constexpr int kKeyBits = 19;
 constexpr int kMaxClasses = 255;
 constexpr size_t kSmemBudget = 227 * 1024;
 
-struct LongCol {
-  int64_t start;
-  int32_t len;
-  int32_t cls;
+struct SlabHdr {      // 8 bytes per slab (per 32*d nonzeros)
+  uint32_t off32;     // first row of the slab in units of 32 elements
+  uint16_t d;         // entries per column
+  uint8_t cls;        // projection class
+  uint8_t ncols;      // active lanes (32 except in the last slab of a (class, d) group)
 };
 
-struct PassEntryU {  // uniform projection map: 8 bytes / pass
-  uint32_t start;
-  uint32_t endmask;
-};
-struct PassEntryC {  // mixed projection map: 16 bytes / pass
-  uint32_t start;
-  uint32_t endmask;
-  uint32_t colbase;  // ordinal (among non-empty short columns) of the pass's first column
-  uint32_t pad;
+struct LongCol {
+  int64_t src_start;  // position of the column's first entry in the caller's CSC value order
+  int64_t off;        // offset into the plan's compact long-column arrays
+  int32_t len;
+  int32_t cls;
 };
 
 }  // namespace dualip
@@ -67,18 +70,22 @@ struct dualip_plan {
   int device = 0;
   int64_t n_cols = 0, nnz = 0;
   int32_t m = 0;
-  const float* a = nullptr;  // borrowed
-  const float* c = nullptr;  // borrowed
-  void* row = nullptr;       // owned, narrowed
   int row_bits = 32;
-  bool uniform = true;
-  void* entries = nullptr;   // PassEntryU[] or PassEntryC[], padded with empty passes
-  int64_t n_passes = 0;      // real passes
-  int64_t n_runs = 0;
-  int run_len = 32;
-  uint8_t* cls_ne = nullptr;  // class id per non-empty short column (mixed maps only)
+  // slabs (owned)
+  float* a_t = nullptr;
+  float* c_t = nullptr;
+  void* row_t = nullptr;
+  SlabHdr* hdr = nullptr;
+  int64_t* orig_start = nullptr;  // per slab lane: first nnz position of the column in the caller's order, or -1
+  int64_t n_slabs = 0;
+  int64_t rows32 = 0;             // total slab rows (32 elements each)
+  int64_t n_short = 0;            // columns stored in slabs
+  // long columns (owned, compact copies)
   LongCol* longcols = nullptr;
   int64_t n_long = 0;
+  float* long_a = nullptr;
+  float* long_c = nullptr;
+  uint32_t* long_row = nullptr;
   dualip_proj_class classes_host[kMaxClasses];
   dualip_proj_class* classes_dev = nullptr;
   int n_classes = 0;
@@ -99,88 +106,109 @@ namespace dualip {
 // ------------------------------------------------------------------------------------------
 // Plan construction (setup time)
 // ------------------------------------------------------------------------------------------
-template <typename IdxT, typename OutT>
-__global__ void narrow_rows_kernel(const IdxT* __restrict__ in, OutT* __restrict__ out, int64_t n, int32_t m,
+template <typename IdxT>
+__global__ void column_keys_kernel(const IdxT* __restrict__ ccol, const uint8_t* __restrict__ col_class, int64_t n_cols,
+                                   int n_classes, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                    unsigned int* bad) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    IdxT v = in[i];
-    if (v < 0 || v >= (IdxT)m) atomicOr(bad, 1u);
-    out[i] = (OutT)v;
+  for (; j < n_cols; j += stride) {
+    const int64_t d = (int64_t)ccol[j + 1] - (int64_t)ccol[j];
+    const uint32_t cls = col_class ? col_class[j] : 0u;
+    if (d < 0) atomicOr(bad, 2u);
+    if (d > 0x7fffffffLL) atomicOr(bad, 4u);
+    if ((int)cls >= n_classes) atomicOr(bad, 8u);
+    uint32_t key;
+    if (d <= 0)
+      key = kKeyEmpty;
+    else if (d > kMaxThreadDeg)
+      key = kKeyLong;
+    else
+      key = (cls << kDegBits) | (uint32_t)d;
+    keys[j] = key;
+    vals[j] = (uint32_t)j;
   }
 }
 
-// Walks one chunk of columns and either counts or emits passes / long columns / class ids.
-template <typename IdxT, bool EMIT, bool UNIFORM>
-__global__ void build_passes_kernel(const IdxT* __restrict__ ccol, const uint8_t* __restrict__ col_class, int64_t n_cols,
-                                    int64_t n_chunks, unsigned long long* __restrict__ counts /* 3*n_chunks */,
-                                    const unsigned long long* __restrict__ offsets /* 3*n_chunks */, void* entries,
-                                    uint8_t* cls_ne, LongCol* longcols, unsigned int* bad) {
-  const int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (chunk >= n_chunks) return;
-  const int64_t j0 = chunk * kChunkCols;
-  const int64_t j1 = min(j0 + (int64_t)kChunkCols, n_cols);
-  unsigned long long n_pass = 0, n_ne = 0, n_long = 0;
-  unsigned long long o_pass = 0, o_ne = 0, o_long = 0;
-  if (EMIT) {
-    o_pass = offsets[3 * chunk + 0];
-    o_ne = offsets[3 * chunk + 1];
-    o_long = offsets[3 * chunk + 2];
+// One thread per short column (in sorted order): copies the column into its slab lane.
+template <typename IdxT, typename RowT>
+__global__ void fill_slabs_kernel(const IdxT* __restrict__ ccol, const IdxT* __restrict__ row, const float* __restrict__ a,
+                                  const float* __restrict__ c, const uint32_t* __restrict__ perm, int64_t n_short,
+                                  const int64_t* __restrict__ g_start, const int64_t* __restrict__ g_slab_base,
+                                  const int64_t* __restrict__ g_off32, const uint32_t* __restrict__ g_key, int n_groups,
+                                  float* __restrict__ a_t, float* __restrict__ c_t, RowT* __restrict__ row_t,
+                                  SlabHdr* __restrict__ hdr, int64_t* __restrict__ orig_start, int32_t m,
+                                  unsigned int* bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_short) return;
+  int lo = 0, hi = n_groups - 1;  // largest g with g_start[g] <= i
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (g_start[mid] <= i)
+      lo = mid;
+    else
+      hi = mid - 1;
   }
-  int cur = 0;  // nonzeros in the open pass
-  uint32_t endmask = 0;
-  int64_t pass_start = 0;
-  unsigned long long pass_colbase = 0;
-  IdxT lo = ccol[j0];
-  auto close_pass = [&]() {
-    if (cur == 0) return;
-    if (EMIT) {
-      if (UNIFORM) {
-        PassEntryU e{(uint32_t)pass_start, endmask};
-        reinterpret_cast<PassEntryU*>(entries)[o_pass + n_pass] = e;
-      } else {
-        PassEntryC e{(uint32_t)pass_start, endmask, (uint32_t)pass_colbase, 0u};
-        reinterpret_cast<PassEntryC*>(entries)[o_pass + n_pass] = e;
-      }
-    }
-    ++n_pass;
-    cur = 0;
-    endmask = 0;
-  };
-  for (int64_t j = j0; j < j1; ++j) {
-    const IdxT hi = ccol[j + 1];
-    const int64_t d = (int64_t)hi - (int64_t)lo;
-    if (d < 0) atomicOr(bad, 2u);
-    if (d > kPassWidth) {
-      close_pass();
-      if (EMIT) {
-        LongCol lc;
-        lc.start = (int64_t)lo;
-        lc.len = (int32_t)d;
-        lc.cls = col_class ? (int32_t)col_class[j] : 0;
-        longcols[o_long + n_long] = lc;
-      }
-      if (d > 0x7fffffffLL) atomicOr(bad, 4u);
-      ++n_long;
-    } else if (d > 0) {
-      if (cur + (int)d > kPassWidth) close_pass();
-      if (cur == 0) {
-        pass_start = (int64_t)lo;
-        pass_colbase = o_ne + n_ne;
-      }
-      cur += (int)d;
-      endmask |= 1u << (cur - 1);
-      if (EMIT && !UNIFORM) cls_ne[o_ne + n_ne] = col_class[j];
-      ++n_ne;
-    }
-    lo = hi;
+  const int g = lo;
+  const uint32_t key = g_key[g];
+  const int d = (int)(key & ((1u << kDegBits) - 1));
+  const int64_t rel = i - g_start[g];
+  const int64_t slab = g_slab_base[g] + rel / kSlabW;
+  const int lane = (int)(rel % kSlabW);
+  const int64_t off32 = g_off32[g] + (rel / kSlabW) * d;
+  const uint32_t col = perm[i];
+  const int64_t e0 = (int64_t)ccol[col];
+  for (int k = 0; k < d; ++k) {
+    const int64_t dst = (off32 + k) * kSlabW + lane;
+    const IdxT r = row[e0 + k];
+    if (r < 0 || r >= (IdxT)m) atomicOr(bad, 1u);
+    a_t[dst] = a[e0 + k];
+    c_t[dst] = c[e0 + k];
+    row_t[dst] = (RowT)r;
   }
-  close_pass();
-  if (!EMIT) {
-    counts[3 * chunk + 0] = n_pass;
-    counts[3 * chunk + 1] = n_ne;
-    counts[3 * chunk + 2] = n_long;
+  orig_start[slab * kSlabW + lane] = e0;
+  if (lane == 0) {
+    const int64_t g_count = (g + 1 < n_groups ? g_start[g + 1] : n_short) - g_start[g];
+    const int64_t left = g_count - (rel / kSlabW) * kSlabW;
+    SlabHdr h;
+    h.off32 = (uint32_t)off32;
+    h.d = (uint16_t)d;
+    h.cls = (uint8_t)(key >> kDegBits);
+    h.ncols = (uint8_t)(left < kSlabW ? left : kSlabW);
+    hdr[slab] = h;
+  }
+}
+
+template <typename IdxT>
+__global__ void long_meta_kernel(const IdxT* __restrict__ ccol, const uint8_t* __restrict__ col_class,
+                                 const uint32_t* __restrict__ perm_long, int64_t n_long, LongCol* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_long) return;
+  const uint32_t col = perm_long[i];
+  LongCol lc;
+  lc.src_start = (int64_t)ccol[col];
+  lc.off = 0;
+  lc.len = (int32_t)((int64_t)ccol[col + 1] - (int64_t)ccol[col]);
+  lc.cls = col_class ? (int32_t)col_class[col] : 0;
+  out[i] = lc;
+}
+
+template <typename IdxT>
+__global__ void long_copy_kernel(const LongCol* __restrict__ cols, int64_t n_long, const IdxT* __restrict__ row,
+                                 const float* __restrict__ a, const float* __restrict__ c, float* __restrict__ la,
+                                 float* __restrict__ lcv, uint32_t* __restrict__ lrow, int32_t m, unsigned int* bad) {
+  const int lane = threadIdx.x & 31;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (; w < n_long; w += nw) {
+    const LongCol lc = cols[w];
+    for (int e = lane; e < lc.len; e += 32) {
+      const IdxT r = row[lc.src_start + e];
+      if (r < 0 || r >= (IdxT)m) atomicOr(bad, 1u);
+      la[lc.off + e] = a[lc.src_start + e];
+      lcv[lc.off + e] = c[lc.src_start + e];
+      lrow[lc.off + e] = (uint32_t)r;
+    }
   }
 }
 
@@ -188,11 +216,12 @@ __global__ void build_passes_kernel(const IdxT* __restrict__ ccol, const uint8_t
 // Hot kernel
 // ------------------------------------------------------------------------------------------
 struct KArgs {
-  const float* a;
-  const float* c;
-  const void* row;
-  const void* entries;
-  const uint8_t* cls_ne;
+  const float* a_t;
+  const float* c_t;
+  const void* row_t;
+  const SlabHdr* hdr;
+  const int64_t* orig_start;
+  int64_t n_slabs;
   const dualip_proj_class* classes;
   int n_classes;
   const float* lambda;
@@ -205,169 +234,45 @@ struct KArgs {
   float* partial_out;        // partial mode: m+2 floats
   float* x_out;              // may be null
   uint8_t* diag;             // may be null
-  int64_t n_runs;
-  int run_len;
   int m;
   double gamma;
   float s;                   // fl32(-1/gamma)   (matching.py:136: `-1.0 / self.gamma * dual_val`)
   int flush_bulk;
   int do_epilogue;           // 1: calc (grad/scalars), 0: partial (packed sums)
+  const float* long_a;
+  const float* long_c;
+  const uint32_t* long_row;
 };
 
-struct Slot {
-  float a, c;
-  uint32_t r;
-  uint32_t cls;
-  uint32_t start, endmask;
-};
-
-template <bool ROW16, bool UNIFORM>
-__device__ __forceinline__ void load_slot(Slot& s, const KArgs& k, uint32_t start, uint32_t endmask, uint32_t colbase,
-                                          int lane) {
-  s.start = start;
-  s.endmask = endmask;
-  const int cnt = 32 - __clz(endmask);
-  s.a = 0.f;
-  s.c = 0.f;
-  s.r = 0u;
-  s.cls = 0u;
-  if (lane < cnt) {
-    const size_t idx = (size_t)start + lane;
-    s.a = __ldg(k.a + idx);
-    s.c = __ldg(k.c + idx);
-    if (ROW16)
-      s.r = __ldg(reinterpret_cast<const unsigned short*>(k.row) + idx);
-    else
-      s.r = __ldg(reinterpret_cast<const uint32_t*>(k.row) + idx);
-    if (!UNIFORM) {
-      const uint32_t headbits = (endmask << 1) | 1u;
-      const uint32_t le = 0xffffffffu >> (31 - lane);
-      s.cls = __ldg(k.cls_ne + (size_t)colbase + (__popc(headbits & le) - 1));
-    }
-  }
+template <bool ROW16>
+__device__ __forceinline__ uint32_t ld_row(const void* row_t, size_t idx) {
+  if (ROW16) return __ldg(reinterpret_cast<const unsigned short*>(row_t) + idx);
+  return __ldg(reinterpret_cast<const uint32_t*>(row_t) + idx);
 }
 
-// Everything per pass.  SMODE 0: scaled lambda and grad accumulator in smem; 1: grad accumulator in smem,
-// lambda gathered from global (L2); 2: neither (global atomics; very large m).
-template <bool UNIFORM, int SMODE>
-__device__ __forceinline__ void process_pass(const Slot& sl, const KArgs& k, const float* s_lam, float* s_grad,
-                                             const dualip_proj_class* s_cls, int lane, double& cx, double& xx) {
-  const unsigned FULL = 0xffffffffu;
-  const uint32_t endmask = sl.endmask;
-  const int cnt = 32 - __clz(endmask);
-  if (cnt == 0) return;  // warp-uniform (padding pass)
-  const bool valid = lane < cnt;
-  const uint32_t headbits = (endmask << 1) | 1u;
-  const uint32_t le = 0xffffffffu >> (31 - lane);
-  int seg_start = 31 - __clz(headbits & le);
-  int seg_end = __ffs(endmask & (0xffffffffu << lane)) - 1;
-  if (!valid) {
-    seg_start = lane;
-    seg_end = lane;
-  }
-  const float av = sl.a, cv = sl.c;
-  const uint32_t rv = sl.r;
-  float lam_s;
-  if (SMODE == 0)
-    lam_s = s_lam[rv];
+// SMODE 0: scaled lambda and the gradient accumulator live in shared memory; 1: accumulator only (lambda is
+// gathered from global/L2); 2: neither (global atomics; only for very large m).
+template <int SMODE>
+__device__ __forceinline__ float lam_scaled(const KArgs& k, const float* s_lam, uint32_t r) {
+  if (SMODE == 0) return s_lam[r];
+  return __fmul_rn(k.s, __ldg(k.lambda + r));
+}
+template <int SMODE>
+__device__ __forceinline__ void grad_add(const KArgs& k, float* s_grad, uint32_t r, float g) {
+  if (SMODE <= 1)
+    atomicAdd(&s_grad[r], g);
   else
-    lam_s = __fmul_rn(k.s, __ldg(k.lambda + rv));
-  // v = fl(fl(a * fl(s*lambda_r)) + fl(s*c)): same operation order as the reference, no FMA contraction.
-  const float v = __fadd_rn(__fmul_rn(av, lam_s), __fmul_rn(k.s, cv));
+    atomicAdd(&k.acc[r], g);
+}
 
-  const dualip_proj_class pc = s_cls[UNIFORM ? 0u : sl.cls];
-  const bool is_sx = valid && (pc.kind != DUALIP_PROJ_CLAMP);
-  float x = fminf(fmaxf(v, pc.lo), pc.hi);  // box.py:16, cone.py:22-28 (lo/hi = -+inf when open)
-  int branch = 0, rho = 0;
+// v = fl(fl(a * fl(s*lambda_r)) + fl(s*c)): the reference's operation order in fp32, no FMA contraction.
+__device__ __forceinline__ float make_v(float a, float lam_s, float s, float c) {
+  return __fadd_rn(__fmul_rn(a, lam_s), __fmul_rn(s, c));
+}
 
-  if (__any_sync(FULL, is_sx)) {
-    // ---- batched Duchi with pre-clamp, one column per lane segment (simplex.py:143-236) ----
-    const float u = is_sx ? fmaxf(v, 0.f) : 0.f;               // simplex.py:148
-    const float un = is_sx ? __fdiv_rn(u, pc.z) : 0.f;         // simplex.py:172 (top-2 test on u/z)
-    float S = u, m1 = un, m2 = 0.f;                            // m2 starts at the zero padding value
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const float tS = __shfl_up_sync(FULL, S, d);
-      const float t1 = __shfl_up_sync(FULL, m1, d);
-      const float t2 = __shfl_up_sync(FULL, m2, d);
-      if (lane - d >= seg_start) {
-        S = __fadd_rn(tS, S);
-        const float mn = fminf(m1, t1);
-        m1 = fmaxf(m1, t1);
-        m2 = fmaxf(fmaxf(m2, t2), mn);
-      }
-    }
-    S = __shfl_sync(FULL, S, seg_end);
-    m1 = __shfl_sync(FULL, m1, seg_end);
-    m2 = __shfl_sync(FULL, m2, seg_end);
-    const int deg = seg_end - seg_start + 1;
-    const uint32_t segmask = (0xffffffffu >> (31 - seg_end)) & (0xffffffffu << seg_start);
-    const bool feasible = (pc.kind == DUALIP_PROJ_SIMPLEX) && (S <= pc.z_thr);                 // simplex.py:153-155
-    const bool padded = (deg > 1) || !(pc.flags & DUALIP_PROJ_FLAG_D1_UNPADDED);                 // simplex.py:166
-    const bool shortcut = !feasible && padded && (__fsub_rn(m1, m2) > 1.0f);                     // simplex.py:178
-    const uint32_t eqb = __ballot_sync(FULL, is_sx && (un == m1)) & segmask;
-    const int amax = __ffs(eqb) - 1;
-    const bool need = is_sx && !feasible && !shortcut;
-    float theta = 0.f;
-    if (__any_sync(FULL, need)) {
-      // Rank every entry inside its column by all-pairs comparison (ties broken by position), and take
-      // the prefix sum in sorted order in fp64 like torch's CPU cumsum does (acc_type<float> = double).
-      const int maxlen = __reduce_max_sync(FULL, need ? deg : 0);
-      int rank = 0;
-      double cs = 0.0;
-      for (int t = 0; t < maxlen; ++t) {
-        const int p = seg_start + t;
-        const float up = __shfl_sync(FULL, u, p & 31);
-        if (p <= seg_end && (up > u || (up == u && p <= lane))) {
-          ++rank;
-          cs += (double)up;
-        }
-      }
-      const float css = (float)cs;
-      // cond_i = u_(i) - (css_i - z)/i > 0 ; rho = max i with cond   (simplex.py:221-225)
-      const bool cond = need && (__fsub_rn(u, __fdiv_rn(__fsub_rn(css, pc.z), (float)rank)) > 0.f);
-      int rr = cond ? rank : 0;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(FULL, rr, d);
-        if (lane - d >= seg_start) rr = max(rr, t);
-      }
-      rho = max(__shfl_sync(FULL, rr, seg_end), 1);
-      const uint32_t rb = __ballot_sync(FULL, need && rank == rho) & segmask;
-      const int src = __ffs(rb) - 1;
-      const float cssr = __shfl_sync(FULL, css, src < 0 ? lane : src);
-      theta = __fdiv_rn(__fsub_rn(cssr, pc.z), (float)rho);                                      // simplex.py:228-230
-    }
-    if (is_sx) {
-      if (feasible) {
-        x = u;
-        branch = 0;
-      } else if (shortcut) {
-        x = (lane == amax) ? pc.z : 0.f;                                                         // simplex.py:185-190
-        branch = 1;
-        rho = 1;
-      } else {
-        x = fmaxf(__fsub_rn(u, theta), 0.f);                                                     // simplex.py:233
-        branch = 2;
-      }
-    }
-  }
-
-  if (valid) {
-    const float g = __fmul_rn(av, x);  // matching.py:153 (elementwise mul), then row sums
-    if (g != 0.f) {
-      if (SMODE <= 1)
-        atomicAdd(&s_grad[rv], g);
-      else
-        atomicAdd(&k.acc[rv], g);
-    }
-    const double xd = (double)x;
-    cx = fma((double)cv, xd, cx);
-    xx = fma(xd, xd, xx);
-    const size_t idx = (size_t)sl.start + lane;
-    if (k.x_out) k.x_out[idx] = x;
-    if (k.diag && is_sx && lane == seg_start) k.diag[idx] = (uint8_t)(branch | (min(rho, 63) << 2));
-  }
+// Largest double below x, for x >= 0 (so that {u > t} becomes {u >= x}).
+__device__ __forceinline__ double just_below(double x) {
+  return x > 0.0 ? __longlong_as_double(__double_as_longlong(x) - 1LL) : -4.9406564584124654e-324;
 }
 
 // m-length tail, executed by one whole CTA.  `sum` = sum_j a_rj x_rj (m floats), cxv = c.x, xxv = ||x||^2.
@@ -404,10 +309,10 @@ __device__ void cta_epilogue(const float* sum, double cxv, double xxv, const flo
   }
 }
 
-template <bool ROW16, bool UNIFORM, int SMODE, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) matching_pass_kernel(const KArgs k) {
+template <bool ROW16, int SMODE, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArgs k) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // carve: [mbarrier 16B][classes][scratch 32 doubles][s_lam m_pad floats][s_grad m floats]
+  // carve: [mbarrier 16B][classes][scratch 32 doubles + 32 floats][s_lam m_pad floats][s_grad m floats]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   dualip_proj_class* s_cls = reinterpret_cast<dualip_proj_class*>(smem_raw + 16);
   const int n_cls_bytes = ((k.n_classes * (int)sizeof(dualip_proj_class)) + 15) & ~15;
@@ -419,6 +324,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_pass_kernel(const KArg
   float* s_grad = s_lam + (SMODE == 0 ? m_pad : 0);
   __shared__ unsigned int s_ticket;
 
+  const unsigned FULL = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = THREADS / 32;
 
@@ -453,61 +359,271 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_pass_kernel(const KArg
   }
   __syncthreads();
 
-  // ---- stream this CTA's share of the pass table ----
+  // ---- stream slabs: warp w of the grid takes slabs w, w + W, w + 2W, ... (neighbouring warps read neighbouring
+  //      slabs, and every warp sees the same mix of column lengths) ----
   double cx = 0.0, xx = 0.0;
-  {
-    const int64_t run_begin = (k.n_runs * (int64_t)blockIdx.x) / gridDim.x;
-    const int64_t run_end = (k.n_runs * (int64_t)(blockIdx.x + 1)) / gridDim.x;
-    const int RL = k.run_len;
-    using Entry = typename std::conditional<UNIFORM, PassEntryU, PassEntryC>::type;
-    const Entry* entries = reinterpret_cast<const Entry*>(k.entries);
-    auto load_entry = [&](int64_t run) -> Entry {
-      Entry e;
-      memset(&e, 0, sizeof(e));
-      if (run < run_end && lane < RL) {
-        if (UNIFORM) {
-          const uint2 t = __ldg(reinterpret_cast<const uint2*>(entries) + run * RL + lane);
-          memcpy(&e, &t, sizeof(t));
-        } else {
-          const uint4 t = __ldg(reinterpret_cast<const uint4*>(entries) + run * RL + lane);
-          memcpy(&e, &t, sizeof(t));
+  const int64_t total_warps = (int64_t)gridDim.x * NW;
+  const bool want_out = (k.x_out != nullptr) || (k.diag != nullptr);
+  const float s = k.s;
+  using RowT = typename std::conditional<ROW16, unsigned short, uint32_t>::type;
+  const RowT* row_all = reinterpret_cast<const RowT*>(k.row_t);
+  int64_t sl = (int64_t)blockIdx.x * NW + warp;
+  uint2 hnext = make_uint2(0u, 0u);
+  if (sl < k.n_slabs) hnext = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl);
+  for (; sl < k.n_slabs; sl += total_warps) {
+    const uint2 hraw = hnext;
+    if (sl + total_warps < k.n_slabs) hnext = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl + total_warps);
+    const int d = (int)(hraw.y & 0xffffu);
+    const int cls = (int)((hraw.y >> 16) & 0xffu);
+    const bool active = lane < (int)(hraw.y >> 24);
+    const size_t base = (size_t)hraw.x * kSlabW + lane;
+    const float* __restrict__ pa = k.a_t + base;
+    const float* __restrict__ pcv = k.c_t + base;
+    const RowT* __restrict__ pr = row_all + base;
+    const dualip_proj_class pc = s_cls[cls];
+    float cxs = 0.f, xxs = 0.f;
+    // per-lane outcome, also what the (rare) output pass needs: x_k = branch 0: u_k, 1: z*[k == i1], 2: max(u_k - theta, 0)
+    int branch = -1, rho = 0, i1 = 0;
+    float theta = 0.f;
+
+    if (pc.kind == DUALIP_PROJ_CLAMP) {
+      // ---- box / cone / identity: one streaming pass (box.py:16, cone.py:21-28) ----
+      const float lo = active ? pc.lo : 0.f, hi = active ? pc.hi : 0.f;  // padding lanes produce x = 0
+      auto body = [&](float a, float c, uint32_t r) {
+        const float v = make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c);
+        const float x = fminf(fmaxf(v, lo), hi);
+        const float g = __fmul_rn(a, x);
+        if (g != 0.f) grad_add<SMODE>(k, s_grad, r, g);
+        cxs = fmaf(c, x, cxs);
+        xxs = fmaf(x, x, xxs);
+      };
+      int kk = 0;
+      for (; kk + 4 <= d; kk += 4) {
+        float a4[4], c4[4];
+        uint32_t r4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          a4[q] = __ldg(pa + (size_t)(kk + q) * kSlabW);
+          c4[q] = __ldg(pcv + (size_t)(kk + q) * kSlabW);
+          r4[q] = __ldg(pr + (size_t)(kk + q) * kSlabW);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) body(a4[q], c4[q], r4[q]);
+        if ((kk & 63) == 60) {  // keep the fp32 partials short
+          cx += (double)cxs;
+          xx += (double)xxs;
+          cxs = 0.f;
+          xxs = 0.f;
         }
       }
-      return e;
-    };
-    int64_t run = run_begin + warp;
-    if (run < run_end) {
-      Entry ent_cur = load_entry(run);
-      Entry ent_next = load_entry(run + NW);
-      Slot slot[kPrefetch];
-      auto fetch = [&](Slot& s, const Entry& e, int idx) {
-        const uint32_t st = __shfl_sync(0xffffffffu, e.start, idx);
-        const uint32_t em = __shfl_sync(0xffffffffu, e.endmask, idx);
-        uint32_t cb = 0;
-        if constexpr (!UNIFORM) cb = __shfl_sync(0xffffffffu, e.colbase, idx);
-        load_slot<ROW16, UNIFORM>(s, k, st, em, cb, lane);
+      for (; kk < d; ++kk)
+        body(__ldg(pa + (size_t)kk * kSlabW), __ldg(pcv + (size_t)kk * kSlabW), __ldg(pr + (size_t)kk * kSlabW));
+    } else {
+      // ---- simplex (simplex.py:143-236 per column at its true length) ----
+      // Pass 1 streams the column once and keeps the column sum, the number of positive entries and the three
+      // largest entries with their positions.  That decides feasible / top-2 shortcut, and resolves the sorted scan in
+      // closed form whenever the support has at most two entries (the usual case); otherwise the lane falls back to a
+      // re-streaming threshold search.
+      const float z = pc.z;
+      auto u_at = [&](int kq) -> float {
+        const float a = __ldg(pa + (size_t)kq * kSlabW);
+        const float c = __ldg(pcv + (size_t)kq * kSlabW);
+        const uint32_t r = __ldg(pr + (size_t)kq * kSlabW);
+        return fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);  // simplex.py:148
       };
+      float S = 0.f, m1 = -1.f, m2 = -1.f, m3 = -1.f;
+      int i2 = 0, i3 = 0, npos = 0;
+      auto track = [&](float a, float c, uint32_t r, int kq) {
+        const float u = fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);
+        S = __fadd_rn(S, u);  // column sum in entry order
+        npos += (u > 0.f) ? 1 : 0;
+        const bool g1 = u > m1, g2 = u > m2, g3 = u > m3;
+        m3 = g2 ? m2 : (g3 ? u : m3);
+        i3 = g2 ? i2 : (g3 ? kq : i3);
+        m2 = g1 ? m1 : (g2 ? u : m2);
+        i2 = g1 ? i1 : (g2 ? kq : i2);
+        m1 = g1 ? u : m1;
+        i1 = g1 ? kq : i1;
+      };
+      int kk = 0;
+      for (; kk + 4 <= d; kk += 4) {
+        float a4[4], c4[4];
+        uint32_t r4[4];
 #pragma unroll
-      for (int u = 0; u < kPrefetch; ++u) fetch(slot[u], ent_cur, u);
-      while (true) {
-        for (int i = 0; i < RL; i += kPrefetch) {
-          const bool from_next = (i + kPrefetch >= RL);
+        for (int q = 0; q < 4; ++q) {
+          a4[q] = __ldg(pa + (size_t)(kk + q) * kSlabW);
+          c4[q] = __ldg(pcv + (size_t)(kk + q) * kSlabW);
+          r4[q] = __ldg(pr + (size_t)(kk + q) * kSlabW);
+        }
 #pragma unroll
-          for (int u = 0; u < kPrefetch; ++u) {
-            const Slot cur = slot[u];
-            const int nidx = from_next ? (i + kPrefetch - RL + u) : (i + kPrefetch + u);
-            if (from_next)
-              fetch(slot[u], ent_next, nidx);
-            else
-              fetch(slot[u], ent_cur, nidx);
-            process_pass<UNIFORM, SMODE>(cur, k, s_lam, s_grad, s_cls, lane, cx, xx);
+        for (int q = 0; q < 4; ++q) track(a4[q], c4[q], r4[q], kk + q);
+      }
+      for (; kk < d; ++kk)
+        track(__ldg(pa + (size_t)kk * kSlabW), __ldg(pcv + (size_t)kk * kSlabW), __ldg(pr + (size_t)kk * kSlabW), kk);
+
+      const bool feasible = (pc.kind == DUALIP_PROJ_SIMPLEX) && (S <= pc.z_thr);                    // simplex.py:153-155
+      const bool padded = (d > 1) || !(pc.flags & DUALIP_PROJ_FLAG_D1_UNPADDED);                    // simplex.py:166
+      const float m2p = fmaxf(m2, 0.f);  // the reference's zero padding takes part in its top-2
+      const float un1 = (z == 1.0f) ? m1 : __fdiv_rn(m1, z), un2 = (z == 1.0f) ? m2p : __fdiv_rn(m2p, z);
+      const bool shortcut = !feasible && padded && (__fsub_rn(un1, un2) > 1.0f);                    // simplex.py:172-178
+      // up to three (position, x) results per lane
+      float x1 = 0.f, x2 = 0.f, x3 = 0.f;
+      bool general = false;
+      if (feasible) {
+        branch = 0;
+        if (npos > 3) {
+          general = true;
+        } else {
+          x1 = m1;
+          x2 = fmaxf(m2, 0.f);
+          x3 = fmaxf(m3, 0.f);
+        }
+      } else if (shortcut) {
+        branch = 1;
+        rho = 1;
+        x1 = z;                                                                                     // simplex.py:185-190
+      } else {
+        branch = 2;
+        // sorted scan restricted to the three largest: css_i = fl32(prefix sum in fp64), cond_i = u_(i) - (css_i - z)/i > 0
+        const float css2 = (float)((double)m1 + (double)fmaxf(m2, 0.f));
+        const float css3 = (float)((double)m1 + (double)fmaxf(m2, 0.f) + (double)fmaxf(m3, 0.f));
+        const float t2 = __fdiv_rn(__fsub_rn(css2, z), 2.0f), t3 = __fdiv_rn(__fsub_rn(css3, z), 3.0f);
+        const bool cond3 = (d >= 3) && (__fsub_rn(m3, t3) > 0.f);
+        const bool cond2 = (d >= 2) && (__fsub_rn(m2, t2) > 0.f);
+        if (cond3) {
+          general = true;  // support of three or more entries
+        } else {
+          rho = cond2 ? 2 : 1;
+          theta = cond2 ? t2 : __fsub_rn(m1, z);                                                    // simplex.py:228-230
+          x1 = fmaxf(__fsub_rn(m1, theta), 0.f);                                                    // simplex.py:233
+          x2 = (d >= 2) ? fmaxf(__fsub_rn(m2, theta), 0.f) : 0.f;
+          x3 = (d >= 3) ? fmaxf(__fsub_rn(m3, theta), 0.f) : 0.f;
+        }
+      }
+      general = general && active;
+      if (!active) {
+        x1 = 0.f;
+        x2 = 0.f;
+        x3 = 0.f;
+      }
+      // accumulate the (at most three) non-zeros: their entries are re-read from lines this warp has just streamed
+      auto emit = [&](int kq, float x) {
+        if (x != 0.f) {
+          const float a = __ldg(pa + (size_t)kq * kSlabW);
+          const float c = __ldg(pcv + (size_t)kq * kSlabW);
+          const uint32_t r = __ldg(pr + (size_t)kq * kSlabW);
+          const float g = __fmul_rn(a, x);
+          if (g != 0.f) grad_add<SMODE>(k, s_grad, r, g);
+          cxs = fmaf(c, x, cxs);
+          xxs = fmaf(x, x, xxs);
+        }
+      };
+      emit(i1, x1);
+      if (__any_sync(FULL, x2 != 0.f)) emit(i2, x2);
+      if (__any_sync(FULL, x3 != 0.f)) emit(i3, x3);
+
+      if (__any_sync(FULL, general)) {
+        // ---- fallback: Michelot fixed point by re-streaming, then alignment with the reference's fp32 conditions ----
+        const bool need = general && branch == 2;
+        if (__any_sync(FULL, need)) {
+          double t = (double)m1 - (double)z, ssum = 0.0;  // theta* >= max - z, so {u > max - z} contains the support
+          t = just_below(fmax(t, 0.0));
+          int cnt = 0, cnt_prev = -1;
+          auto recount = [&]() {
+            cnt = 0;
+            ssum = 0.0;
+            for (int kq = 0; kq < d; ++kq) {
+              const float u = u_at(kq);
+              if ((double)u > t) {
+                ++cnt;
+                ssum += (double)u;
+              }
+            }
+          };
+          for (int it = 0; it < 64; ++it) {
+            recount();
+            const bool done = !need || cnt == cnt_prev || cnt == 0;
+            if (!done) {
+              cnt_prev = cnt;
+              t = (ssum - (double)z) / (double)cnt;
+            }
+            if (__all_sync(FULL, done)) break;
+          }
+          float th = 0.f;
+          for (int fix = 0; fix < 4; ++fix) {
+            float umin = INFINITY, uout = -INFINITY;
+            for (int kq = 0; kq < d; ++kq) {
+              const float u = u_at(kq);
+              const bool in = (double)u > t;
+              umin = in ? fminf(umin, u) : umin;
+              uout = in ? uout : fmaxf(uout, u);
+            }
+            th = __fdiv_rn(__fsub_rn((float)ssum, z), (float)max(cnt, 1));
+            bool changed = false;
+            if (need && cnt > 1 && !(__fsub_rn(umin, th) > 0.f)) {
+              t = (double)umin;  // cond_rho fails in the fp32 formula: drop the smallest support value(s)
+              changed = true;
+            } else if (need && uout > -INFINITY) {
+              const float t1 = __fdiv_rn(__fsub_rn((float)(ssum + (double)uout), z), (float)(cnt + 1));
+              if (__fsub_rn(uout, t1) > 0.f) {  // cond_{rho+1} holds: the support grows
+                t = just_below((double)uout);
+                changed = true;
+              }
+            }
+            if (!__any_sync(FULL, changed)) break;
+            if (changed) recount();
+          }
+          if (need) {
+            theta = th;
+            rho = max(cnt, 1);
           }
         }
-        run += NW;
-        if (run >= run_end) break;
-        ent_cur = ent_next;
-        ent_next = load_entry(run + NW);
+        for (int kq = 0; kq < d; ++kq) {
+          if (general) {
+            const float a = __ldg(pa + (size_t)kq * kSlabW);
+            const float c = __ldg(pcv + (size_t)kq * kSlabW);
+            const uint32_t r = __ldg(pr + (size_t)kq * kSlabW);
+            const float u = fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);
+            const float x = (branch == 0) ? u : fmaxf(__fsub_rn(u, theta), 0.f);
+            const float g = __fmul_rn(a, x);
+            if (g != 0.f) grad_add<SMODE>(k, s_grad, r, g);
+            cxs = fmaf(c, x, cxs);
+            xxs = fmaf(x, x, xxs);
+          }
+          if ((kq & 63) == 63) {
+            cx += (double)cxs;
+            xx += (double)xxs;
+            cxs = 0.f;
+            xxs = 0.f;
+          }
+        }
       }
+    }
+    cx += (double)cxs;
+    xx += (double)xxs;
+
+    if (want_out && active) {
+      // ---- primal / diagnostics output (save_primal on the last iteration, tests): plain re-stream ----
+      const int64_t os = k.orig_start[sl * kSlabW + lane];
+      if (k.x_out) {
+        for (int kq = 0; kq < d; ++kq) {
+          const float a = __ldg(pa + (size_t)kq * kSlabW);
+          const float c = __ldg(pcv + (size_t)kq * kSlabW);
+          const uint32_t r = __ldg(pr + (size_t)kq * kSlabW);
+          const float v = make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c);
+          float x;
+          if (branch < 0)
+            x = fminf(fmaxf(v, pc.lo), pc.hi);
+          else if (branch == 0)
+            x = fmaxf(v, 0.f);
+          else if (branch == 1)
+            x = (kq == i1) ? pc.z : 0.f;
+          else
+            x = fmaxf(__fsub_rn(fmaxf(v, 0.f), theta), 0.f);
+          k.x_out[os + kq] = x;
+        }
+      }
+      if (k.diag && branch >= 0) k.diag[os] = (uint8_t)(branch | (min(rho, 63) << 2));
     }
   }
 
@@ -573,11 +689,10 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_pass_kernel(const KArg
 }
 
 // ------------------------------------------------------------------------------------------
-// Long columns (> 32 entries): one warp per column, multi-sweep, straight from global memory.
-// The threshold is found with Michelot's fixed point (same support set and theta formula as Duchi's
-// sorted scan in exact arithmetic); sums over the support are fp64 like the reference's CPU cumsum.
+// Very long columns (> kMaxThreadDeg entries): one warp per column, multi-sweep over the plan's compact copy.
+// Threshold by Michelot's fixed point (same support set and theta formula as the sorted scan in exact arithmetic);
+// sums over the support are fp64 like the reference's CPU cumsum.
 // ------------------------------------------------------------------------------------------
-template <bool ROW16>
 __global__ void __launch_bounds__(256) matching_long_kernel(const KArgs k, const LongCol* __restrict__ cols, int64_t n_long) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -587,26 +702,21 @@ __global__ void __launch_bounds__(256) matching_long_kernel(const KArgs k, const
   for (int64_t ci = warp_global; ci < n_long; ci += n_warps) {
     const LongCol lc = cols[ci];
     const dualip_proj_class pc = k.classes[lc.cls];
-    const float* a = k.a + lc.start;
-    const float* c = k.c + lc.start;
-    auto row_at = [&](int e) -> uint32_t {
-      if (ROW16) return __ldg(reinterpret_cast<const unsigned short*>(k.row) + lc.start + e);
-      return __ldg(reinterpret_cast<const uint32_t*>(k.row) + lc.start + e);
-    };
+    const float* a = k.long_a + lc.off;
+    const float* c = k.long_c + lc.off;
+    const uint32_t* row = k.long_row + lc.off;
     auto v_at = [&](int e, float& av, float& cv, uint32_t& rv) -> float {
       av = __ldg(a + e);
       cv = __ldg(c + e);
-      rv = row_at(e);
-      const float lam_s = __fmul_rn(k.s, __ldg(k.lambda + rv));
-      return __fadd_rn(__fmul_rn(av, lam_s), __fmul_rn(k.s, cv));
+      rv = __ldg(row + e);
+      return make_v(av, __fmul_rn(k.s, __ldg(k.lambda + rv)), k.s, cv);
     };
     const bool is_sx = pc.kind != DUALIP_PROJ_CLAMP;
     float theta = 0.f;
     int branch = 0, rho = 0, amax = -1;
     if (is_sx) {
-      // sweep 1: sum, top-2 of u/z, position of the maximum
       double S = 0.0;
-      float m1 = 0.f, m2 = 0.f;
+      float m1 = -1.f, m2 = 0.f;
       int am = 0x7fffffff;
       for (int e = lane; e < lc.len; e += 32) {
         float av, cv;
@@ -614,13 +724,9 @@ __global__ void __launch_bounds__(256) matching_long_kernel(const KArgs k, const
         const float u = fmaxf(v_at(e, av, cv, rv), 0.f);
         const float un = __fdiv_rn(u, pc.z);
         S += (double)u;
-        if (un > m1) {
-          m2 = m1;
-          m1 = un;
-          am = e;
-        } else if (un > m2) {
-          m2 = un;
-        }
+        if (un > m1) am = e;
+        m2 = fmaxf(m2, fminf(m1, un));
+        m1 = fmaxf(m1, un);
       }
       S = warp_sum(S);
 #pragma unroll
@@ -642,10 +748,8 @@ __global__ void __launch_bounds__(256) matching_long_kernel(const KArgs k, const
         amax = am;
       } else {
         branch = 2;
-        // Michelot: t <- (sum_{u>t} u - z)/|{u>t}| until the support stops shrinking.
-        double t = (S - (double)pc.z) / (double)lc.len;
-        int cnt_prev = lc.len;
-        double Ssup = S;
+        double t = -INFINITY, Ssup = S;
+        int cnt_prev = -1;
         for (int it = 0; it < 64; ++it) {
           double s2 = 0.0;
           int n2 = 0;
@@ -664,14 +768,13 @@ __global__ void __launch_bounds__(256) matching_long_kernel(const KArgs k, const
           Ssup = s2;
           const bool done = (n2 == cnt_prev);
           cnt_prev = n2;
-          t = (s2 - (double)pc.z) / (double)n2;
           if (done) break;
+          t = (s2 - (double)pc.z) / (double)n2;
         }
-        rho = cnt_prev;
+        rho = max(cnt_prev, 1);
         theta = __fdiv_rn(__fsub_rn((float)Ssup, pc.z), (float)rho);
       }
     }
-    // final sweep: x, gradient scatter, scalars
     for (int e = lane; e < lc.len; e += 32) {
       float av, cv;
       uint32_t rv;
@@ -688,8 +791,8 @@ __global__ void __launch_bounds__(256) matching_long_kernel(const KArgs k, const
       const double xd = (double)x;
       cx = fma((double)cv, xd, cx);
       xx = fma(xd, xd, xx);
-      if (k.x_out) k.x_out[lc.start + e] = x;
-      if (k.diag && is_sx && e == 0) k.diag[lc.start] = (uint8_t)(branch | (min(rho, 63) << 2));
+      if (k.x_out) k.x_out[lc.src_start + e] = x;
+      if (k.diag && is_sx && e == 0) k.diag[lc.src_start] = (uint8_t)(branch | (min(rho, 63) << 2));
     }
   }
   cx = warp_sum(cx);
@@ -710,32 +813,26 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(const float* sum, int m,
 // ------------------------------------------------------------------------------------------
 // Launch plumbing
 // ------------------------------------------------------------------------------------------
-typedef void (*PassKernel)(const KArgs);
+typedef void (*SlabKernel)(const KArgs);
 
 template <int THREADS, int MINB>
-static PassKernel pick_kernel(bool row16, bool uniform, int smode) {
-#define DUALIP_PICK(R, U, S) \
-  if (row16 == R && uniform == U && smode == S) return matching_pass_kernel<R, U, S, THREADS, MINB>;
-  DUALIP_PICK(true, true, 0)
-  DUALIP_PICK(true, true, 1)
-  DUALIP_PICK(true, true, 2)
-  DUALIP_PICK(true, false, 0)
-  DUALIP_PICK(true, false, 1)
-  DUALIP_PICK(true, false, 2)
-  DUALIP_PICK(false, true, 0)
-  DUALIP_PICK(false, true, 1)
-  DUALIP_PICK(false, true, 2)
-  DUALIP_PICK(false, false, 0)
-  DUALIP_PICK(false, false, 1)
-  DUALIP_PICK(false, false, 2)
+static SlabKernel pick_kernel(bool row16, int smode) {
+#define DUALIP_PICK(R, S) \
+  if (row16 == R && smode == S) return matching_slab_kernel<R, S, THREADS, MINB>;
+  DUALIP_PICK(true, 0)
+  DUALIP_PICK(true, 1)
+  DUALIP_PICK(true, 2)
+  DUALIP_PICK(false, 0)
+  DUALIP_PICK(false, 1)
+  DUALIP_PICK(false, 2)
 #undef DUALIP_PICK
   return nullptr;
 }
 
-static PassKernel plan_kernel(const dualip_plan* p) {
+static SlabKernel plan_kernel(const dualip_plan* p) {
   const bool row16 = p->row_bits == 16;
-  if (p->threads == 512) return pick_kernel<512, 2>(row16, p->uniform, p->smode);
-  return pick_kernel<1024, 1>(row16, p->uniform, p->smode);
+  if (p->threads == 512) return pick_kernel<512, 2>(row16, p->smode);
+  return pick_kernel<1024, 1>(row16, p->smode);
 }
 
 static size_t smem_fixed_bytes(int n_classes) {
@@ -750,11 +847,12 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
     return DUALIP_EINVAL;
   }
   KArgs k;
-  k.a = p->a;
-  k.c = p->c;
-  k.row = p->row;
-  k.entries = p->entries;
-  k.cls_ne = p->cls_ne;
+  k.a_t = p->a_t;
+  k.c_t = p->c_t;
+  k.row_t = p->row_t;
+  k.hdr = p->hdr;
+  k.orig_start = p->orig_start;
+  k.n_slabs = p->n_slabs;
   k.classes = p->classes_dev;
   k.n_classes = p->n_classes;
   k.lambda = lambda;
@@ -767,114 +865,212 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.partial_out = partial_out;
   k.x_out = x_out;
   k.diag = diag;
-  k.n_runs = p->n_runs;
-  k.run_len = p->run_len;
   k.m = p->m;
   k.gamma = gamma;
   k.s = (float)(-1.0 / gamma);
   k.flush_bulk = p->flush_bulk;
   k.do_epilogue = do_epilogue;
+  k.long_a = p->long_a;
+  k.long_c = p->long_c;
+  k.long_row = p->long_row;
   if (p->n_long > 0) {
-    const int64_t warps = p->n_long;
-    int blocks = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)p->n_sms * 8);
-    if (p->row_bits == 16)
-      matching_long_kernel<true><<<blocks, 256, 0, stream>>>(k, p->longcols, p->n_long);
-    else
-      matching_long_kernel<false><<<blocks, 256, 0, stream>>>(k, p->longcols, p->n_long);
+    const int blocks = (int)std::min<int64_t>((p->n_long + 7) / 8, (int64_t)p->n_sms * 8);
+    matching_long_kernel<<<blocks, 256, 0, stream>>>(k, p->longcols, p->n_long);
   }
-  PassKernel kern = plan_kernel(p);
+  SlabKernel kern = plan_kernel(p);
   kern<<<p->n_ctas, p->threads, p->smem_bytes, stream>>>(k);
   DUALIP_CUDA_TRY(cudaGetLastError());
   return DUALIP_OK;
 }
 
-template <typename IdxT>
-static int build_passes(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t stream) {
-  const int64_t n_chunks = (p->n_cols + kChunkCols - 1) / kChunkCols;
-  unsigned long long *counts = nullptr, *offsets = nullptr;
-  unsigned int* bad = nullptr;
-  DUALIP_CUDA_TRY(cudaMalloc(&counts, sizeof(unsigned long long) * 3 * (n_chunks + 1)));
-  DUALIP_CUDA_TRY(cudaMalloc(&offsets, sizeof(unsigned long long) * 3 * (n_chunks + 1)));
-  DUALIP_CUDA_TRY(cudaMalloc(&bad, sizeof(unsigned int)));
-  DUALIP_CUDA_TRY(cudaMemsetAsync(bad, 0, sizeof(unsigned int), stream));
-  DUALIP_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 3 * (n_chunks + 1), stream));
-  const IdxT* ccol = reinterpret_cast<const IdxT*>(d->ccol_dev);
-  const int tb = 128;
-  const int nb = (int)((n_chunks + tb - 1) / tb);
-  if (n_chunks > 0) {
-    if (p->uniform)
-      build_passes_kernel<IdxT, false, true><<<nb, tb, 0, stream>>>(ccol, d->col_class_dev, p->n_cols, n_chunks, counts,
-                                                                    nullptr, nullptr, nullptr, nullptr, bad);
-    else
-      build_passes_kernel<IdxT, false, false><<<nb, tb, 0, stream>>>(ccol, d->col_class_dev, p->n_cols, n_chunks, counts,
-                                                                     nullptr, nullptr, nullptr, nullptr, bad);
-  }
-  // exclusive scan over the interleaved triples: scan each of the three streams with stride-3 via a
-  // single scan of 3*(n_chunks+1) values is wrong, so scan three strided views with a custom iterator.
-  // Simpler: copy to host when small, else three cub scans over de-interleaved temporaries.
-  const int64_t N = n_chunks + 1;
-  unsigned long long *tmp_in = nullptr, *tmp_out = nullptr;
-  DUALIP_CUDA_TRY(cudaMalloc(&tmp_in, sizeof(unsigned long long) * N));
-  DUALIP_CUDA_TRY(cudaMalloc(&tmp_out, sizeof(unsigned long long) * N));
-  void* cub_tmp = nullptr;
-  size_t cub_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, tmp_in, tmp_out, (int)N, stream);
-  DUALIP_CUDA_TRY(cudaMalloc(&cub_tmp, cub_bytes ? cub_bytes : 16));
-  unsigned long long totals[3] = {0, 0, 0};
-  for (int f = 0; f < 3; ++f) {
-    DUALIP_CUDA_TRY(cudaMemcpy2DAsync(tmp_in, sizeof(unsigned long long), counts + f, 3 * sizeof(unsigned long long),
-                                      sizeof(unsigned long long), N, cudaMemcpyDeviceToDevice, stream));
-    cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, tmp_in, tmp_out, (int)N, stream);
-    DUALIP_CUDA_TRY(cudaMemcpy2DAsync(offsets + f, 3 * sizeof(unsigned long long), tmp_out, sizeof(unsigned long long),
-                                      sizeof(unsigned long long), N, cudaMemcpyDeviceToDevice, stream));
-    DUALIP_CUDA_TRY(cudaMemcpyAsync(&totals[f], tmp_out + n_chunks, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-  }
-  DUALIP_CUDA_TRY(cudaStreamSynchronize(stream));
-  p->n_passes = (int64_t)totals[0];
-  const int64_t n_ne = (int64_t)totals[1];
-  p->n_long = (int64_t)totals[2];
+struct Group {
+  uint32_t key;
+  int64_t start, count, slab_base, off32;
+};
 
-  // run length: shorter runs for small problems so that every warp gets work
-  int rl = 32;
-  const int64_t warps_total = (int64_t)p->n_ctas * (p->threads / 32);
-  while (rl > kPrefetch && p->n_passes / rl < warps_total * 4) rl >>= 1;
-  p->run_len = rl;
-  p->n_runs = (p->n_passes + rl - 1) / rl;
-  const int64_t padded = (p->n_runs + 2) * rl + 32;
-  const size_t esz = p->uniform ? sizeof(PassEntryU) : sizeof(PassEntryC);
-  DUALIP_CUDA_TRY(cudaMalloc(&p->entries, esz * padded));
-  DUALIP_CUDA_TRY(cudaMemsetAsync(p->entries, 0, esz * padded, stream));
-  p->owned_bytes += esz * padded;
-  if (!p->uniform) {
-    DUALIP_CUDA_TRY(cudaMalloc(&p->cls_ne, (size_t)n_ne + 16));
-    p->owned_bytes += (size_t)n_ne + 16;
+template <typename IdxT>
+static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t stream) {
+  const int64_t n = p->n_cols;
+  const IdxT* ccol = reinterpret_cast<const IdxT*>(d->ccol_dev);
+  const IdxT* row = reinterpret_cast<const IdxT*>(d->row_dev);
+  unsigned int* bad = nullptr;
+  uint32_t *keys = nullptr, *vals = nullptr, *keys_s = nullptr, *perm = nullptr, *uniq = nullptr, *counts = nullptr;
+  int* n_runs_dev = nullptr;
+  void* tmp = nullptr;
+  int64_t *g_start_d = nullptr, *g_slab_d = nullptr, *g_off_d = nullptr;
+  uint32_t* g_key_d = nullptr;
+  int rc = DUALIP_OK;
+  auto cleanup = [&]() {
+    cudaFree(bad);
+    cudaFree(keys);
+    cudaFree(vals);
+    cudaFree(keys_s);
+    cudaFree(perm);
+    cudaFree(uniq);
+    cudaFree(counts);
+    cudaFree(n_runs_dev);
+    cudaFree(tmp);
+    cudaFree(g_start_d);
+    cudaFree(g_slab_d);
+    cudaFree(g_off_d);
+    cudaFree(g_key_d);
+  };
+#define BS_TRY(expr)                                                            \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) {                                                    \
+      set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                \
+      cleanup();                                                                \
+      return _e == cudaErrorMemoryAllocation ? DUALIP_ENOMEM : DUALIP_ECUDA;    \
+    }                                                                           \
+  } while (0)
+  const int64_t n_alloc = std::max<int64_t>(n, 1);
+  const int64_t max_runs = std::min<int64_t>(n_alloc, (int64_t)256 * 2048) + 2;
+  BS_TRY(cudaMalloc(&bad, sizeof(unsigned int)));
+  BS_TRY(cudaMemsetAsync(bad, 0, sizeof(unsigned int), stream));
+  BS_TRY(cudaMalloc(&keys, sizeof(uint32_t) * n_alloc));
+  BS_TRY(cudaMalloc(&vals, sizeof(uint32_t) * n_alloc));
+  BS_TRY(cudaMalloc(&keys_s, sizeof(uint32_t) * n_alloc));
+  BS_TRY(cudaMalloc(&perm, sizeof(uint32_t) * n_alloc));
+  BS_TRY(cudaMalloc(&uniq, sizeof(uint32_t) * max_runs));
+  BS_TRY(cudaMalloc(&counts, sizeof(uint32_t) * max_runs));
+  BS_TRY(cudaMalloc(&n_runs_dev, sizeof(int)));
+  BS_TRY(cudaMemsetAsync(n_runs_dev, 0, sizeof(int), stream));
+  std::vector<Group> groups;
+  int64_t n_short = 0, n_long = 0, long_start = 0;
+  if (n > 0) {
+    const int tb = 256;
+    const int nb = (int)std::min<int64_t>((n + tb - 1) / tb, (int64_t)p->n_sms * 32);
+    column_keys_kernel<IdxT><<<nb, tb, 0, stream>>>(ccol, d->col_class_dev, n, p->n_classes, keys, vals, bad);
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, keys, keys_s, vals, perm, (int)n, 0, kKeyBits, stream);
+    cub::DeviceRunLengthEncode::Encode(nullptr, b2, keys_s, uniq, counts, n_runs_dev, (int)n, stream);
+    BS_TRY(cudaMalloc(&tmp, std::max(b1, b2) + 16));
+    size_t tb1 = std::max(b1, b2) + 16;
+    cub::DeviceRadixSort::SortPairs(tmp, tb1, keys, keys_s, vals, perm, (int)n, 0, kKeyBits, stream);
+    tb1 = std::max(b1, b2) + 16;
+    cub::DeviceRunLengthEncode::Encode(tmp, tb1, keys_s, uniq, counts, n_runs_dev, (int)n, stream);
+    int n_runs = 0;
+    unsigned int bad_h = 0;
+    BS_TRY(cudaMemcpyAsync(&n_runs, n_runs_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    BS_TRY(cudaMemcpyAsync(&bad_h, bad, sizeof(bad_h), cudaMemcpyDeviceToHost, stream));
+    BS_TRY(cudaStreamSynchronize(stream));
+    if (bad_h) {
+      set_error(bad_h & 8u ? "col_class id out of range" : "ccol_indices must be non-decreasing (flags=%u)", bad_h);
+      cleanup();
+      return DUALIP_EINVAL;
+    }
+    std::vector<uint32_t> uk(n_runs), uc(n_runs);
+    if (n_runs > 0) {
+      BS_TRY(cudaMemcpy(uk.data(), uniq, sizeof(uint32_t) * n_runs, cudaMemcpyDeviceToHost));
+      BS_TRY(cudaMemcpy(uc.data(), counts, sizeof(uint32_t) * n_runs, cudaMemcpyDeviceToHost));
+    }
+    int64_t pos = 0, slab = 0, off32 = 0;
+    for (int r = 0; r < n_runs; ++r) {
+      if (uk[r] == kKeyLong) {
+        long_start = pos;
+        n_long = uc[r];
+      } else if (uk[r] != kKeyEmpty) {
+        Group g;
+        g.key = uk[r];
+        g.start = pos;
+        g.count = uc[r];
+        g.slab_base = slab;
+        g.off32 = off32;
+        const int64_t ns = (g.count + kSlabW - 1) / kSlabW;
+        slab += ns;
+        off32 += ns * (int64_t)(g.key & ((1u << kDegBits) - 1));
+        groups.push_back(g);
+        n_short = pos + g.count;
+      }
+      pos += uc[r];
+    }
+    p->n_slabs = slab;
+    p->rows32 = off32;
   }
-  if (p->n_long > 0) {
-    DUALIP_CUDA_TRY(cudaMalloc(&p->longcols, sizeof(LongCol) * p->n_long));
-    p->owned_bytes += sizeof(LongCol) * p->n_long;
+  p->n_short = n_short;
+  p->n_long = n_long;
+  if (p->rows32 >= (1LL << 32)) {
+    set_error("shard too large for 32-bit slab offsets; shard the columns");
+    cleanup();
+    return DUALIP_ERANGE;
   }
-  if (n_chunks > 0) {
-    if (p->uniform)
-      build_passes_kernel<IdxT, true, true><<<nb, tb, 0, stream>>>(ccol, d->col_class_dev, p->n_cols, n_chunks, nullptr,
-                                                                   offsets, p->entries, p->cls_ne, p->longcols, bad);
+  // slab storage
+  const size_t elems = (size_t)std::max<int64_t>(p->rows32, 1) * kSlabW;
+  const size_t row_bytes = (size_t)(p->row_bits / 8) * elems;
+  BS_TRY(cudaMalloc(&p->a_t, sizeof(float) * elems));
+  BS_TRY(cudaMalloc(&p->c_t, sizeof(float) * elems));
+  BS_TRY(cudaMalloc(&p->row_t, row_bytes));
+  BS_TRY(cudaMalloc(&p->hdr, sizeof(SlabHdr) * std::max<int64_t>(p->n_slabs, 1)));
+  BS_TRY(cudaMalloc(&p->orig_start, sizeof(int64_t) * std::max<int64_t>(p->n_slabs, 1) * kSlabW));
+  p->owned_bytes += 8 * elems + row_bytes + (sizeof(SlabHdr) + 8 * kSlabW) * (size_t)std::max<int64_t>(p->n_slabs, 1);
+  BS_TRY(cudaMemsetAsync(p->a_t, 0, sizeof(float) * elems, stream));
+  BS_TRY(cudaMemsetAsync(p->c_t, 0, sizeof(float) * elems, stream));
+  BS_TRY(cudaMemsetAsync(p->row_t, 0, row_bytes, stream));
+  BS_TRY(cudaMemsetAsync(p->orig_start, 0xff, sizeof(int64_t) * std::max<int64_t>(p->n_slabs, 1) * kSlabW, stream));
+  if (n_short > 0) {
+    const int G = (int)groups.size();
+    std::vector<int64_t> gs(G), gb(G), go(G);
+    std::vector<uint32_t> gk(G);
+    for (int i = 0; i < G; ++i) {
+      gs[i] = groups[i].start;
+      gb[i] = groups[i].slab_base;
+      go[i] = groups[i].off32;
+      gk[i] = groups[i].key;
+    }
+    BS_TRY(cudaMalloc(&g_start_d, sizeof(int64_t) * G));
+    BS_TRY(cudaMalloc(&g_slab_d, sizeof(int64_t) * G));
+    BS_TRY(cudaMalloc(&g_off_d, sizeof(int64_t) * G));
+    BS_TRY(cudaMalloc(&g_key_d, sizeof(uint32_t) * G));
+    BS_TRY(cudaMemcpyAsync(g_start_d, gs.data(), sizeof(int64_t) * G, cudaMemcpyHostToDevice, stream));
+    BS_TRY(cudaMemcpyAsync(g_slab_d, gb.data(), sizeof(int64_t) * G, cudaMemcpyHostToDevice, stream));
+    BS_TRY(cudaMemcpyAsync(g_off_d, go.data(), sizeof(int64_t) * G, cudaMemcpyHostToDevice, stream));
+    BS_TRY(cudaMemcpyAsync(g_key_d, gk.data(), sizeof(uint32_t) * G, cudaMemcpyHostToDevice, stream));
+    const int tb = 128;
+    const unsigned nb = (unsigned)((n_short + tb - 1) / tb);
+    if (p->row_bits == 16)
+      fill_slabs_kernel<IdxT, unsigned short><<<nb, tb, 0, stream>>>(ccol, row, d->a_dev, d->c_dev, perm, n_short, g_start_d,
+                                                                      g_slab_d, g_off_d, g_key_d, G, p->a_t, p->c_t,
+                                                                      (unsigned short*)p->row_t, p->hdr, p->orig_start, p->m, bad);
     else
-      build_passes_kernel<IdxT, true, false><<<nb, tb, 0, stream>>>(ccol, d->col_class_dev, p->n_cols, n_chunks, nullptr,
-                                                                    offsets, p->entries, p->cls_ne, p->longcols, bad);
+      fill_slabs_kernel<IdxT, uint32_t><<<nb, tb, 0, stream>>>(ccol, row, d->a_dev, d->c_dev, perm, n_short, g_start_d, g_slab_d,
+                                                                g_off_d, g_key_d, G, p->a_t, p->c_t, (uint32_t*)p->row_t,
+                                                                p->hdr, p->orig_start, p->m, bad);
+    BS_TRY(cudaStreamSynchronize(stream));  // host vectors go out of scope
+  }
+  if (n_long > 0) {
+    BS_TRY(cudaMalloc(&p->longcols, sizeof(LongCol) * n_long));
+    const int tb = 128;
+    long_meta_kernel<IdxT><<<(unsigned)((n_long + tb - 1) / tb), tb, 0, stream>>>(ccol, d->col_class_dev, perm + long_start,
+                                                                                  n_long, p->longcols);
+    std::vector<LongCol> lc(n_long);
+    BS_TRY(cudaMemcpyAsync(lc.data(), p->longcols, sizeof(LongCol) * n_long, cudaMemcpyDeviceToHost, stream));
+    BS_TRY(cudaStreamSynchronize(stream));
+    int64_t tot = 0;
+    for (auto& c : lc) {
+      c.off = tot;
+      tot += c.len;
+    }
+    BS_TRY(cudaMemcpyAsync(p->longcols, lc.data(), sizeof(LongCol) * n_long, cudaMemcpyHostToDevice, stream));
+    BS_TRY(cudaMalloc(&p->long_a, sizeof(float) * tot));
+    BS_TRY(cudaMalloc(&p->long_c, sizeof(float) * tot));
+    BS_TRY(cudaMalloc(&p->long_row, sizeof(uint32_t) * tot));
+    p->owned_bytes += 12 * (size_t)tot + sizeof(LongCol) * n_long;
+    const int blocks = (int)std::min<int64_t>((n_long + 3) / 4, (int64_t)p->n_sms * 16);
+    long_copy_kernel<IdxT><<<blocks, 128, 0, stream>>>(p->longcols, n_long, row, d->a_dev, d->c_dev, p->long_a, p->long_c,
+                                                       p->long_row, p->m, bad);
+    BS_TRY(cudaStreamSynchronize(stream));
   }
   unsigned int bad_h = 0;
-  DUALIP_CUDA_TRY(cudaMemcpyAsync(&bad_h, bad, sizeof(bad_h), cudaMemcpyDeviceToHost, stream));
-  DUALIP_CUDA_TRY(cudaStreamSynchronize(stream));
-  cudaFree(counts);
-  cudaFree(offsets);
-  cudaFree(tmp_in);
-  cudaFree(tmp_out);
-  cudaFree(cub_tmp);
-  cudaFree(bad);
+  BS_TRY(cudaMemcpyAsync(&bad_h, bad, sizeof(bad_h), cudaMemcpyDeviceToHost, stream));
+  BS_TRY(cudaStreamSynchronize(stream));
+  cleanup();
+#undef BS_TRY
   if (bad_h) {
-    set_error("ccol_indices must be non-decreasing (flags=%u)", bad_h);
+    set_error("row index out of range [0,%d)", p->m);
     return DUALIP_EINVAL;
   }
-  return DUALIP_OK;
+  return rc;
 }
 
 }  // namespace dualip
@@ -890,10 +1086,15 @@ const char* dualip_last_error(void) { return g_last_error.c_str(); }
 void dualip_plan_destroy(dualip_plan* p) {
   if (!p) return;
   DeviceGuard g(p->device);
-  cudaFree(p->row);
-  cudaFree(p->entries);
-  cudaFree(p->cls_ne);
+  cudaFree(p->a_t);
+  cudaFree(p->c_t);
+  cudaFree(p->row_t);
+  cudaFree(p->hdr);
+  cudaFree(p->orig_start);
   cudaFree(p->longcols);
+  cudaFree(p->long_a);
+  cudaFree(p->long_c);
+  cudaFree(p->long_row);
   cudaFree(p->classes_dev);
   cudaFree(p->acc);
   cudaFree(p->acc_scal);
@@ -922,11 +1123,11 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
     set_error("n_classes must be in 1..%d", kMaxClasses);
     return DUALIP_EINVAL;
   }
-  if (d->nnz >= (1LL << 32)) {
-    set_error("nnz >= 2^32 per shard is not supported by this build; shard the columns");
+  if (d->n_cols >= (1LL << 31)) {
+    set_error("more than 2^31-1 columns per shard is not supported by this build; shard the columns");
     return DUALIP_ERANGE;
   }
-  if (d->nnz > 0 && (!d->ccol_dev || !d->row_dev || !d->a_dev || !d->c_dev)) {
+  if (!d->ccol_dev || (d->nnz > 0 && (!d->row_dev || !d->a_dev || !d->c_dev))) {
     set_error("null CSC array");
     return DUALIP_EINVAL;
   }
@@ -952,9 +1153,6 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   p->n_cols = d->n_cols;
   p->nnz = d->nnz;
   p->m = d->n_rows;
-  p->a = d->a_dev;
-  p->c = d->c_dev;
-  p->uniform = (d->col_class_dev == nullptr);
   p->n_classes = d->n_classes;
   memcpy(p->classes_host, d->classes, sizeof(dualip_proj_class) * d->n_classes);
   const char* fb = getenv("DUALIP_FLUSH");
@@ -998,6 +1196,7 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   }
   const char* env_ctas = getenv("DUALIP_CTAS");
   if (env_ctas && atoi(env_ctas) > 0) p->n_ctas = atoi(env_ctas);
+  p->row_bits = (p->m <= 65536) ? 16 : 32;
 
 #define DUALIP_TRY_FAIL(expr)                                                                    \
   do {                                                                                           \
@@ -1008,43 +1207,15 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
     }                                                                                            \
   } while (0)
 
-  // narrowed row indices (owned)
-  p->row_bits = (p->m <= 65536) ? 16 : 32;
   {
-    const size_t rb = (size_t)(p->row_bits / 8) * (size_t)std::max<int64_t>(p->nnz, 1) + 64;
-    DUALIP_TRY_FAIL(cudaMalloc(&p->row, rb));
-    p->owned_bytes += rb;
-    unsigned int* bad = nullptr;
-    DUALIP_TRY_FAIL(cudaMalloc(&bad, sizeof(unsigned int)));
-    DUALIP_TRY_FAIL(cudaMemsetAsync(bad, 0, sizeof(unsigned int), stream));
-    if (p->nnz > 0) {
-      const int tb = 256;
-      const int nb = (int)std::min<int64_t>((p->nnz + tb - 1) / tb, (int64_t)p->n_sms * 16);
-      if (d->index_bits == 64) {
-        if (p->row_bits == 16)
-          narrow_rows_kernel<long long, unsigned short><<<nb, tb, 0, stream>>>((const long long*)d->row_dev, (unsigned short*)p->row, p->nnz, p->m, bad);
-        else
-          narrow_rows_kernel<long long, uint32_t><<<nb, tb, 0, stream>>>((const long long*)d->row_dev, (uint32_t*)p->row, p->nnz, p->m, bad);
-      } else {
-        if (p->row_bits == 16)
-          narrow_rows_kernel<int, unsigned short><<<nb, tb, 0, stream>>>((const int*)d->row_dev, (unsigned short*)p->row, p->nnz, p->m, bad);
-        else
-          narrow_rows_kernel<int, uint32_t><<<nb, tb, 0, stream>>>((const int*)d->row_dev, (uint32_t*)p->row, p->nnz, p->m, bad);
-      }
-    }
-    unsigned int bad_h = 0;
-    DUALIP_TRY_FAIL(cudaMemcpyAsync(&bad_h, bad, sizeof(bad_h), cudaMemcpyDeviceToHost, stream));
-    DUALIP_TRY_FAIL(cudaStreamSynchronize(stream));
-    cudaFree(bad);
-    if (bad_h) {
-      set_error("row index out of range [0,%d)", p->m);
-      return fail(DUALIP_EINVAL);
-    }
-  }
-  // pass table
-  {
-    int rc = (d->index_bits == 64) ? build_passes<long long>(p, d, stream) : build_passes<int>(p, d, stream);
+    int rc = (d->index_bits == 64) ? build_slabs<long long>(p, d, stream) : build_slabs<int>(p, d, stream);
     if (rc != DUALIP_OK) return fail(rc);
+  }
+  // do not launch more warps than there are slabs (tiny problems)
+  {
+    const int64_t warps_per_cta = p->threads / 32;
+    const int64_t want = std::max<int64_t>(1, (p->n_slabs + warps_per_cta - 1) / warps_per_cta);
+    if (!(env_ctas && atoi(env_ctas) > 0) && want < p->n_ctas) p->n_ctas = (int)want;
   }
   // small state
   DUALIP_TRY_FAIL(cudaMalloc(&p->classes_dev, sizeof(dualip_proj_class) * p->n_classes));
@@ -1060,7 +1231,7 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   DUALIP_TRY_FAIL(cudaMalloc(&p->scal_stage, sizeof(dualip_scalars)));
   p->owned_bytes += sizeof(float) * 3 * (m_pad + 4) + 64;
 
-  PassKernel kern = plan_kernel(p);
+  SlabKernel kern = plan_kernel(p);
   if (!kern) {
     set_error("no kernel variant");
     return fail(DUALIP_EINVAL);
@@ -1077,9 +1248,9 @@ int dualip_plan_info(const dualip_plan* p, int64_t* out, int cap) {
     set_error("null argument");
     return DUALIP_EINVAL;
   }
-  const int64_t v[10] = {p->n_passes, p->n_long, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
-                         p->smode,    p->run_len, (p->n_long > 0) ? 2 : 1, (int64_t)p->owned_bytes};
-  for (int i = 0; i < cap && i < 10; ++i) out[i] = v[i];
+  const int64_t v[12] = {p->n_slabs, p->n_long, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
+                         p->smode,   p->rows32 * kSlabW, (p->n_long > 0) ? 2 : 1, (int64_t)p->owned_bytes, p->n_short, p->nnz};
+  for (int i = 0; i < cap && i < 12; ++i) out[i] = v[i];
   return DUALIP_OK;
 }
 

@@ -104,7 +104,7 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
     """Dual gradient, objective and regularisation penalty of a matching LP on one GPU.
 
     Drop-in for the reference class of the same name (matching.py:37-188): same constructor, same `calculate`
-    keywords, same ObjectiveResult fields.  Construction builds the device-side pass table
+    keywords, same ObjectiveResult fields.  Construction builds the device-side slab layout
     (dualip_plan_create); `calculate` is one fused kernel launch."""
 
     def __init__(self, matching_input_args: MatchingInputArgs, gamma: float, batching: bool = True):
@@ -167,10 +167,10 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
 
     # -- introspection -------------------------------------------------------------------------------------
     def plan_info(self) -> dict:
-        buf = (ctypes.c_int64 * 10)()
-        _native.check(_native.lib().dualip_plan_info(self._plan, buf, 10))
-        names = ["n_passes", "n_long_cols", "n_ctas", "threads", "smem_bytes", "row_bits", "smem_mode", "run_len",
-                 "launches_per_calc", "owned_bytes"]
+        buf = (ctypes.c_int64 * 12)()
+        _native.check(_native.lib().dualip_plan_info(self._plan, buf, 12))
+        names = ["n_slabs", "n_long_cols", "n_ctas", "threads", "smem_bytes", "row_bits", "smem_mode", "slab_elems",
+                 "launches_per_calc", "owned_bytes", "n_slab_cols", "nnz"]
         return dict(zip(names, list(buf)))
 
     def algorithmic_bytes(self, save_primal: bool = False) -> int:

@@ -61,9 +61,10 @@ typedef struct dualip_csc_desc {
   int32_t n_rows;          /* dual dimension m                                          */
   int32_t index_bits;      /* 32 or 64: width of ccol_dev[] and row_dev[] entries       */
   const void* ccol_dev;    /* n_cols+1 column pointers, non-decreasing, ccol[0]=0       */
-  const void* row_dev;     /* nnz row indices in [0,m)  (copied, narrowed; not retained) */
-  const float* a_dev;      /* nnz values of A   (BORROWED: must outlive the plan)        */
-  const float* c_dev;      /* nnz values of c   (BORROWED: must outlive the plan)        */
+  const void* row_dev;     /* nnz row indices in [0,m)                                   */
+  const float* a_dev;      /* nnz values of A                                            */
+  const float* c_dev;      /* nnz values of c                                            */
+                           /* all four arrays are COPIED into the plan's own layout; the caller may free them */
   const uint8_t* col_class_dev; /* n_cols class ids into classes[], or NULL = all columns class 0 */
   const dualip_proj_class* classes; /* host array                                        */
   int32_t n_classes;       /* 1..255                                                    */
@@ -90,15 +91,15 @@ typedef struct dualip_scalars {
 int dualip_abi_version(void);
 const char* dualip_last_error(void);
 
-/* Build the device-side pass table for a shard (setup time; synchronises).  Replaces
+/* Build the device-side slab layout for a shard (setup time; synchronises).  Replaces
  * MatchingSolverDualObjectiveFunction.__init__ / _compute_buckets (matching.py:43-114). */
 int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* desc);
 void dualip_plan_destroy(dualip_plan* plan);
 
 /* Introspection: fills up to `cap` int64 values:
- * [0] n_passes [1] n_long_cols [2] n_ctas [3] threads/cta [4] smem bytes/cta [5] row index bits
- * [6] smem mode (0: lambda+grad in smem, 1: grad in smem, 2: neither) [7] passes per run
- * [8] kernel launches per calc  [9] plan-owned device bytes */
+ * [0] n_slabs [1] n_long_cols [2] n_ctas [3] threads/cta [4] smem bytes/cta [5] row index bits
+ * [6] smem mode (0: lambda+grad in smem, 1: grad in smem, 2: neither) [7] stored slab elements (incl. padding)
+ * [8] kernel launches per calc  [9] plan-owned device bytes [10] columns stored in slabs [11] nnz */
 int dualip_plan_info(const dualip_plan* plan, int64_t* out, int cap);
 
 /* One evaluation of the dual at lambda on this shard, epilogue included (single device).
