@@ -41,6 +41,7 @@ void set_error(const char* fmt, ...) {
 
 constexpr int kSlabW = 32;            // columns per slab = lanes per warp
 constexpr int kMaxThreadDeg = 1024;   // longest column handled one-lane-per-column
+constexpr int kStashDeg = 16;          // simplex columns up to this length keep u in the warp's shared-memory stash
 constexpr int kDegBits = 11;          // key = class << kDegBits | degree
 constexpr uint32_t kKeyEmpty = (255u << kDegBits) | 2047u;
 constexpr uint32_t kKeyLong = (255u << kDegBits) | 2046u;
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   const int m = k.m;
   const int m_pad = (m + 3) & ~3;
   float* s_grad = s_lam + (SMODE == 0 ? m_pad : 0);
+  float* s_stash = s_grad + (SMODE <= 1 ? m_pad : 0);  // kStashDeg x 32 floats per warp
   __shared__ unsigned int s_ticket;
 
   const unsigned FULL = 0xffffffffu;
@@ -397,86 +399,108 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
         cxs = fmaf(c, x, cxs);
         xxs = fmaf(x, x, xxs);
       };
-      int kk = 0;
-      for (; kk + 4 <= d; kk += 4) {
-        float a4[4], c4[4];
-        uint32_t r4[4];
+      // batches of 8, then 4/2/1 for the tail: every batch issues all of its loads before the first use
+      auto batch = [&](auto n_tag, int k0) {
+        constexpr int N = decltype(n_tag)::value;
+        float a4[N], c4[N];
+        uint32_t r4[N];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          a4[q] = __ldg(pa + (size_t)(kk + q) * kSlabW);
-          c4[q] = __ldg(pcv + (size_t)(kk + q) * kSlabW);
-          r4[q] = __ldg(pr + (size_t)(kk + q) * kSlabW);
+        for (int q = 0; q < N; ++q) {
+          a4[q] = __ldg(pa + (size_t)(k0 + q) * kSlabW);
+          c4[q] = __ldg(pcv + (size_t)(k0 + q) * kSlabW);
+          r4[q] = __ldg(pr + (size_t)(k0 + q) * kSlabW);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) body(a4[q], c4[q], r4[q]);
-        if ((kk & 63) == 60) {  // keep the fp32 partials short
+        for (int q = 0; q < N; ++q) body(a4[q], c4[q], r4[q]);
+      };
+      int kk = 0;
+      for (; kk + 8 <= d; kk += 8) {
+        batch(std::integral_constant<int, 8>{}, kk);
+        if ((kk & 63) == 56) {  // keep the fp32 partials short
           cx += (double)cxs;
           xx += (double)xxs;
           cxs = 0.f;
           xxs = 0.f;
         }
       }
-      for (; kk < d; ++kk)
-        body(__ldg(pa + (size_t)kk * kSlabW), __ldg(pcv + (size_t)kk * kSlabW), __ldg(pr + (size_t)kk * kSlabW));
+      if (d & 4) {
+        batch(std::integral_constant<int, 4>{}, kk);
+        kk += 4;
+      }
+      if (d & 2) {
+        batch(std::integral_constant<int, 2>{}, kk);
+        kk += 2;
+      }
+      if (d & 1) batch(std::integral_constant<int, 1>{}, kk);
     } else {
       // ---- simplex (simplex.py:143-236 per column at its true length) ----
-      // Pass 1 streams the column once and keeps the column sum, the number of positive entries and the three
-      // largest entries with their positions.  That decides feasible / top-2 shortcut, and resolves the sorted scan in
-      // closed form whenever the support has at most two entries (the usual case); otherwise the lane falls back to a
-      // re-streaming threshold search.
+      // Pass 1 streams the column once: column sum, the two largest entries with their positions, the third largest
+      // value, and (for d <= kStashDeg) a copy of u in this warp's shared-memory stash.  That decides feasible / top-2
+      // shortcut and resolves the sorted scan in closed form when the support has at most two entries.  Lanes with a
+      // larger support run a Michelot threshold search on the stash; lanes with more than two non-zeros take pass 2.
       const float z = pc.z;
+      const bool stash = d <= kStashDeg;
+      float* __restrict__ su = s_stash + (size_t)warp * (kStashDeg * kSlabW) + lane;
       auto u_at = [&](int kq) -> float {
+        if (stash) return su[kq * kSlabW];
         const float a = __ldg(pa + (size_t)kq * kSlabW);
         const float c = __ldg(pcv + (size_t)kq * kSlabW);
         const uint32_t r = __ldg(pr + (size_t)kq * kSlabW);
         return fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);  // simplex.py:148
       };
       float S = 0.f, m1 = -1.f, m2 = -1.f, m3 = -1.f;
-      int i2 = 0, i3 = 0, npos = 0;
+      int i2 = 0;
       auto track = [&](float a, float c, uint32_t r, int kq) {
         const float u = fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);
+        if (stash) su[kq * kSlabW] = u;
         S = __fadd_rn(S, u);  // column sum in entry order
-        npos += (u > 0.f) ? 1 : 0;
-        const bool g1 = u > m1, g2 = u > m2, g3 = u > m3;
-        m3 = g2 ? m2 : (g3 ? u : m3);
-        i3 = g2 ? i2 : (g3 ? kq : i3);
+        const bool g1 = u > m1, g2 = u > m2;
+        m3 = fmaxf(m3, fminf(m2, u));
         m2 = g1 ? m1 : (g2 ? u : m2);
         i2 = g1 ? i1 : (g2 ? kq : i2);
         m1 = g1 ? u : m1;
         i1 = g1 ? kq : i1;
       };
-      int kk = 0;
-      for (; kk + 4 <= d; kk += 4) {
-        float a4[4], c4[4];
-        uint32_t r4[4];
+      auto batch = [&](auto n_tag, int k0) {
+        constexpr int N = decltype(n_tag)::value;
+        float a4[N], c4[N];
+        uint32_t r4[N];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          a4[q] = __ldg(pa + (size_t)(kk + q) * kSlabW);
-          c4[q] = __ldg(pcv + (size_t)(kk + q) * kSlabW);
-          r4[q] = __ldg(pr + (size_t)(kk + q) * kSlabW);
+        for (int q = 0; q < N; ++q) {
+          a4[q] = __ldg(pa + (size_t)(k0 + q) * kSlabW);
+          c4[q] = __ldg(pcv + (size_t)(k0 + q) * kSlabW);
+          r4[q] = __ldg(pr + (size_t)(k0 + q) * kSlabW);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) track(a4[q], c4[q], r4[q], kk + q);
+        for (int q = 0; q < N; ++q) track(a4[q], c4[q], r4[q], k0 + q);
+      };
+      int kk = 0;
+      for (; kk + 8 <= d; kk += 8) batch(std::integral_constant<int, 8>{}, kk);
+      if (d & 4) {
+        batch(std::integral_constant<int, 4>{}, kk);
+        kk += 4;
       }
-      for (; kk < d; ++kk)
-        track(__ldg(pa + (size_t)kk * kSlabW), __ldg(pcv + (size_t)kk * kSlabW), __ldg(pr + (size_t)kk * kSlabW), kk);
+      if (d & 2) {
+        batch(std::integral_constant<int, 2>{}, kk);
+        kk += 2;
+      }
+      if (d & 1) batch(std::integral_constant<int, 1>{}, kk);
 
       const bool feasible = (pc.kind == DUALIP_PROJ_SIMPLEX) && (S <= pc.z_thr);                    // simplex.py:153-155
       const bool padded = (d > 1) || !(pc.flags & DUALIP_PROJ_FLAG_D1_UNPADDED);                    // simplex.py:166
-      const float m2p = fmaxf(m2, 0.f);  // the reference's zero padding takes part in its top-2
+      const float m2p = fmaxf(m2, 0.f), m3p = fmaxf(m3, 0.f);  // the reference's zero padding takes part in its top-2
       const float un1 = (z == 1.0f) ? m1 : __fdiv_rn(m1, z), un2 = (z == 1.0f) ? m2p : __fdiv_rn(m2p, z);
       const bool shortcut = !feasible && padded && (__fsub_rn(un1, un2) > 1.0f);                    // simplex.py:172-178
-      // up to three (position, x) results per lane
-      float x1 = 0.f, x2 = 0.f, x3 = 0.f;
-      bool general = false;
+      float x1 = 0.f, x2 = 0.f;     // results for the two largest entries when they are the only non-zeros
+      bool need_theta = false;      // support of three or more: threshold search
+      bool need_p2 = false;         // more than two non-zeros: second streaming pass
       if (feasible) {
         branch = 0;
-        if (npos > 3) {
-          general = true;
+        if (m3p > 0.f) {
+          need_p2 = true;
         } else {
           x1 = m1;
-          x2 = fmaxf(m2, 0.f);
-          x3 = fmaxf(m3, 0.f);
+          x2 = m2p;
         }
       } else if (shortcut) {
         branch = 1;
@@ -485,28 +509,35 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       } else {
         branch = 2;
         // sorted scan restricted to the three largest: css_i = fl32(prefix sum in fp64), cond_i = u_(i) - (css_i - z)/i > 0
-        const float css2 = (float)((double)m1 + (double)fmaxf(m2, 0.f));
-        const float css3 = (float)((double)m1 + (double)fmaxf(m2, 0.f) + (double)fmaxf(m3, 0.f));
-        const float t2 = __fdiv_rn(__fsub_rn(css2, z), 2.0f), t3 = __fdiv_rn(__fsub_rn(css3, z), 3.0f);
-        const bool cond3 = (d >= 3) && (__fsub_rn(m3, t3) > 0.f);
+        const float css2 = (float)((double)m1 + (double)m2p);
+        const float t2 = __fmul_rn(__fsub_rn(css2, z), 0.5f);  // division by 2 is exact
         const bool cond2 = (d >= 2) && (__fsub_rn(m2, t2) > 0.f);
+        bool cond3 = false;
+        if (d >= 3 && m3p > __fsub_rn(__fsub_rn(m1, z), 1e-3f * fabsf(m1))) {  // cond_3 needs m3 > m1 - z (exactly)
+          const float css3 = (float)((double)m1 + (double)m2p + (double)m3p);
+          cond3 = __fsub_rn(m3p, __fdiv_rn(__fsub_rn(css3, z), 3.0f)) > 0.f;
+        }
         if (cond3) {
-          general = true;  // support of three or more entries
+          need_theta = true;
+          need_p2 = true;
         } else {
           rho = cond2 ? 2 : 1;
           theta = cond2 ? t2 : __fsub_rn(m1, z);                                                    // simplex.py:228-230
-          x1 = fmaxf(__fsub_rn(m1, theta), 0.f);                                                    // simplex.py:233
-          x2 = (d >= 2) ? fmaxf(__fsub_rn(m2, theta), 0.f) : 0.f;
-          x3 = (d >= 3) ? fmaxf(__fsub_rn(m3, theta), 0.f) : 0.f;
+          if (m3p > theta) {
+            need_p2 = true;  // rounding leaves a third entry above the threshold: take the general pass
+          } else {
+            x1 = fmaxf(__fsub_rn(m1, theta), 0.f);                                                  // simplex.py:233
+            x2 = (d >= 2) ? fmaxf(__fsub_rn(m2, theta), 0.f) : 0.f;
+          }
         }
       }
-      general = general && active;
+      need_theta = need_theta && active;
+      need_p2 = need_p2 && active;
       if (!active) {
         x1 = 0.f;
         x2 = 0.f;
-        x3 = 0.f;
       }
-      // accumulate the (at most three) non-zeros: their entries are re-read from lines this warp has just streamed
+      // non-zeros of the closed-form lanes: their entries are re-read from lines this warp has just streamed
       auto emit = [&](int kq, float x) {
         if (x != 0.f) {
           const float a = __ldg(pa + (size_t)kq * kSlabW);
@@ -518,85 +549,119 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
           xxs = fmaf(x, x, xxs);
         }
       };
-      emit(i1, x1);
+      if (__any_sync(FULL, x1 != 0.f)) emit(i1, x1);
       if (__any_sync(FULL, x2 != 0.f)) emit(i2, x2);
-      if (__any_sync(FULL, x3 != 0.f)) emit(i3, x3);
 
-      if (__any_sync(FULL, general)) {
-        // ---- fallback: Michelot fixed point by re-streaming, then alignment with the reference's fp32 conditions ----
-        const bool need = general && branch == 2;
-        if (__any_sync(FULL, need)) {
-          double t = (double)m1 - (double)z, ssum = 0.0;  // theta* >= max - z, so {u > max - z} contains the support
-          t = just_below(fmax(t, 0.0));
-          int cnt = 0, cnt_prev = -1;
-          auto recount = [&]() {
-            cnt = 0;
-            ssum = 0.0;
-            for (int kq = 0; kq < d; ++kq) {
-              const float u = u_at(kq);
-              if ((double)u > t) {
-                ++cnt;
-                ssum += (double)u;
-              }
+      if (__any_sync(FULL, need_theta)) {
+        // ---- Michelot fixed point, then alignment with the reference's fp32 conditions (simplex.py:207-231) ----
+        // theta* >= max - z, so {u > max - z} contains the support.  (double)u > t  <=>  u > round_down_to_float(t).
+        float tf = __double2float_rd(fmax((double)m1 - (double)z, 0.0));
+        tf = (tf > 0.f) ? __uint_as_float(__float_as_uint(tf) - 1u) : -1.f;  // just below: start from {u >= max - z}
+        int cnt = 0, cnt_prev = -1;
+        float fsum = 0.f;
+        for (int it = 0; it < 64; ++it) {
+          cnt = 0;
+          fsum = 0.f;
+          for (int kq = 0; kq < d; ++kq) {
+            const float u = u_at(kq);
+            if (u > tf) {
+              ++cnt;
+              fsum += u;
             }
-          };
-          for (int it = 0; it < 64; ++it) {
-            recount();
-            const bool done = !need || cnt == cnt_prev || cnt == 0;
-            if (!done) {
-              cnt_prev = cnt;
-              t = (ssum - (double)z) / (double)cnt;
-            }
-            if (__all_sync(FULL, done)) break;
           }
-          float th = 0.f;
-          for (int fix = 0; fix < 4; ++fix) {
-            float umin = INFINITY, uout = -INFINITY;
-            for (int kq = 0; kq < d; ++kq) {
-              const float u = u_at(kq);
-              const bool in = (double)u > t;
-              umin = in ? fminf(umin, u) : umin;
-              uout = in ? uout : fmaxf(uout, u);
-            }
-            th = __fdiv_rn(__fsub_rn((float)ssum, z), (float)max(cnt, 1));
-            bool changed = false;
-            if (need && cnt > 1 && !(__fsub_rn(umin, th) > 0.f)) {
-              t = (double)umin;  // cond_rho fails in the fp32 formula: drop the smallest support value(s)
-              changed = true;
-            } else if (need && uout > -INFINITY) {
-              const float t1 = __fdiv_rn(__fsub_rn((float)(ssum + (double)uout), z), (float)(cnt + 1));
-              if (__fsub_rn(uout, t1) > 0.f) {  // cond_{rho+1} holds: the support grows
-                t = just_below((double)uout);
-                changed = true;
-              }
-            }
-            if (!__any_sync(FULL, changed)) break;
-            if (changed) recount();
+          const bool done = !need_theta || cnt == cnt_prev || cnt == 0;
+          if (!done) {
+            cnt_prev = cnt;
+            tf = __double2float_rd(((double)fsum - (double)z) / (double)cnt);
           }
-          if (need) {
-            theta = th;
-            rho = max(cnt, 1);
-          }
+          if (__all_sync(FULL, done)) break;
         }
-        for (int kq = 0; kq < d; ++kq) {
-          if (general) {
-            const float a = __ldg(pa + (size_t)kq * kSlabW);
-            const float c = __ldg(pcv + (size_t)kq * kSlabW);
-            const uint32_t r = __ldg(pr + (size_t)kq * kSlabW);
-            const float u = fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);
-            const float x = (branch == 0) ? u : fmaxf(__fsub_rn(u, theta), 0.f);
+        double ssum = 0.0;
+        auto recount = [&]() {
+          cnt = 0;
+          ssum = 0.0;
+          for (int kq = 0; kq < d; ++kq) {
+            const float u = u_at(kq);
+            if (u > tf) {
+              ++cnt;
+              ssum += (double)u;
+            }
+          }
+        };
+        recount();
+        float th = 0.f;
+        for (int fix = 0; fix < 6; ++fix) {
+          float umin = INFINITY, uout = -INFINITY;
+          for (int kq = 0; kq < d; ++kq) {
+            const float u = u_at(kq);
+            const bool in = u > tf;
+            umin = in ? fminf(umin, u) : umin;
+            uout = in ? uout : fmaxf(uout, u);
+          }
+          th = __fdiv_rn(__fsub_rn((float)ssum, z), (float)max(cnt, 1));
+          bool changed = false;
+          if (need_theta && cnt > 1 && !(__fsub_rn(umin, th) > 0.f)) {
+            tf = umin;  // cond_rho fails in the fp32 formula: drop the smallest support value(s)
+            changed = true;
+          } else if (need_theta && uout > -INFINITY) {
+            const float t1 = __fdiv_rn(__fsub_rn((float)(ssum + (double)uout), z), (float)(cnt + 1));
+            if (__fsub_rn(uout, t1) > 0.f) {  // cond_{rho+1} holds: the support grows
+              tf = (uout > 0.f) ? __uint_as_float(__float_as_uint(uout) - 1u) : -1.f;
+              changed = true;
+            }
+          }
+          if (!__any_sync(FULL, changed)) break;
+          if (changed) recount();
+        }
+        if (need_theta) {
+          theta = th;
+          rho = max(cnt, 1);
+        }
+      }
+      if (__any_sync(FULL, need_p2)) {
+        // ---- pass 2: x_k = u_k (feasible) or max(u_k - theta, 0); re-reads lines this warp has just streamed ----
+        auto scatter = [&](float a, float c, uint32_t r, int kq) {
+          const float u = stash ? su[kq * kSlabW] : fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);
+          const float x = (branch == 0) ? u : fmaxf(__fsub_rn(u, theta), 0.f);
+          if (need_p2 && x != 0.f) {
             const float g = __fmul_rn(a, x);
             if (g != 0.f) grad_add<SMODE>(k, s_grad, r, g);
             cxs = fmaf(c, x, cxs);
             xxs = fmaf(x, x, xxs);
           }
-          if ((kq & 63) == 63) {
+        };
+        auto batch2 = [&](auto n_tag, int k0) {
+          constexpr int N = decltype(n_tag)::value;
+          float a4[N], c4[N];
+          uint32_t r4[N];
+#pragma unroll
+          for (int q = 0; q < N; ++q) {
+            a4[q] = __ldg(pa + (size_t)(k0 + q) * kSlabW);
+            c4[q] = __ldg(pcv + (size_t)(k0 + q) * kSlabW);
+            r4[q] = __ldg(pr + (size_t)(k0 + q) * kSlabW);
+          }
+#pragma unroll
+          for (int q = 0; q < N; ++q) scatter(a4[q], c4[q], r4[q], k0 + q);
+        };
+        int k2 = 0;
+        for (; k2 + 8 <= d; k2 += 8) {
+          batch2(std::integral_constant<int, 8>{}, k2);
+          if ((k2 & 63) == 56) {
             cx += (double)cxs;
             xx += (double)xxs;
             cxs = 0.f;
             xxs = 0.f;
           }
         }
+        if (d & 4) {
+          batch2(std::integral_constant<int, 4>{}, k2);
+          k2 += 4;
+        }
+        if (d & 2) {
+          batch2(std::integral_constant<int, 2>{}, k2);
+          k2 += 2;
+        }
+        if (d & 1) batch2(std::integral_constant<int, 1>{}, k2);
       }
     }
     cx += (double)cxs;
@@ -831,7 +896,6 @@ static SlabKernel pick_kernel(bool row16, int smode) {
 
 static SlabKernel plan_kernel(const dualip_plan* p) {
   const bool row16 = p->row_bits == 16;
-  if (p->threads == 512) return pick_kernel<512, 2>(row16, p->smode);
   return pick_kernel<1024, 1>(row16, p->smode);
 }
 
@@ -1170,12 +1234,17 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   }
   p->n_sms = prop.multiProcessorCount;
 
-  // shared-memory mode and CTA shape
+  // shared-memory mode and CTA shape: ONE 1024-thread CTA per SM.  lambda and the gradient accumulator are per CTA,
+  // so a single CTA halves their footprint (and the flush traffic) against two 512-thread CTAs, and leaves the rest
+  // of the 256 KB L1/shared array to the L1 that serves the second pass over a slab.
+  p->threads = 1024;
+  p->n_ctas = p->n_sms;
   const size_t fixed = smem_fixed_bytes(p->n_classes);
   const size_t m_pad = ((size_t)p->m + 3) & ~(size_t)3;
-  const size_t need0 = fixed + 4 * m_pad + 4 * (size_t)p->m;
-  const size_t need1 = fixed + 4 * (size_t)p->m;
-  const size_t smem_max = std::min<size_t>(kSmemBudget, prop.sharedMemPerBlockOptin);
+  const size_t stash_bytes = (size_t)(p->threads / 32) * kStashDeg * kSlabW * sizeof(float);
+  const size_t need0 = fixed + 8 * m_pad + stash_bytes;
+  const size_t need1 = fixed + 4 * m_pad + stash_bytes;
+  const size_t smem_max = std::min<size_t>(kSmemBudget, prop.sharedMemPerBlockOptin) - 1024;  // static smem + slack
   if (need0 <= smem_max) {
     p->smode = 0;
     p->smem_bytes = need0;
@@ -1184,15 +1253,7 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
     p->smem_bytes = need1;
   } else {
     p->smode = 2;
-    p->smem_bytes = fixed;
-  }
-  // two 512-thread CTAs per SM when both fit (each SM has 228 KB; 1 KB per CTA is reserved)
-  if (2 * (p->smem_bytes + 1024) <= prop.sharedMemPerMultiprocessor) {
-    p->threads = 512;
-    p->n_ctas = 2 * p->n_sms;
-  } else {
-    p->threads = 1024;
-    p->n_ctas = p->n_sms;
+    p->smem_bytes = fixed + stash_bytes;
   }
   const char* env_ctas = getenv("DUALIP_CTAS");
   if (env_ctas && atoi(env_ctas) > 0) p->n_ctas = atoi(env_ctas);
@@ -1236,7 +1297,13 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
     set_error("no kernel variant");
     return fail(DUALIP_EINVAL);
   }
-  DUALIP_TRY_FAIL(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+  // the attribute is per function, not per plan: always allow the device maximum so that plans of different m coexist
+  {
+    cudaFuncAttributes fa;
+    DUALIP_TRY_FAIL(cudaFuncGetAttributes(&fa, (const void*)kern));
+    const int max_dyn = (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes;
+    DUALIP_TRY_FAIL(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  }
   DUALIP_TRY_FAIL(cudaDeviceSynchronize());
 #undef DUALIP_TRY_FAIL
   *out = p;
