@@ -441,13 +441,6 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       const float z = pc.z;
       const bool stash = d <= kStashDeg;
       float* __restrict__ su = s_stash + (size_t)warp * (kStashDeg * kSlabW) + lane;
-      auto u_at = [&](int kq) -> float {
-        if (stash) return su[kq * kSlabW];
-        const float a = __ldg(pa + (size_t)kq * kSlabW);
-        const float c = __ldg(pcv + (size_t)kq * kSlabW);
-        const uint32_t r = __ldg(pr + (size_t)kq * kSlabW);
-        return fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);  // simplex.py:148
-      };
       float S = 0.f, m1 = -1.f, m2 = -1.f, m3 = -1.f;
       int i2 = 0;
       auto track = [&](float a, float c, uint32_t r, int kq) {
@@ -491,6 +484,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       const float m2p = fmaxf(m2, 0.f), m3p = fmaxf(m3, 0.f);  // the reference's zero padding takes part in its top-2
       const float un1 = (z == 1.0f) ? m1 : __fdiv_rn(m1, z), un2 = (z == 1.0f) ? m2p : __fdiv_rn(m2p, z);
       const bool shortcut = !feasible && padded && (__fsub_rn(un1, un2) > 1.0f);                    // simplex.py:172-178
+      float t3lo = -1.f;            // lower bound on theta from the top-3 scan (threshold search start)
       float x1 = 0.f, x2 = 0.f;     // results for the two largest entries when they are the only non-zeros
       bool need_theta = false;      // support of three or more: threshold search
       bool need_p2 = false;         // more than two non-zeros: second streaming pass
@@ -515,7 +509,9 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
         bool cond3 = false;
         if (d >= 3 && m3p > __fsub_rn(__fsub_rn(m1, z), 1e-3f * fabsf(m1))) {  // cond_3 needs m3 > m1 - z (exactly)
           const float css3 = (float)((double)m1 + (double)m2p + (double)m3p);
-          cond3 = __fsub_rn(m3p, __fdiv_rn(__fsub_rn(css3, z), 3.0f)) > 0.f;
+          const float t3 = __fdiv_rn(__fsub_rn(css3, z), 3.0f);
+          cond3 = __fsub_rn(m3p, t3) > 0.f;
+          t3lo = __fsub_rd(t3, 4e-7f * fabsf(t3));
         }
         if (cond3) {
           need_theta = true;
@@ -554,114 +550,135 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
 
       if (__any_sync(FULL, need_theta)) {
         // ---- Michelot fixed point, then alignment with the reference's fp32 conditions (simplex.py:207-231) ----
-        // theta* >= max - z, so {u > max - z} contains the support.  (double)u > t  <=>  u > round_down_to_float(t).
-        float tf = __double2float_rd(fmax((double)m1 - (double)z, 0.0));
-        tf = (tf > 0.f) ? __uint_as_float(__float_as_uint(tf) - 1u) : -1.f;  // just below: start from {u >= max - z}
-        int cnt = 0, cnt_prev = -1;
-        float fsum = 0.f;
-        for (int it = 0; it < 64; ++it) {
-          cnt = 0;
-          fsum = 0.f;
-          for (int kq = 0; kq < d; ++kq) {
-            const float u = u_at(kq);
-            if (u > tf) {
-              ++cnt;
-              fsum += u;
+        // The sequence t_0 = (sum - z)/d <= t_1 <= ... increases to theta*, and theta* >= max - z, so the search
+        // starts from the larger of the two.  (double)u > t  <=>  u > round_down_to_float(t).
+        auto search = [&](auto stash_tag) {
+          constexpr bool ST = decltype(stash_tag)::value;
+          auto uq = [&](int kq) -> float {
+            if (ST) return su[kq * kSlabW];
+            const float a = __ldg(pa + (size_t)kq * kSlabW);
+            const float c = __ldg(pcv + (size_t)kq * kSlabW);
+            const uint32_t r = __ldg(pr + (size_t)kq * kSlabW);
+            return fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);
+          };
+          // Newton steps from below on f(t) = sum max(u - t, 0) - z (Michelot): t <- (sum_{u>t} u - z)/#{u>t}.  Lower
+          // bounds to start from: (S - z)/d, max - z, and the top-3 scan value t3 (the scan thresholds increase while
+          // their conditions hold).  fp32 sums are scaled down by `guard` so that no step overshoots theta*.
+          const float guard = 1.0f - 2.4e-7f * (float)d;
+          float tf = fmaxf(fmaxf(__fdiv_rd(__fsub_rd(__fmul_rd(S, guard), z), (float)d), __fsub_rd(m1, z)), t3lo);
+          tf = (tf > 0.f) ? __uint_as_float(__float_as_uint(tf) - 1u) : -1.f;  // strictly below the bound
+          int cnt = 0;
+          for (int it = 0; it < 64; ++it) {
+            cnt = 0;
+            float fsum = 0.f, umin = INFINITY;
+#pragma unroll 4
+            for (int kq = 0; kq < d; ++kq) {
+              const float u = uq(kq);
+              const bool in = u > tf;
+              cnt += in ? 1 : 0;
+              fsum += in ? u : 0.f;
+              umin = in ? fminf(umin, u) : umin;
             }
+            // next step; converged when it removes nothing, i.e. the smallest support value stays above it
+            const float tn = __fdiv_rd(__fsub_rd(__fmul_rd(fsum, guard), z), (float)max(cnt, 1));
+            const bool done = !need_theta || cnt == 0 || !(tn > tf) || umin > tn;
+            if (!done) tf = tn;
+            if (__all_sync(FULL, done)) break;
           }
-          const bool done = !need_theta || cnt == cnt_prev || cnt == 0;
-          if (!done) {
-            cnt_prev = cnt;
-            tf = __double2float_rd(((double)fsum - (double)z) / (double)cnt);
-          }
-          if (__all_sync(FULL, done)) break;
-        }
-        double ssum = 0.0;
-        auto recount = [&]() {
-          cnt = 0;
-          ssum = 0.0;
-          for (int kq = 0; kq < d; ++kq) {
-            const float u = u_at(kq);
-            if (u > tf) {
-              ++cnt;
-              ssum += (double)u;
+          // exact sums over the support and the two boundary values, then the reference's own conditions
+          float th = 0.f;
+          for (int fix = 0; fix < 6; ++fix) {
+            double ssum = 0.0;
+            float umin = INFINITY, uout = -INFINITY;
+            cnt = 0;
+#pragma unroll 2
+            for (int kq = 0; kq < d; ++kq) {
+              const float u = uq(kq);
+              const bool in = u > tf;
+              cnt += in ? 1 : 0;
+              ssum += in ? (double)u : 0.0;
+              umin = in ? fminf(umin, u) : umin;
+              uout = in ? uout : fmaxf(uout, u);
             }
+            th = __fdiv_rn(__fsub_rn((float)ssum, z), (float)max(cnt, 1));
+            bool changed = false;
+            if (need_theta && cnt > 1 && !(__fsub_rn(umin, th) > 0.f)) {
+              tf = umin;  // cond_rho fails in the fp32 formula: drop the smallest support value(s)
+              changed = true;
+            } else if (need_theta && uout > -INFINITY) {
+              const float t1 = __fdiv_rn(__fsub_rn((float)(ssum + (double)uout), z), (float)(cnt + 1));
+              if (__fsub_rn(uout, t1) > 0.f) {  // cond_{rho+1} holds: the support grows
+                tf = (uout > 0.f) ? __uint_as_float(__float_as_uint(uout) - 1u) : -1.f;
+                changed = true;
+              }
+            }
+            if (!__any_sync(FULL, changed)) break;
+          }
+          if (need_theta) {
+            theta = th;
+            rho = max(cnt, 1);
           }
         };
-        recount();
-        float th = 0.f;
-        for (int fix = 0; fix < 6; ++fix) {
-          float umin = INFINITY, uout = -INFINITY;
-          for (int kq = 0; kq < d; ++kq) {
-            const float u = u_at(kq);
-            const bool in = u > tf;
-            umin = in ? fminf(umin, u) : umin;
-            uout = in ? uout : fmaxf(uout, u);
-          }
-          th = __fdiv_rn(__fsub_rn((float)ssum, z), (float)max(cnt, 1));
-          bool changed = false;
-          if (need_theta && cnt > 1 && !(__fsub_rn(umin, th) > 0.f)) {
-            tf = umin;  // cond_rho fails in the fp32 formula: drop the smallest support value(s)
-            changed = true;
-          } else if (need_theta && uout > -INFINITY) {
-            const float t1 = __fdiv_rn(__fsub_rn((float)(ssum + (double)uout), z), (float)(cnt + 1));
-            if (__fsub_rn(uout, t1) > 0.f) {  // cond_{rho+1} holds: the support grows
-              tf = (uout > 0.f) ? __uint_as_float(__float_as_uint(uout) - 1u) : -1.f;
-              changed = true;
-            }
-          }
-          if (!__any_sync(FULL, changed)) break;
-          if (changed) recount();
-        }
-        if (need_theta) {
-          theta = th;
-          rho = max(cnt, 1);
-        }
+        if (stash)
+          search(std::true_type{});
+        else
+          search(std::false_type{});
       }
       if (__any_sync(FULL, need_p2)) {
         // ---- pass 2: x_k = u_k (feasible) or max(u_k - theta, 0); re-reads lines this warp has just streamed ----
-        auto scatter = [&](float a, float c, uint32_t r, int kq) {
-          const float u = stash ? su[kq * kSlabW] : fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);
-          const float x = (branch == 0) ? u : fmaxf(__fsub_rn(u, theta), 0.f);
-          if (need_p2 && x != 0.f) {
-            const float g = __fmul_rn(a, x);
-            if (g != 0.f) grad_add<SMODE>(k, s_grad, r, g);
-            cxs = fmaf(c, x, cxs);
-            xxs = fmaf(x, x, xxs);
-          }
-        };
-        auto batch2 = [&](auto n_tag, int k0) {
-          constexpr int N = decltype(n_tag)::value;
-          float a4[N], c4[N];
-          uint32_t r4[N];
+        auto pass2 = [&](auto stash_tag) {
+          constexpr bool ST = decltype(stash_tag)::value;
+          auto scatter = [&](float a, float c, uint32_t r, int kq) {
+            float u;
+            if (ST)
+              u = su[kq * kSlabW];
+            else
+              u = fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);
+            const float x = (branch == 0) ? u : fmaxf(__fsub_rn(u, theta), 0.f);
+            if (need_p2 && x != 0.f) {
+              const float g = __fmul_rn(a, x);
+              if (g != 0.f) grad_add<SMODE>(k, s_grad, r, g);
+              cxs = fmaf(c, x, cxs);
+              xxs = fmaf(x, x, xxs);
+            }
+          };
+          auto batch2 = [&](auto n_tag, int k0) {
+            constexpr int N = decltype(n_tag)::value;
+            float a4[N], c4[N];
+            uint32_t r4[N];
 #pragma unroll
-          for (int q = 0; q < N; ++q) {
-            a4[q] = __ldg(pa + (size_t)(k0 + q) * kSlabW);
-            c4[q] = __ldg(pcv + (size_t)(k0 + q) * kSlabW);
-            r4[q] = __ldg(pr + (size_t)(k0 + q) * kSlabW);
-          }
+            for (int q = 0; q < N; ++q) {
+              a4[q] = __ldg(pa + (size_t)(k0 + q) * kSlabW);
+              c4[q] = __ldg(pcv + (size_t)(k0 + q) * kSlabW);
+              r4[q] = __ldg(pr + (size_t)(k0 + q) * kSlabW);
+            }
 #pragma unroll
-          for (int q = 0; q < N; ++q) scatter(a4[q], c4[q], r4[q], k0 + q);
-        };
-        int k2 = 0;
-        for (; k2 + 8 <= d; k2 += 8) {
-          batch2(std::integral_constant<int, 8>{}, k2);
-          if ((k2 & 63) == 56) {
-            cx += (double)cxs;
-            xx += (double)xxs;
-            cxs = 0.f;
-            xxs = 0.f;
+            for (int q = 0; q < N; ++q) scatter(a4[q], c4[q], r4[q], k0 + q);
+          };
+          int k2 = 0;
+          for (; k2 + 8 <= d; k2 += 8) {
+            batch2(std::integral_constant<int, 8>{}, k2);
+            if ((k2 & 63) == 56) {
+              cx += (double)cxs;
+              xx += (double)xxs;
+              cxs = 0.f;
+              xxs = 0.f;
+            }
           }
-        }
-        if (d & 4) {
-          batch2(std::integral_constant<int, 4>{}, k2);
-          k2 += 4;
-        }
-        if (d & 2) {
-          batch2(std::integral_constant<int, 2>{}, k2);
-          k2 += 2;
-        }
-        if (d & 1) batch2(std::integral_constant<int, 1>{}, k2);
+          if (d & 4) {
+            batch2(std::integral_constant<int, 4>{}, k2);
+            k2 += 4;
+          }
+          if (d & 2) {
+            batch2(std::integral_constant<int, 2>{}, k2);
+            k2 += 2;
+          }
+          if (d & 1) batch2(std::integral_constant<int, 1>{}, k2);
+        };
+        if (stash)
+          pass2(std::true_type{});
+        else
+          pass2(std::false_type{});
       }
     }
     cx += (double)cxs;
