@@ -1,0 +1,192 @@
+"""Host-side mirror of the reference API: registry, projection-map keys, sharding helpers, Maximizer on CPU objectives,
+step-size rule.  Modelled on the reference's tests/test_agd.py, tests/test_utils.py, tests/test_dist_utils.py."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from dualip_b200 import _native
+from dualip_b200.objectives.matching import MatchingInputArgs, MatchingSolverDualObjectiveFunction, _build_class_table
+from dualip_b200.optimizers.agd import AcceleratedGradientDescent, project_on_nn_cone
+from dualip_b200.optimizers.agd_utils import (
+    calculate_step_size,
+    estimate_lipschitz_constant,
+    step_size_from_lipschitz_constants,
+    update_dual_gradient_history,
+)
+from dualip_b200.projections import ProjectionEntry, create_projection_map, project
+from dualip_b200.run_solver import run_solver
+from dualip_b200.types import ComputeArgs, ObjectiveArgs, ObjectiveResult, SolverArgs, SolverResult
+from dualip_b200.utils.dist_utils import global_to_local_projection_map, shard_sizes, split_tensors_to_devices
+from dualip_b200.utils.sparse_utils import split_csc_by_cols
+from oracle import dualip_oracle as O
+
+
+# ---- types / defaults (reference types.py:7-50) ----
+def test_dataclass_defaults_match_reference():
+    s = SolverArgs()
+    assert (s.max_iter, s.initial_step_size, s.gamma, s.max_step_size) == (10000, 1e-5, 1e-3, 0.1)
+    assert s.initial_dual_path is None and s.gamma_decay_type is None and s.save_primal is False
+    assert ComputeArgs(host_device="cuda:0").compute_device_num == 1
+    o = ObjectiveArgs(objective_type="matching")
+    assert o.use_jacobi_precondition is False and o.objective_kwargs is None
+    r = ObjectiveResult(dual_gradient=torch.zeros(1), dual_objective=torch.tensor(0.0))
+    assert r.reg_penalty is None and r.primal_var is None and r.max_pos_slack is None
+    assert [f for f in SolverResult.__dataclass_fields__] == ["dual_val", "dual_objective", "objective_result",
+                                                               "dual_objective_log", "step_size_log"]
+
+
+# ---- projections registry (reference projections/base.py) ----
+def test_registry_and_keys():
+    assert project("box").native_class().kind == _native.PROJ_CLAMP
+    c = project("cone", lower=0.0).native_class()
+    assert c.lo == 0.0 and math.isinf(c.hi)
+    c = project("cone").native_class()
+    assert math.isinf(c.lo) and math.isinf(c.hi)
+    sx = project("simplex", z=2.0).native_class()
+    assert sx.kind == _native.PROJ_SIMPLEX and sx.z == 2.0 and sx.z_thr == float(np.float32(2.0 + 1e-6))
+    assert project("simplex_eq").native_class().kind == _native.PROJ_SIMPLEX_EQ
+    with pytest.raises(ValueError):
+        project("nope")
+    with pytest.raises(ValueError):
+        project("cone", lower=0.0, upper=1.0)
+    with pytest.raises(ValueError):
+        project("simplex", method="newton")
+    with pytest.raises(TypeError):
+        project("box", l=0, u=1)  # the reference's operators take lower/upper
+    pm = create_projection_map("simplex", {"z": 1}, 5)
+    assert list(pm) == ["simplex_z_1"] and list(pm["simplex_z_1"].indices) == [0, 1, 2, 3, 4]
+    pm = create_projection_map("box", {"upper": 1.0, "lower": 0.0}, 10, indices=[0, 2], key_prefix="p_")
+    assert list(pm) == ["p_box_lower_0.0_upper_1.0"] and pm["p_box_lower_0.0_upper_1.0"].indices == [0, 2]
+
+
+def test_projection_call_requires_cuda():
+    with pytest.raises(RuntimeError, match="CUDA"):
+        project("simplex")(torch.zeros(3, 2))
+
+
+def test_objective_requires_cuda_and_csc():
+    A = torch.eye(3).to_sparse_csc()
+    args = MatchingInputArgs(A, A, create_projection_map("simplex", {"z": 1.0}, 3), torch.ones(3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        MatchingSolverDualObjectiveFunction(args, gamma=1e-3)
+    with pytest.raises(ValueError):
+        MatchingSolverDualObjectiveFunction(MatchingInputArgs(torch.eye(3), A, {}, torch.ones(3)), gamma=1e-3)
+
+
+def test_class_table_from_projection_map():
+    ccol = torch.tensor([0, 1, 3, 3, 6, 7])  # lengths 1,2,0,3,1
+    pm = create_projection_map("simplex", {"z": 1.0}, 5)
+    classes, n, col_class = _build_class_table(ccol, 5, pm, batching=True)
+    assert n == 1 and col_class is None and classes[0].flags == 0  # a 2-entry column pads the {1,2} bucket
+    pm = {}
+    pm.update(create_projection_map("simplex", {"z": 1.0}, 5, indices=[0, 4]))
+    pm.update(create_projection_map("box", {"lower": 0.0, "upper": 1.0}, 5, indices=[1, 3]))
+    classes, n, col_class = _build_class_table(ccol, 5, pm, batching=True)
+    assert n == 3 and col_class.tolist() == [1, 2, 0, 2, 1]
+    assert classes[0].kind == _native.PROJ_CLAMP and math.isinf(classes[0].hi)  # identity for unlisted columns
+    assert classes[1].flags & _native.PROJ_FLAG_D1_UNPADDED  # its 1-entry columns have no 2-entry bucket mate
+    with pytest.raises(ValueError, match="overlaps"):
+        bad = dict(pm)
+        bad.update(create_projection_map("cone", {"lower": 0.0}, 5, indices=[3], key_prefix="x"))
+        _build_class_table(ccol, 5, bad, batching=True)
+    with pytest.raises(IndexError):
+        _build_class_table(ccol, 5, create_projection_map("box", {}, 5, indices=[7]), batching=True)
+
+
+# ---- sharding helpers (reference utils/dist_utils.py, tests/test_dist_utils.py) ----
+def test_shard_sizes_and_split():
+    assert shard_sizes(5, 2) == [3, 2] and shard_sizes(7, 3) == [3, 2, 2] and shard_sizes(6, 2) == [3, 3]
+    dense = torch.arange(30, dtype=torch.float32).reshape(5, 6) * (torch.rand(5, 6) > 0.3)
+    a = dense.to_sparse_csc()
+    parts = split_csc_by_cols(a, [2, 3, 1])
+    assert torch.equal(torch.cat([p.to_dense() for p in parts], dim=1), dense)
+    with pytest.raises(ValueError):
+        split_csc_by_cols(a, [2, 2])
+    a_s, c_s, index_map = split_tensors_to_devices(a, a, ["cpu", "cpu"])
+    assert a_s[0].shape == (5, 3) and c_s[1].shape == (5, 3) and index_map == [[0, 1, 2], [3, 4, 5]]
+    a_s, c_s, index_map = split_tensors_to_devices(a, a, [])
+    assert len(a_s) == 1 and index_map == list(range(6))
+
+
+def test_global_to_local_projection_map():
+    pm = create_projection_map("simplex_ineq", {"z": 1}, 6)  # the reference's test uses this unregistered name
+    loc = [global_to_local_projection_map(pm, cols) for cols in ([0, 1, 2], [3, 4, 5])]
+    assert list(loc[0]["simplex_ineq_z_1"].indices) == [0, 1, 2] and list(loc[1]["simplex_ineq_z_1"].indices) == [0, 1, 2]
+    pm = {**create_projection_map("simplex", {"z": 1}, 10, indices=[0, 1]),
+          **create_projection_map("simplex_eq", {"z": 2}, 10, indices=[2, 3, 4, 5, 6, 7, 8, 9])}
+    l0 = global_to_local_projection_map(pm, list(range(0, 5)))
+    l1 = global_to_local_projection_map(pm, range(5, 10))
+    assert l0["simplex_z_1"].indices == [0, 1] and l0["simplex_eq_z_2"].indices == [2, 3, 4]
+    assert "simplex_z_1" not in l1 and l1["simplex_eq_z_2"].indices == [0, 1, 2, 3, 4]
+    big = create_projection_map("box", {}, 10**9)  # range-based: no per-column dictionary
+    loc = global_to_local_projection_map(big, range(250_000_000, 500_000_000))
+    assert loc["box_"].indices == range(0, 250_000_000)
+
+
+# ---- Maximizer on host objectives (reference tests/test_agd.py) ----
+class _Quadratic2D:
+    equality_mask = None
+
+    def calculate(self, dual_val, save_primal=False, **kwargs):
+        x, y = dual_val
+        obj = -((x - 3.0) ** 2) - (y + 5.0) ** 2
+        return ObjectiveResult(dual_gradient=torch.tensor([-2.0 * (x - 3.0), -2.0 * (y + 5.0)]), dual_objective=obj)
+
+
+def test_agd_known_answers_on_cpu_objective():
+    solver = AcceleratedGradientDescent(max_iter=30, gamma=None, initial_step_size=1e-5, iteration_callback=lambda i, r: None)
+    res = solver.maximize(_Quadratic2D(), torch.tensor([0.0, 0.0]))
+    for i, true_val in [(2, -33.9996400036), (16, -28.60551547593112), (23, -25.473701313626133), (29, -25.00382134903756)]:
+        assert abs(res.dual_objective_log[i - 1] - true_val) < 1e-5
+    one = AcceleratedGradientDescent(max_iter=1, gamma=None, initial_step_size=0.1, iteration_callback=lambda i, r: None)
+    assert abs(float(one.maximize(_Quadratic2D(), torch.tensor([0.0, 0.0])).dual_val[0]) - 0.6) < 1e-6
+
+
+def test_beta_sequence_and_cone_projection():
+    s = AcceleratedGradientDescent(max_iter=50, gamma=1e-3)
+    assert np.array_equal(s.beta_seq.numpy(), O.compute_beta_seq(50))
+    y = torch.tensor([-1.0, 2.0, -3.0])
+    assert project_on_nn_cone(y).tolist() == [0.0, 2.0, 0.0]
+    assert project_on_nn_cone(y, torch.tensor([True, False, False])).tolist() == [-1.0, 2.0, 0.0]
+    with pytest.raises(ValueError):
+        AcceleratedGradientDescent(max_iter=2, gamma=1.0, gamma_decay_type="exp", gamma_decay_params={})._update_gamma(1, 0.1)
+
+
+def test_step_size_rule():
+    gh, dh = [], []
+    for k in range(3):
+        update_dual_gradient_history(torch.tensor([float(k)]), torch.tensor([float(k)]), gh, dh, 2)
+    assert len(gh) == 2 and gh[0].item() == 1.0
+    L = estimate_lipschitz_constant(torch.tensor([0.0]), torch.tensor([2.0]), torch.tensor([0.0]), torch.tensor([1.0]))
+    assert L.item() == 2.0
+    assert step_size_from_lipschitz_constants([L] * 3, 15, 1e-5, 0.1) == 1e-5  # history incomplete
+    assert step_size_from_lipschitz_constants([torch.tensor(float("nan"))] + [L] * 13, 15, 1e-5, 0.1) == 1e-5
+    assert step_size_from_lipschitz_constants([L] * 14, 15, 1e-5, 0.1) == 0.1  # 1/2 clamped to max_step_size
+    assert step_size_from_lipschitz_constants([torch.tensor(100.0)] * 14, 15, 1e-5, 0.1) == 0.01
+    assert step_size_from_lipschitz_constants([torch.tensor(0.0)] * 14, 15, 1e-5, 0.1) == 0.1
+    gh, dh = [], []
+    assert calculate_step_size(torch.tensor([1.0]), torch.tensor([0.0]), gh, dh) == 1e-5
+
+
+def test_run_solver_argument_errors():
+    A = torch.eye(3).to_sparse_csc()
+    args = MatchingInputArgs(A, A, create_projection_map("simplex", {"z": 1.0}, 3), torch.ones(3))
+    with pytest.raises(ValueError):
+        run_solver(args, SolverArgs(max_iter=1), ComputeArgs("cpu"), ObjectiveArgs("unknown"))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        run_solver(args, SolverArgs(max_iter=1), ComputeArgs("cpu"), ObjectiveArgs("matching"))
+
+
+def test_install_as_alias():
+    import importlib
+    import sys
+
+    import dualip_b200
+
+    dualip_b200.install_as("dualip_alias_for_test")
+    mod = importlib.import_module("dualip_alias_for_test.objectives.matching")
+    assert mod.MatchingInputArgs is MatchingInputArgs
+    for k in [k for k in sys.modules if k.startswith("dualip_alias_for_test")]:
+        del sys.modules[k]
