@@ -251,6 +251,9 @@ def run_native(args):
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    loop.kernel_events = kev  # FusedAscentLoop brackets the objective's kernel(s) of step W+j with kev[j]
+    loop.kernel_events_base = W + 1
     ev0.record()
     for i in range(W + 1, W + K + 1):
         loop.step(i)
@@ -263,52 +266,37 @@ def run_native(args):
     loop.close()
     launches_per_step = info["plan"]["launches_per_calc"] + 1 + (1 if world > 1 else 0)
 
-    # ---- dominant kernel alone, for the roofline (CUDA events on the launching stream) ----
-    grad = torch.empty(m, dtype=torch.float32, device=device)
-    scal = torch.zeros(8, dtype=torch.float64, device=device)
-    part = torch.empty(m + 2, dtype=torch.float32, device=device)
-    reps = max(5, min(K, 50))
-
-    def kernel_once():
-        if world == 1:
-            local.launch_calc(lam_now.data_ptr(), GAMMA, grad.data_ptr(), scal.data_ptr())
-        else:
-            local.launch_partial(lam_now.data_ptr(), GAMMA, part.data_ptr())
-
-    for _ in range(3):
-        kernel_once()
+    # ---- dominant kernel, for the roofline: CUDA events around every launch of the timed region ----
     torch.cuda.synchronize(device)
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(reps):
-        kernel_once()
-    k1.record()
-    torch.cuda.synchronize(device)
-    kernel_ms = k0.elapsed_time(k1) / reps
+    kernel_times = [a.elapsed_time(b) for a, b in kev]
+    kernel_ms = sum(kernel_times) / len(kernel_times)
     b_alg = local.algorithmic_bytes()
     peak, peak_src = measured_peak_gbs()
     achieved = b_alg / (kernel_ms * 1e-3) / 1e9
 
-    # ---- end to end through the public API with host buffers ----
+    # ---- end to end through the public API with host buffers: same schedule (W warm-up + K timed iterations) ----
     e2e = None
     if not args.no_e2e:
-        Ke = max(3, min(K, args.e2e_steps))
-        host_solver = AcceleratedGradientDescent(max_iter=Ke + 3, gamma=GAMMA, initial_step_size=INITIAL_STEP,
-                                                 max_step_size=MAX_STEP, iteration_callback=lambda i, r: None)
+        Ke = K if args.e2e_steps <= 0 else min(K, args.e2e_steps)
+        marks = {}
+
+        def mark(i, r):
+            if i == W:
+                if world > 1:
+                    dist.barrier()
+                marks["t0"] = time.perf_counter()
+
+        host_solver = AcceleratedGradientDescent(max_iter=W + Ke, gamma=GAMMA, initial_step_size=INITIAL_STEP,
+                                                 max_step_size=MAX_STEP, iteration_callback=mark)
         lam_host = torch.zeros(m, dtype=torch.float32).pin_memory()
-        # warm-up of the host path (pinned staging buffers, first-touch)
-        obj.calculate(lam_host, gamma=GAMMA)
         barrier()
-        t0 = time.perf_counter()
-        host_solver.max_iter = Ke
-        host_solver.beta_seq = host_solver._compute_beta_seq(Ke)
-        host_solver.maximize(obj, lam_host, rank=0 if world == 1 else rank)
+        host_solver.maximize(obj, lam_host, rank=0)  # every rank runs the host loop on its own copy of lambda
         torch.cuda.synchronize(device)
-        dt = max_over_ranks(time.perf_counter() - t0)
+        dt = max_over_ranks(time.perf_counter() - marks["t0"])
         h2d, d2h = obj.host_io_bytes()
         e2e = {"value": Ke / dt, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": Ke, "path": "AcceleratedGradientDescent.maximize with a pinned host dual vector: per iteration lambda "
-               "host->device, fused kernel(s), grad+scalars device->host, host-side update"}
+               "host->device, fused kernel(s), grad+scalars device->host, host-side update; same iterations as `value`"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
@@ -342,9 +330,11 @@ def run_native(args):
             "gpu_launches": launches_per_step * K,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "matching_pass_kernel", "kernel_ms": kernel_ms,
+                         "traffic": args.ncu_traffic_bytes, "kernel": "matching_slab_kernel", "kernel_ms": kernel_ms,
+                         "kernel_ms_min": min(kernel_times), "kernel_ms_max": max(kernel_times),
                          "algorithmic_bytes": b_alg, "peak_source": peak_src,
-                         "note": "rank-0 shard" if world > 1 else "whole problem"},
+                         "note": ("rank-0 shard; " if world > 1 else "") + "average over the K launches of the timed region "
+                                 "(the kernel's cost depends on the iterate: how many columns need the threshold search)"},
             "final_dual_objective": result.dual_objective,
             "setup": {"generate_s": info["gen_s"], "plan_s": info["plan_s"], "plan": info["plan"]},
         }
@@ -435,7 +425,9 @@ def main():
     ap.add_argument("--entities", type=int, default=None)
     ap.add_argument("--duals", type=int, default=None)
     ap.add_argument("--sparsity", type=float, default=None)
-    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same K as the device loop")
+    ap.add_argument("--ncu-traffic-bytes", type=float, default=None,
+                    help="dram__bytes_read.sum + dram__bytes_write.sum per launch from an ncu --set full capture of this workload")
     ap.add_argument("--cpu-sample-cols", type=int, default=4_000_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

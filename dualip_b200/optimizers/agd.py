@@ -229,6 +229,8 @@ class FusedAscentLoop:
             self.scal = torch.zeros(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=self.device)
             self.partial = torch.empty(self.m + 2, dtype=torch.float32, device=self.device) if self.sharded else None
         self.primal = None
+        self.kernel_events = None  # optional list of (start, end) CUDA events per step, for measurement
+        self.kernel_events_base = 1
 
     def step(self, i: int) -> None:
         solver, f = self.solver, self.f
@@ -237,15 +239,26 @@ class FusedAscentLoop:
         last_primal = i == solver.max_iter and solver.save_primal
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
+            ev = None
+            if self.kernel_events is not None and 0 <= i - self.kernel_events_base < len(self.kernel_events):
+                ev = self.kernel_events[i - self.kernel_events_base]
+                ev[0].record()
             if self.sharded:
+                from dualip_b200.objectives.matching import reduce_partials
+
                 f.local_objective.gamma = gamma_i
-                f.launch_partial_and_reduce(self.x_ptr, gamma_i, self.partial)
+                f.local_objective.launch_partial(self.x_ptr, gamma_i, self.partial.data_ptr())
+                if ev is not None:
+                    ev[1].record()
+                reduce_partials(self.partial)
                 f.launch_epilogue(self.partial.data_ptr(), self.x_ptr, gamma_i, self.grad.data_ptr(), self.scal.data_ptr())
             else:
                 if last_primal:
                     self.primal = torch.empty(f.nnz, dtype=torch.float32, device=self.device)
                 f.launch_calc(self.x_ptr, gamma_i, self.grad.data_ptr(), self.scal.data_ptr(),
                               self.primal.data_ptr() if last_primal else None)
+                if ev is not None:
+                    ev[1].record()
             if self.rank == 0 and solver._user_callback_active():
                 solver.iteration_callback(i, solver._view_result(self.grad, self.scal, self.primal if last_primal else None))
             decay_now, factor = 0, 1.0

@@ -1,0 +1,67 @@
+"""Worker for tests/test_gpu_distributed.py: run under torchrun, one process per GPU (NCCL).
+
+Reference counterpart: tests/distributed/test_matching_distributed.py:116-195 (same 5x5 problem and golden values, sharded
+across world_size GPUs), plus a random problem checked against the C oracle on every rank."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    from conftest import random_problem
+    from dualip_b200.objectives.matching import MatchingInputArgs, MatchingSolverDualObjectiveFunctionDistributed
+    from dualip_b200.optimizers.agd import AcceleratedGradientDescent
+    from dualip_b200.projections import create_projection_map
+    from dualip_b200.run_solver import run_solver
+    from dualip_b200.types import ComputeArgs, ObjectiveArgs, SolverArgs
+    from dualip_b200.utils.dist_utils import global_to_local_projection_map, split_tensors_to_devices
+    from oracle import c_oracle
+    from test_oracle_golden import _scala_5x5
+
+    # 1) the reference's distributed known-answer test
+    ccol, row, a, c, b = _scala_5x5()
+    A = torch.sparse_csc_tensor(torch.from_numpy(ccol), torch.from_numpy(row), torch.from_numpy(a), size=(5, 5))
+    C = torch.sparse_csc_tensor(torch.from_numpy(ccol), torch.from_numpy(row), torch.from_numpy(c), size=(5, 5))
+    pm = create_projection_map("simplex", {"z": 1}, 5)
+    a_s, c_s, index_map = split_tensors_to_devices(A, C, ["cpu"] * world)
+    local = MatchingInputArgs(a_s[rank].to(dev), c_s[rank].to(dev), global_to_local_projection_map(pm, index_map[rank]), None, None)
+    f = MatchingSolverDualObjectiveFunctionDistributed(local_matching_input_args=local, b_vec=torch.from_numpy(b), gamma=1e-3, host_device=dev)
+    solver = AcceleratedGradientDescent(max_iter=30, gamma=1e-3, iteration_callback=lambda i, r: None)
+    res = solver.maximize(f, 0.1 * torch.ones(5, device=dev), rank=rank)
+    for i, true_val in [(2, -3.6010155991401818), (16, -3.60842718733725), (23, -3.5080258013053136), (29, -3.4868496294227143)]:
+        assert abs(res.dual_objective_log[i - 1] - true_val) < 1e-5, (rank, i, res.dual_objective_log[i - 1])
+
+    # 2) random problem through run_solver(compute_device_num=world): every rank gets the full result
+    p = random_problem(77, 4001, 64, 8.0, scale_c=10.0)
+    n, m, gamma = p["n_cols"], p["n_rows"], 2e-2
+    A = torch.sparse_csc_tensor(torch.from_numpy(p["ccol"]), torch.from_numpy(p["row"]), torch.from_numpy(p["a"]), size=(m, n))
+    C = torch.sparse_csc_tensor(torch.from_numpy(p["ccol"]), torch.from_numpy(p["row"]), torch.from_numpy(p["c"]), size=(m, n))
+    args = MatchingInputArgs(A, C, create_projection_map("simplex", {"z": 1.0}, n), torch.from_numpy(p["b"]))
+    out = run_solver(args, SolverArgs(max_iter=15, gamma=gamma, initial_step_size=1e-3), ComputeArgs(f"cuda:{local_rank}", world),
+                     ObjectiveArgs("matching"))
+    lam = out.dual_val.clone()
+    ref_first = c_oracle.calculate(p["ccol"], p["row"], p["a"], p["c"], m, [c_oracle.make_class("simplex", {"z": 1.0})],
+                                   np.zeros(m, np.float32), gamma, p["b"])
+    assert abs(out.dual_objective_log[0] - ref_first["scal"][0]) <= 1e-5 * abs(ref_first["scal"][0])
+    gathered = [torch.empty_like(lam) for _ in range(world)]
+    dist.all_gather(gathered, lam)
+    assert all(torch.equal(g, gathered[0]) for g in gathered), "replicated optimizer state diverged across ranks"
+    dist.barrier()
+    if rank == 0:
+        print("DIST_WORKER_OK", world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
