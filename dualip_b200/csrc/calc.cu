@@ -8,12 +8,16 @@
 //   grad -= b ; dual_obj = cx + gamma/2*xx + lambda.grad ; slacks      matching.py:25-34,164-178
 //
 // HBM layout ("slabs", a sliced-ELL format sorted by projection class and column length): at plan time the
-// columns are stably sorted by (class, nnz) and cut into slabs of 32 columns of EQUAL length d; a slab stores
-// its values transposed, a_t[(off + k)*32 + lane] = k-th entry of column `lane`.  A warp owns a slab and a lane
-// owns a column: every load of a, c, row is one fully coalesced 128-byte (64-byte for uint16 rows) request, all
-// per-column reductions are plain sequential register arithmetic (no shuffles), and lanes never diverge on
-// column length or projection type.  The only shared-memory traffic per nonzero is the lambda gather and the
-// gradient scatter.  Columns longer than kMaxThreadDeg go to a warp-per-column kernel.
+// columns are stably sorted by (class, nnz) and cut into slabs of 32 columns of EQUAL length d.  A slab stores
+// its 32*d values in CHUNKS of four entries per column: entry k of column `lane` sits at
+//     (k & ~3)*32 + lane*4 + (k & 3)                      for k < (d & ~3)        (one 16-byte vector per lane and chunk)
+// and the d & 3 trailing entries form a 2-entry chunk (lane*2 + j) and/or a 1-entry chunk (lane); see slab_elem().
+// A warp owns a slab and a lane owns a column: one LDG.128 per lane fetches four entries of a (or c), one LDG.64
+// four uint16 row ids, every request is fully coalesced (512 contiguous bytes per warp instruction), all per-column
+// reductions are register arithmetic without shuffles, and lanes never diverge on column length or projection
+// type.  Columns of up to kRegDeg entries are processed entirely in registers by code specialised on d (one load
+// phase, no second pass); longer ones stream through the generic path.  The only shared-memory traffic per nonzero is
+// the lambda gather and the gradient scatter.  Columns longer than kMaxThreadDeg go to a warp-per-column kernel.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
 #include <algorithm>
@@ -48,6 +52,7 @@ constexpr uint32_t kKeyLong = (255u << kDegBits) | 2046u;
 constexpr int kKeyBits = 19;
 constexpr int kMaxClasses = 255;
 constexpr size_t kSmemBudget = 227 * 1024;
+constexpr int kThreads = 512;         // one CTA of 16 warps per SM: up to 128 registers per thread for the register path
 
 struct SlabHdr {      // 8 bytes per slab (per 32*d nonzeros)
   uint32_t off32;     // first row of the slab in units of 32 elements
@@ -55,6 +60,15 @@ struct SlabHdr {      // 8 bytes per slab (per 32*d nonzeros)
   uint8_t cls;        // projection class
   uint8_t ncols;      // active lanes (32 except in the last slab of a (class, d) group)
 };
+
+// Position of entry k of column `lane` inside a slab of column length d, in elements from the slab's start.
+__host__ __device__ __forceinline__ uint32_t slab_elem(int k, int d, int lane) {
+  const int full = d & ~3;
+  if (k < full) return (uint32_t)((k & ~3) * 32 + lane * 4 + (k & 3));
+  const int two = d & 2, kr = k - full;
+  if (kr < two) return (uint32_t)(full * 32 + lane * 2 + kr);
+  return (uint32_t)(full * 32 + two * 32 + lane);
+}
 
 struct LongCol {
   int64_t src_start;  // position of the column's first entry in the caller's CSC value order
@@ -91,6 +105,15 @@ struct dualip_plan {
   dualip_proj_class* classes_dev = nullptr;
   int n_classes = 0;
   float* acc = nullptr;        // m floats, zero between calls
+  int* acc_lo = nullptr;       // fixed-point mode: m ints each, zero between calls
+  int* acc_hi = nullptr;
+  bool class_used[256] = {};   // classes that own at least one non-empty column
+  int fixed_point = 0;         // 1: 32-bit fixed-point gradient accumulation (native shared-memory integer adds)
+  int fx_bits = 0;             // F
+  float fx_scale = 1.f;        // 2^F
+  double fx_inv = 1.0;         // 2^-F
+  double fx_bound = 0.0;       // largest possible |row sum| inside one CTA
+  double fx_relerr = 0.0;      // worst-row rounding error estimate relative to the row's largest possible sum
   double* acc_scal = nullptr;  // [c.x, ||x||^2], zero between calls
   unsigned int* counter = nullptr;
   float* lambda_stage = nullptr;  // m floats, for *_calc_host
@@ -100,6 +123,8 @@ struct dualip_plan {
   size_t smem_bytes = 0;
   size_t owned_bytes = 0;
   int flush_bulk = 1;
+  int prefetch = 0;
+  int stage = 0;               // per-warp TMA staging buffers fit in shared memory
 };
 
 namespace dualip {
@@ -160,7 +185,7 @@ __global__ void fill_slabs_kernel(const IdxT* __restrict__ ccol, const IdxT* __r
   const uint32_t col = perm[i];
   const int64_t e0 = (int64_t)ccol[col];
   for (int k = 0; k < d; ++k) {
-    const int64_t dst = (off32 + k) * kSlabW + lane;
+    const int64_t dst = off32 * kSlabW + slab_elem(k, d, lane);
     const IdxT r = row[e0 + k];
     if (r < 0 || r >= (IdxT)m) atomicOr(bad, 1u);
     a_t[dst] = a[e0 + k];
@@ -227,7 +252,11 @@ struct KArgs {
   int n_classes;
   const float* lambda;
   const float* b;            // may be null
-  float* acc;                // m floats (global accumulator across CTAs)
+  float* acc;                // m floats (global accumulator across CTAs; fp32 mode)
+  int* acc_lo;               // fixed-point mode: low 16 bits / high part of every CTA's 32-bit row sums, m ints each
+  int* acc_hi;
+  float fx_scale;            // 2^F
+  double fx_inv;             // 2^-F
   double* acc_scal;          // 2 doubles
   unsigned int* counter;
   float* grad_out;           // calc mode
@@ -240,6 +269,8 @@ struct KArgs {
   float s;                   // fl32(-1/gamma)   (matching.py:136: `-1.0 / self.gamma * dual_val`)
   int flush_bulk;
   int do_epilogue;           // 1: calc (grad/scalars), 0: partial (packed sums)
+  int stage;                 // 1: TMA-staged slabs (per-warp shared-memory buffer + mbarrier)
+  int prefetch;              // L2 prefetch of each warp's next slab: 0 off, 1 bulk (TMA engine), 2 per-line
   const float* long_a;
   const float* long_c;
   const uint32_t* long_row;
@@ -258,12 +289,16 @@ __device__ __forceinline__ float lam_scaled(const KArgs& k, const float* s_lam, 
   if (SMODE == 0) return s_lam[r];
   return __fmul_rn(k.s, __ldg(k.lambda + r));
 }
-template <int SMODE>
+template <int SMODE, int ACC>
 __device__ __forceinline__ void grad_add(const KArgs& k, float* s_grad, uint32_t r, float g) {
-  if (SMODE <= 1)
+  if (ACC == 1) {
+    const int gi = __float2int_rn(g * k.fx_scale);
+    if (gi != 0) atomicAdd(reinterpret_cast<int*>(s_grad) + r, gi);
+  } else if (SMODE <= 1) {
     atomicAdd(&s_grad[r], g);
-  else
+  } else {
     atomicAdd(&k.acc[r], g);
+  }
 }
 
 // v = fl(fl(a * fl(s*lambda_r)) + fl(s*c)): the reference's operation order in fp32, no FMA contraction.
@@ -276,14 +311,62 @@ __device__ __forceinline__ double just_below(double x) {
   return x > 0.0 ? __longlong_as_double(__double_as_longlong(x) - 1LL) : -4.9406564584124654e-324;
 }
 
-// m-length tail, executed by one whole CTA.  `sum` = sum_j a_rj x_rj (m floats), cxv = c.x, xxv = ||x||^2.
+}  // namespace dualip
+#include "slab_fast.cuh"
+namespace dualip {
+
+// Generic-path loads of N consecutive entries k0 .. k0+N-1 of this lane's column (N = 8/4: whole 4-entry chunks,
+// N = 2 / 1: the tail chunks; k0 is where the plan's layout puts that chunk, see slab_elem()).
+template <int N, typename RowT>
+__device__ __forceinline__ void load_batch(const float* __restrict__ pa0, const float* __restrict__ pc0,
+                                           const RowT* __restrict__ pr0, int k0, int lane, float (&a4)[N], float (&c4)[N],
+                                           uint32_t (&r4)[N]) {
+  if (N >= 4) {
+#pragma unroll
+    for (int j = 0; j < N / 4; ++j) {
+      const size_t o = (size_t)(k0 + 4 * j) * kSlabW + (size_t)lane * 4;
+      const float4 va = __ldg(reinterpret_cast<const float4*>(pa0 + o));
+      const float4 vc = __ldg(reinterpret_cast<const float4*>(pc0 + o));
+      a4[4 * j] = va.x, a4[4 * j + 1] = va.y, a4[4 * j + 2] = va.z, a4[4 * j + 3] = va.w;
+      c4[4 * j] = vc.x, c4[4 * j + 1] = vc.y, c4[4 * j + 2] = vc.z, c4[4 * j + 3] = vc.w;
+      if (sizeof(RowT) == 2) {
+        const uint2 vr = __ldg(reinterpret_cast<const uint2*>(pr0 + o));
+        r4[4 * j] = vr.x & 0xffffu, r4[4 * j + 1] = vr.x >> 16, r4[4 * j + 2] = vr.y & 0xffffu, r4[4 * j + 3] = vr.y >> 16;
+      } else {
+        const uint4 vr = __ldg(reinterpret_cast<const uint4*>(pr0 + o));
+        r4[4 * j] = vr.x, r4[4 * j + 1] = vr.y, r4[4 * j + 2] = vr.z, r4[4 * j + 3] = vr.w;
+      }
+    }
+  } else if (N == 2) {
+    const size_t o = (size_t)k0 * kSlabW + (size_t)lane * 2;
+    const float2 va = __ldg(reinterpret_cast<const float2*>(pa0 + o));
+    const float2 vc = __ldg(reinterpret_cast<const float2*>(pc0 + o));
+    a4[0] = va.x, a4[1] = va.y, c4[0] = vc.x, c4[1] = vc.y;
+    if (sizeof(RowT) == 2) {
+      const uint32_t vr = __ldg(reinterpret_cast<const uint32_t*>(pr0 + o));
+      r4[0] = vr & 0xffffu, r4[1] = vr >> 16;
+    } else {
+      const uint2 vr = __ldg(reinterpret_cast<const uint2*>(pr0 + o));
+      r4[0] = vr.x, r4[1] = vr.y;
+    }
+  } else {
+    const size_t o = (size_t)k0 * kSlabW + (size_t)lane;
+    a4[0] = __ldg(pa0 + o);
+    c4[0] = __ldg(pc0 + o);
+    r4[0] = (uint32_t)__ldg(pr0 + o);
+  }
+}
+
+// m-length tail, executed by one whole CTA.  sum_at(i) = sum_j a_ij x_ij, cxv = c.x, xxv = ||x||^2.
 // Reference: calc_grad (matching.py:25-34) and matching.py:164-178 / :280-299.
-__device__ void cta_epilogue(const float* sum, double cxv, double xxv, const float* lambda, const float* b, int m,
-                             double gamma, float* grad_out, dualip_scalars* out, double* dscratch, float* fscratch) {
+template <typename SumFn>
+__device__ __forceinline__ void cta_epilogue(SumFn sum_at, double cxv, double xxv, const float* lambda, const float* b, int m,
+                                             double gamma, float* grad_out, dualip_scalars* out, double* dscratch,
+                                             float* fscratch) {
   double lg = 0.0, sp = 0.0, g2 = 0.0;
   float mx = -INFINITY;
   for (int i = threadIdx.x; i < m; i += blockDim.x) {
-    const float raw = __ldcg(sum + i);
+    const float raw = sum_at(i);
     const float g = b ? __fsub_rn(raw, b[i]) : raw;
     grad_out[i] = g;
     lg = fma((double)lambda[i], (double)g, lg);
@@ -310,25 +393,31 @@ __device__ void cta_epilogue(const float* sum, double cxv, double xxv, const flo
   }
 }
 
-template <bool ROW16, int SMODE, int THREADS, int MINB>
+template <bool ROW16, int SMODE, int ACC, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArgs k) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // carve: [mbarrier 16B][classes][scratch 32 doubles + 32 floats][s_lam m_pad floats][s_grad m floats]
+  // carve: [mbarrier 16B][per-warp mbarriers 128B][classes][scratch 32 doubles + 32 floats][s_lam m_pad floats]
+  //        [s_grad m_pad floats][per-warp stash (generic path) or per-warp staging buffers (register path)]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  dualip_proj_class* s_cls = reinterpret_cast<dualip_proj_class*>(smem_raw + 16);
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(smem_raw + 16);
+  dualip_proj_class* s_cls = reinterpret_cast<dualip_proj_class*>(smem_raw + 16 + 128);
   const int n_cls_bytes = ((k.n_classes * (int)sizeof(dualip_proj_class)) + 15) & ~15;
-  double* dscratch = reinterpret_cast<double*>(smem_raw + 16 + n_cls_bytes);
+  double* dscratch = reinterpret_cast<double*>(smem_raw + 16 + 128 + n_cls_bytes);
   float* fscratch = reinterpret_cast<float*>(dscratch + 32);
   float* s_lam = fscratch + 32;
   const int m = k.m;
   const int m_pad = (m + 3) & ~3;
   float* s_grad = s_lam + (SMODE == 0 ? m_pad : 0);
-  float* s_stash = s_grad + (SMODE <= 1 ? m_pad : 0);  // kStashDeg x 32 floats per warp
+  float* s_stash = s_grad + (SMODE <= 1 ? m_pad : 0);  // kStashDeg x 32 floats per warp (generic path)
+  unsigned char* s_stage = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(s_stash) + 127) & ~(uintptr_t)127);  // kStageBytes per warp (register path)
   __shared__ unsigned int s_ticket;
 
   const unsigned FULL = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = THREADS / 32;
+  constexpr bool FAST = ROW16 && (SMODE == 0);  // register path (slab_fast.cuh)
+  const uint32_t s_grad_u32 = pin_u32(smem_u32(s_grad));
 
   // ---- stage lambda into shared memory with a bulk async copy (TMA engine), then scale by -1/gamma ----
   bool bulk_ok = false;
@@ -337,6 +426,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     bulk_ok = ((reinterpret_cast<uintptr_t>(k.lambda) & 15u) == 0) && bulk_bytes >= 16;
     if (tid == 0) {
       mbar_init(bar, 1);
+      for (int w = 0; w < THREADS / 32; ++w) mbar_init(wbar + w, 1);
       fence_mbar_init();
     }
     __syncthreads();
@@ -370,19 +460,108 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   using RowT = typename std::conditional<ROW16, unsigned short, uint32_t>::type;
   const RowT* row_all = reinterpret_cast<const RowT*>(k.row_t);
   int64_t sl = (int64_t)blockIdx.x * NW + warp;
-  uint2 hnext = make_uint2(0u, 0u);
+  // slab headers are fetched two slabs ahead: the next slab's header is needed NOW (to start its staging copy)
+  uint2 hnext = make_uint2(0u, 0u), hnext2 = make_uint2(0u, 0u);
   if (sl < k.n_slabs) hnext = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl);
+  if (sl + total_warps < k.n_slabs) hnext2 = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl + total_warps);
+  // TMA staging (register path): while a warp works on a slab, the engine copies its next slab into the warp's buffer
+  const bool use_stage = FAST && (k.stage != 0);
+  unsigned char* my_stage = s_stage + (size_t)warp * kStageBytes;
+  uint64_t* my_bar = wbar + warp;
+  uint32_t stage_phase = 0;
+  bool cur_staged = false;
+  auto stage_slab = [&](const uint2 h) {  // h: header of a slab with d <= kRegDeg
+    if (lane == 0) {
+      const size_t nb = (size_t)h.x * kSlabW;
+      stage_issue(my_stage, my_bar, k.a_t + nb, k.c_t + nb, reinterpret_cast<const unsigned short*>(k.row_t) + nb,
+                  (int)(h.y & 0xffffu));
+    }
+  };
+  if (use_stage && sl < k.n_slabs && (int)(hnext.y & 0xffffu) <= kRegDeg) {
+    stage_slab(hnext);
+    cur_staged = true;
+  }
   for (; sl < k.n_slabs; sl += total_warps) {
     const uint2 hraw = hnext;
-    if (sl + total_warps < k.n_slabs) hnext = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl + total_warps);
+    hnext = hnext2;
+    if (sl + 2 * total_warps < k.n_slabs) hnext2 = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl + 2 * total_warps);
     const int d = (int)(hraw.y & 0xffffu);
     const int cls = (int)((hraw.y >> 16) & 0xffu);
     const bool active = lane < (int)(hraw.y >> 24);
-    const size_t base = (size_t)hraw.x * kSlabW + lane;
+    const size_t base = (size_t)hraw.x * kSlabW;  // the slab's first element
     const float* __restrict__ pa = k.a_t + base;
     const float* __restrict__ pcv = k.c_t + base;
     const RowT* __restrict__ pr = row_all + base;
     const dualip_proj_class pc = s_cls[cls];
+    if (k.prefetch && sl + total_warps < k.n_slabs) {
+      // pull this warp's NEXT slab into L2 while the current one is processed
+      const size_t nb = (size_t)hnext.x * kSlabW;
+      const uint32_t ne = (hnext.y & 0xffffu) * (uint32_t)kSlabW;
+      if (k.prefetch == 1) {  // three bulk requests to the TMA engine
+        if (lane == 0) {
+          prefetch_l2_bulk(k.a_t + nb, ne * 4u);
+          prefetch_l2_bulk(k.c_t + nb, ne * 4u);
+          prefetch_l2_bulk(row_all + nb, ne * (uint32_t)sizeof(RowT));
+        }
+      } else {  // one 128-byte line per lane and request
+        const uint32_t la = (ne * 4u + 127u) >> 7, lr = (ne * (uint32_t)sizeof(RowT) + 127u) >> 7;
+        for (uint32_t i = lane; i < 2 * la + lr; i += 32) {
+          const char* q = i < la ? reinterpret_cast<const char*>(k.a_t + nb) + ((size_t)i << 7)
+                                 : (i < 2 * la ? reinterpret_cast<const char*>(k.c_t + nb) + ((size_t)(i - la) << 7)
+                                               : reinterpret_cast<const char*>(row_all + nb) + ((size_t)(i - 2 * la) << 7));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        }
+      }
+    }
+    const bool have_next = sl + total_warps < k.n_slabs;
+    const bool next_staged = use_stage && have_next && (int)(hnext.y & 0xffffu) <= kRegDeg;
+    const bool staged = cur_staged;
+    cur_staged = next_staged;
+    auto issue_next = [&]() {
+      if (next_staged) {
+        __syncwarp();
+        stage_slab(hnext);
+      }
+    };
+    if (FAST && d <= kRegDeg) {
+      // ---- register path: the whole column lives in registers, code specialised on d ----
+      const unsigned char* s_lam_b = reinterpret_cast<const unsigned char*>(s_lam);
+      const unsigned short* pr16 = reinterpret_cast<const unsigned short*>(pr);
+      switch (d) {
+#define DUALIP_FAST_CASE(DD)                                                                              \
+  case DD:                                                                                                \
+    fast_slab<DD, SMODE, ACC>(k, pc, pa, pcv, pr16, lane, active, s_lam_b, s_grad_u32, s, sl, cx, xx,    \
+                              staged, my_stage, my_bar, stage_phase, issue_next);                        \
+    break;
+        DUALIP_FAST_CASE(1)
+        DUALIP_FAST_CASE(2)
+        DUALIP_FAST_CASE(3)
+        DUALIP_FAST_CASE(4)
+        DUALIP_FAST_CASE(5)
+        DUALIP_FAST_CASE(6)
+        DUALIP_FAST_CASE(7)
+        DUALIP_FAST_CASE(8)
+        DUALIP_FAST_CASE(9)
+        DUALIP_FAST_CASE(10)
+        DUALIP_FAST_CASE(11)
+        DUALIP_FAST_CASE(12)
+        DUALIP_FAST_CASE(13)
+        DUALIP_FAST_CASE(14)
+        DUALIP_FAST_CASE(15)
+        DUALIP_FAST_CASE(16)
+#undef DUALIP_FAST_CASE
+        default:
+          break;
+      }
+      continue;
+    }
+    issue_next();  // the generic path does not use the staging buffer
+    auto ld1 = [&](int kq, float& av, float& cv, uint32_t& rv) {
+      const uint32_t o = slab_elem(kq, d, lane);
+      av = __ldg(pa + o);
+      cv = __ldg(pcv + o);
+      rv = (uint32_t)__ldg(pr + o);
+    };
     float cxs = 0.f, xxs = 0.f;
     // per-lane outcome, also what the (rare) output pass needs: x_k = branch 0: u_k, 1: z*[k == i1], 2: max(u_k - theta, 0)
     int branch = -1, rho = 0, i1 = 0;
@@ -395,7 +574,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
         const float v = make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c);
         const float x = fminf(fmaxf(v, lo), hi);
         const float g = __fmul_rn(a, x);
-        if (g != 0.f) grad_add<SMODE>(k, s_grad, r, g);
+        if (g != 0.f) grad_add<SMODE, ACC>(k, s_grad, r, g);
         cxs = fmaf(c, x, cxs);
         xxs = fmaf(x, x, xxs);
       };
@@ -404,12 +583,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
         constexpr int N = decltype(n_tag)::value;
         float a4[N], c4[N];
         uint32_t r4[N];
-#pragma unroll
-        for (int q = 0; q < N; ++q) {
-          a4[q] = __ldg(pa + (size_t)(k0 + q) * kSlabW);
-          c4[q] = __ldg(pcv + (size_t)(k0 + q) * kSlabW);
-          r4[q] = __ldg(pr + (size_t)(k0 + q) * kSlabW);
-        }
+        load_batch<N, RowT>(pa, pcv, pr, k0, lane, a4, c4, r4);
 #pragma unroll
         for (int q = 0; q < N; ++q) body(a4[q], c4[q], r4[q]);
       };
@@ -458,12 +632,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
         constexpr int N = decltype(n_tag)::value;
         float a4[N], c4[N];
         uint32_t r4[N];
-#pragma unroll
-        for (int q = 0; q < N; ++q) {
-          a4[q] = __ldg(pa + (size_t)(k0 + q) * kSlabW);
-          c4[q] = __ldg(pcv + (size_t)(k0 + q) * kSlabW);
-          r4[q] = __ldg(pr + (size_t)(k0 + q) * kSlabW);
-        }
+        load_batch<N, RowT>(pa, pcv, pr, k0, lane, a4, c4, r4);
 #pragma unroll
         for (int q = 0; q < N; ++q) track(a4[q], c4[q], r4[q], k0 + q);
       };
@@ -536,11 +705,11 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       // non-zeros of the closed-form lanes: their entries are re-read from lines this warp has just streamed
       auto emit = [&](int kq, float x) {
         if (x != 0.f) {
-          const float a = __ldg(pa + (size_t)kq * kSlabW);
-          const float c = __ldg(pcv + (size_t)kq * kSlabW);
-          const uint32_t r = __ldg(pr + (size_t)kq * kSlabW);
+          float a, c;
+          uint32_t r;
+          ld1(kq, a, c, r);
           const float g = __fmul_rn(a, x);
-          if (g != 0.f) grad_add<SMODE>(k, s_grad, r, g);
+          if (g != 0.f) grad_add<SMODE, ACC>(k, s_grad, r, g);
           cxs = fmaf(c, x, cxs);
           xxs = fmaf(x, x, xxs);
         }
@@ -556,9 +725,9 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
           constexpr bool ST = decltype(stash_tag)::value;
           auto uq = [&](int kq) -> float {
             if (ST) return su[kq * kSlabW];
-            const float a = __ldg(pa + (size_t)kq * kSlabW);
-            const float c = __ldg(pcv + (size_t)kq * kSlabW);
-            const uint32_t r = __ldg(pr + (size_t)kq * kSlabW);
+            float a, c;
+            uint32_t r;
+            ld1(kq, a, c, r);
             return fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);
           };
           // Newton steps from below on f(t) = sum max(u - t, 0) - z (Michelot): t <- (sum_{u>t} u - z)/#{u>t}.  Lower
@@ -637,7 +806,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
             const float x = (branch == 0) ? u : fmaxf(__fsub_rn(u, theta), 0.f);
             if (need_p2 && x != 0.f) {
               const float g = __fmul_rn(a, x);
-              if (g != 0.f) grad_add<SMODE>(k, s_grad, r, g);
+              if (g != 0.f) grad_add<SMODE, ACC>(k, s_grad, r, g);
               cxs = fmaf(c, x, cxs);
               xxs = fmaf(x, x, xxs);
             }
@@ -646,12 +815,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
             constexpr int N = decltype(n_tag)::value;
             float a4[N], c4[N];
             uint32_t r4[N];
-#pragma unroll
-            for (int q = 0; q < N; ++q) {
-              a4[q] = __ldg(pa + (size_t)(k0 + q) * kSlabW);
-              c4[q] = __ldg(pcv + (size_t)(k0 + q) * kSlabW);
-              r4[q] = __ldg(pr + (size_t)(k0 + q) * kSlabW);
-            }
+            load_batch<N, RowT>(pa, pcv, pr, k0, lane, a4, c4, r4);
 #pragma unroll
             for (int q = 0; q < N; ++q) scatter(a4[q], c4[q], r4[q], k0 + q);
           };
@@ -689,9 +853,9 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       const int64_t os = k.orig_start[sl * kSlabW + lane];
       if (k.x_out) {
         for (int kq = 0; kq < d; ++kq) {
-          const float a = __ldg(pa + (size_t)kq * kSlabW);
-          const float c = __ldg(pcv + (size_t)kq * kSlabW);
-          const uint32_t r = __ldg(pr + (size_t)kq * kSlabW);
+          float a, c;
+          uint32_t r;
+          ld1(kq, a, c, r);
           const float v = make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c);
           float x;
           if (branch < 0)
@@ -717,7 +881,35 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     if (xx != 0.0) atomicAdd(&k.acc_scal[1], xx);
   }
   __syncthreads();
-  if (SMODE <= 1) {
+  if (ACC == 1) {
+    // fixed point: every CTA sum s (|s| < 2^31) is split as s = hi*65536 + lo with 0 <= lo < 65536, so that the
+    // grid-wide totals of both parts fit 32 bits; lo stays in place, hi reuses the (now dead) lambda array; two TMA
+    // bulk reductions (SASS UBLKRED, element-wise s32 add performed at L2) flush them.
+    int* s_lo = reinterpret_cast<int*>(s_grad);
+    int* s_hi = reinterpret_cast<int*>(s_lam);
+    for (int i = tid; i < m; i += THREADS) {
+      const int v = s_lo[i];
+      s_lo[i] = v & 0xffff;
+      s_hi[i] = v >> 16;
+    }
+    const uint32_t bulk_bytes = (uint32_t)(m & ~3) * 4u;
+    const bool bulk = k.flush_bulk && bulk_bytes >= 16 && ((reinterpret_cast<uintptr_t>(k.acc_lo) & 15u) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(k.acc_hi) & 15u) == 0);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (bulk) {
+      if (tid == 0) {
+        bulk_reduce_add_s32_s2g(k.acc_lo, s_lo, bulk_bytes);
+        bulk_reduce_add_s32_s2g(k.acc_hi, s_hi, bulk_bytes);
+        bulk_commit();
+        bulk_wait_all();
+      }
+    }
+    for (int i = (bulk ? (m & ~3) : 0) + tid; i < m; i += THREADS) {
+      if (s_lo[i] != 0) atomicAdd(&k.acc_lo[i], s_lo[i]);
+      if (s_hi[i] != 0) atomicAdd(&k.acc_hi[i], s_hi[i]);
+    }
+  } else if (SMODE <= 1) {
     const uint32_t bulk_bytes = (uint32_t)(m & ~3) * 4u;
     if (k.flush_bulk && bulk_bytes >= 16 && ((reinterpret_cast<uintptr_t>(k.acc) & 15u) == 0)) {
       // one TMA bulk reduction: acc[0..m) += s_grad[0..m) performed at L2 (SASS UBLKRED)
@@ -752,17 +944,31 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   __threadfence();
   const double cxv = __ldcg(&k.acc_scal[0]);
   const double xxv = __ldcg(&k.acc_scal[1]);
+  auto sum_at = [&](int i) -> float {
+    if (ACC == 1) {
+      const long long v = (long long)__ldcg(k.acc_hi + i) * 65536LL + (long long)__ldcg(k.acc_lo + i);
+      return (float)((double)v * k.fx_inv);
+    }
+    return __ldcg(k.acc + i);
+  };
   if (k.do_epilogue) {
-    cta_epilogue(k.acc, cxv, xxv, k.lambda, k.b, m, k.gamma, k.grad_out, k.scalars_out, dscratch, fscratch);
+    cta_epilogue(sum_at, cxv, xxv, k.lambda, k.b, m, k.gamma, k.grad_out, k.scalars_out, dscratch, fscratch);
   } else {
-    for (int i = tid; i < m; i += THREADS) k.partial_out[i] = __ldcg(k.acc + i);
+    for (int i = tid; i < m; i += THREADS) k.partial_out[i] = sum_at(i);
     if (tid == 0) {
       k.partial_out[m] = (float)cxv;
       k.partial_out[m + 1] = (float)xxv;
     }
   }
   __syncthreads();
-  for (int i = tid; i < m; i += THREADS) k.acc[i] = 0.f;
+  for (int i = tid; i < m; i += THREADS) {
+    if (ACC == 1) {
+      k.acc_lo[i] = 0;
+      k.acc_hi[i] = 0;
+    } else {
+      k.acc[i] = 0.f;
+    }
+  }
   if (tid == 0) {
     k.acc_scal[0] = 0.0;
     k.acc_scal[1] = 0.0;
@@ -775,6 +981,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
 // Threshold by Michelot's fixed point (same support set and theta formula as the sorted scan in exact arithmetic);
 // sums over the support are fp64 like the reference's CPU cumsum.
 // ------------------------------------------------------------------------------------------
+template <int ACC>
 __global__ void __launch_bounds__(256) matching_long_kernel(const KArgs k, const LongCol* __restrict__ cols, int64_t n_long) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -869,7 +1076,15 @@ __global__ void __launch_bounds__(256) matching_long_kernel(const KArgs k, const
         x = branch == 0 ? u : (branch == 1 ? (e == amax ? pc.z : 0.f) : fmaxf(__fsub_rn(u, theta), 0.f));
       }
       const float g = __fmul_rn(av, x);
-      if (g != 0.f) atomicAdd(&k.acc[rv], g);
+      if (ACC == 1) {
+        const long long gi = __double2ll_rn((double)g * (double)k.fx_scale);
+        if (gi != 0) {
+          atomicAdd(&k.acc_lo[rv], (int)(gi & 0xffff));
+          atomicAdd(&k.acc_hi[rv], (int)(gi >> 16));
+        }
+      } else if (g != 0.f) {
+        atomicAdd(&k.acc[rv], g);
+      }
       const double xd = (double)x;
       cx = fma((double)cv, xd, cx);
       xx = fma(xd, xd, xx);
@@ -889,7 +1104,64 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(const float* sum, int m,
                                                         double gamma, float* grad_out, dualip_scalars* out) {
   __shared__ double dscratch[32];
   __shared__ float fscratch[32];
-  cta_epilogue(sum, (double)sum[m], (double)sum[m + 1], lambda, b, m, gamma, grad_out, out, dscratch, fscratch);
+  cta_epilogue([&](int i) { return __ldcg(sum + i); }, (double)sum[m], (double)sum[m + 1], lambda, b, m, gamma, grad_out, out,
+               dscratch, fscratch);
+}
+
+// ------------------------------------------------------------------------------------------
+// Plan time: bound on every CTA's row sums, for the fixed-point accumulator.  Same slab -> CTA assignment as the hot
+// kernel (warp w of CTA b takes slabs b*NW + w, + gridDim*NW, ...).  |a * x| <= |a| * xmax(class).
+// ------------------------------------------------------------------------------------------
+template <typename RowT>
+__global__ void cta_row_bound_kernel(const float* __restrict__ a_t, const RowT* __restrict__ row_t,
+                                     const SlabHdr* __restrict__ hdr, int64_t n_slabs, const float* __restrict__ cls_xmax,
+                                     int m, float* __restrict__ table, unsigned int* __restrict__ row_cnt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  const int64_t total_warps = (int64_t)gridDim.x * NW;
+  float* my = table + (size_t)blockIdx.x * m;
+  for (int64_t sl = (int64_t)blockIdx.x * NW + warp; sl < n_slabs; sl += total_warps) {
+    const SlabHdr h = hdr[sl];
+    if (lane >= (int)h.ncols) continue;
+    const float xmax = cls_xmax[h.cls];
+    const size_t base = (size_t)h.off32 * kSlabW;
+    for (int k = 0; k < (int)h.d; ++k) {
+      const size_t idx = base + slab_elem(k, (int)h.d, lane);
+      const uint32_t r = (uint32_t)row_t[idx];
+      atomicAdd(&my[r], fabsf(a_t[idx]) * xmax);
+      atomicAdd(&row_cnt[r], 1u);
+    }
+  }
+}
+
+__global__ void long_row_bound_kernel(const LongCol* __restrict__ cols, int64_t n_long, const float* __restrict__ la,
+                                      const uint32_t* __restrict__ lrow, const float* __restrict__ cls_xmax,
+                                      float* __restrict__ long_bound, unsigned int* __restrict__ row_cnt) {
+  const int lane = threadIdx.x & 31;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (; w < n_long; w += nw) {
+    const LongCol lc = cols[w];
+    const float xmax = cls_xmax[lc.cls];
+    for (int e = lane; e < lc.len; e += 32) {
+      atomicAdd(&long_bound[lrow[lc.off + e]], fabsf(la[lc.off + e]) * xmax);
+      atomicAdd(&row_cnt[lrow[lc.off + e]], 1u);
+    }
+  }
+}
+
+// per row: largest CTA bound and the sum over CTAs
+__global__ void bound_reduce_kernel(const float* __restrict__ table, int n_ctas, int m, float* __restrict__ row_max,
+                                    float* __restrict__ row_sum) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  float mx = 0.f, sm = 0.f;
+  for (int c = 0; c < n_ctas; ++c) {
+    const float v = table[(size_t)c * m + r];
+    mx = fmaxf(mx, v);
+    sm += v;
+  }
+  row_max[r] = mx;
+  row_sum[r] = sm;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -897,27 +1169,20 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(const float* sum, int m,
 // ------------------------------------------------------------------------------------------
 typedef void (*SlabKernel)(const KArgs);
 
-template <int THREADS, int MINB>
-static SlabKernel pick_kernel(bool row16, int smode) {
-#define DUALIP_PICK(R, S) \
-  if (row16 == R && smode == S) return matching_slab_kernel<R, S, THREADS, MINB>;
-  DUALIP_PICK(true, 0)
-  DUALIP_PICK(true, 1)
-  DUALIP_PICK(true, 2)
-  DUALIP_PICK(false, 0)
-  DUALIP_PICK(false, 1)
-  DUALIP_PICK(false, 2)
-#undef DUALIP_PICK
+// Variants: the register path and fixed-point accumulation exist for uint16 rows with lambda and the accumulator in
+// shared memory (m up to ~24k); larger m streams through the generic path with fp32 accumulation.
+static SlabKernel plan_kernel(const dualip_plan* p) {
+  const bool row16 = p->row_bits == 16;
+  if (row16 && p->smode == 0) return p->fixed_point ? matching_slab_kernel<true, 0, 1, kThreads, 1> : matching_slab_kernel<true, 0, 0, kThreads, 1>;
+  if (row16 && p->smode == 1) return matching_slab_kernel<true, 1, 0, kThreads, 1>;
+  if (row16 && p->smode == 2) return matching_slab_kernel<true, 2, 0, kThreads, 1>;
+  if (!row16 && p->smode == 1) return matching_slab_kernel<false, 1, 0, kThreads, 1>;
+  if (!row16 && p->smode == 2) return matching_slab_kernel<false, 2, 0, kThreads, 1>;
   return nullptr;
 }
 
-static SlabKernel plan_kernel(const dualip_plan* p) {
-  const bool row16 = p->row_bits == 16;
-  return pick_kernel<1024, 1>(row16, p->smode);
-}
-
 static size_t smem_fixed_bytes(int n_classes) {
-  return 16 + (((size_t)n_classes * sizeof(dualip_proj_class) + 15) & ~(size_t)15) + 32 * sizeof(double) + 32 * sizeof(float);
+  return 16 + 128 + (((size_t)n_classes * sizeof(dualip_proj_class) + 15) & ~(size_t)15) + 32 * sizeof(double) + 32 * sizeof(float);
 }
 
 static int launch_eval(dualip_plan* p, const float* lambda, const float* b, double gamma, float* grad_out,
@@ -939,6 +1204,10 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.lambda = lambda;
   k.b = b;
   k.acc = p->acc;
+  k.acc_lo = p->acc_lo;
+  k.acc_hi = p->acc_hi;
+  k.fx_scale = p->fx_scale;
+  k.fx_inv = p->fx_inv;
   k.acc_scal = p->acc_scal;
   k.counter = p->counter;
   k.grad_out = grad_out;
@@ -951,12 +1220,17 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.s = (float)(-1.0 / gamma);
   k.flush_bulk = p->flush_bulk;
   k.do_epilogue = do_epilogue;
+  k.prefetch = p->prefetch;
+  k.stage = p->stage;
   k.long_a = p->long_a;
   k.long_c = p->long_c;
   k.long_row = p->long_row;
   if (p->n_long > 0) {
     const int blocks = (int)std::min<int64_t>((p->n_long + 7) / 8, (int64_t)p->n_sms * 8);
-    matching_long_kernel<<<blocks, 256, 0, stream>>>(k, p->longcols, p->n_long);
+    if (p->fixed_point)
+      matching_long_kernel<1><<<blocks, 256, 0, stream>>>(k, p->longcols, p->n_long);
+    else
+      matching_long_kernel<0><<<blocks, 256, 0, stream>>>(k, p->longcols, p->n_long);
   }
   SlabKernel kern = plan_kernel(p);
   kern<<<p->n_ctas, p->threads, p->smem_bytes, stream>>>(k);
@@ -1062,6 +1336,7 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
         slab += ns;
         off32 += ns * (int64_t)(g.key & ((1u << kDegBits) - 1));
         groups.push_back(g);
+        p->class_used[(g.key >> kDegBits) & 0xffu] = true;
         n_short = pos + g.count;
       }
       pos += uc[r];
@@ -1131,6 +1406,7 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
     for (auto& c : lc) {
       c.off = tot;
       tot += c.len;
+      p->class_used[c.cls & 0xff] = true;
     }
     BS_TRY(cudaMemcpyAsync(p->longcols, lc.data(), sizeof(LongCol) * n_long, cudaMemcpyHostToDevice, stream));
     BS_TRY(cudaMalloc(&p->long_a, sizeof(float) * tot));
@@ -1152,6 +1428,103 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
     return DUALIP_EINVAL;
   }
   return rc;
+}
+
+// Chooses the accumulation mode of a plan.  Fixed point needs (a) a finite bound on x for every class, (b) the register /
+// shared-memory configuration it is built for (uint16 rows, lambda + accumulator in shared memory), and (c) enough
+// resolution: with quantum q = 2^-F the rounding error of a row sum of N terms is ~ q*sqrt(N/12); it must stay below a
+// few fp32 ulps of the row's largest possible sum, otherwise (heavy-tailed row bounds) the plan keeps fp32 atomics.
+static int choose_accumulator(dualip_plan* p, cudaStream_t stream) {
+  p->fixed_point = 0;
+  const char* env = getenv("DUALIP_ACCUM");
+  if (env && strcmp(env, "f32") == 0) return DUALIP_OK;
+  if (p->row_bits != 16 || p->smode != 0) return DUALIP_OK;
+  std::vector<float> xmax(p->n_classes);
+  for (int i = 0; i < p->n_classes; ++i) {
+    const dualip_proj_class& pc = p->classes_host[i];
+    xmax[i] = (pc.kind == DUALIP_PROJ_CLAMP) ? fmaxf(fabsf(pc.lo), fabsf(pc.hi)) : pc.z;
+    if (!p->class_used[i]) xmax[i] = 0.f;
+    if (!(xmax[i] < INFINITY)) return DUALIP_OK;  // open cone / identity: no bound
+  }
+  const int m = p->m;
+  float *xmax_d = nullptr, *table = nullptr, *row_max = nullptr, *row_sum = nullptr, *long_bound = nullptr;
+  unsigned int* row_cnt = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(xmax_d);
+    cudaFree(table);
+    cudaFree(row_max);
+    cudaFree(row_sum);
+    cudaFree(long_bound);
+    cudaFree(row_cnt);
+  };
+#define CA_TRY(expr)                                               \
+  do {                                                             \
+    cudaError_t _e = (expr);                                       \
+    if (_e != cudaSuccess) {                                       \
+      cleanup();                                                   \
+      if (_e == cudaErrorMemoryAllocation) {                       \
+        cudaGetLastError();                                        \
+        return DUALIP_OK; /* no room for the table: fp32 mode */   \
+      }                                                            \
+      set_error("%s failed: %s", #expr, cudaGetErrorString(_e));   \
+      return DUALIP_ECUDA;                                         \
+    }                                                              \
+  } while (0)
+  const size_t tab = (size_t)p->n_ctas * m;
+  CA_TRY(cudaMalloc(&xmax_d, sizeof(float) * p->n_classes));
+  CA_TRY(cudaMalloc(&table, sizeof(float) * tab));
+  CA_TRY(cudaMalloc(&row_max, sizeof(float) * m));
+  CA_TRY(cudaMalloc(&row_sum, sizeof(float) * m));
+  CA_TRY(cudaMalloc(&long_bound, sizeof(float) * m));
+  CA_TRY(cudaMalloc(&row_cnt, sizeof(unsigned int) * m));
+  CA_TRY(cudaMemcpyAsync(xmax_d, xmax.data(), sizeof(float) * p->n_classes, cudaMemcpyHostToDevice, stream));
+  CA_TRY(cudaMemsetAsync(table, 0, sizeof(float) * tab, stream));
+  CA_TRY(cudaMemsetAsync(long_bound, 0, sizeof(float) * m, stream));
+  CA_TRY(cudaMemsetAsync(row_cnt, 0, sizeof(unsigned int) * m, stream));
+  if (p->n_slabs > 0)
+    cta_row_bound_kernel<unsigned short><<<p->n_ctas, p->threads, 0, stream>>>(
+        p->a_t, reinterpret_cast<const unsigned short*>(p->row_t), p->hdr, p->n_slabs, xmax_d, m, table, row_cnt);
+  if (p->n_long > 0) {
+    const int blocks = (int)std::min<int64_t>((p->n_long + 7) / 8, (int64_t)p->n_sms * 8);
+    long_row_bound_kernel<<<blocks, 256, 0, stream>>>(p->longcols, p->n_long, p->long_a, p->long_row, xmax_d, long_bound, row_cnt);
+  }
+  bound_reduce_kernel<<<(m + 255) / 256, 256, 0, stream>>>(table, p->n_ctas, m, row_max, row_sum);
+  std::vector<float> h_max(m), h_sum(m), h_long(m);
+  std::vector<unsigned int> h_cnt(m);
+  CA_TRY(cudaMemcpyAsync(h_max.data(), row_max, sizeof(float) * m, cudaMemcpyDeviceToHost, stream));
+  CA_TRY(cudaMemcpyAsync(h_sum.data(), row_sum, sizeof(float) * m, cudaMemcpyDeviceToHost, stream));
+  CA_TRY(cudaMemcpyAsync(h_long.data(), long_bound, sizeof(float) * m, cudaMemcpyDeviceToHost, stream));
+  CA_TRY(cudaMemcpyAsync(h_cnt.data(), row_cnt, sizeof(unsigned int) * m, cudaMemcpyDeviceToHost, stream));
+  CA_TRY(cudaStreamSynchronize(stream));
+  CA_TRY(cudaGetLastError());
+  cleanup();
+#undef CA_TRY
+  double bmax = 0.0, total_max = 0.0;
+  for (int r = 0; r < m; ++r) {
+    bmax = std::max(bmax, (double)h_max[r]);
+    total_max = std::max(total_max, (double)h_sum[r] + (double)h_long[r]);
+  }
+  if (!(bmax < INFINITY) || !(total_max < INFINITY)) return DUALIP_OK;
+  // the float table itself carries rounding error: 1.001 covers it.  B * 2^F <= 2^30 leaves 2^30 of headroom for the
+  // +-1/2 per term of the integer rounding (up to 2^31 terms).
+  int F = 20;
+  if (bmax > 0.0) F = (int)floor(log2(1073741824.0 / (bmax * 1.001)));
+  F = std::max(-64, std::min(64, F));
+  const double q = ldexp(1.0, -F);
+  if (total_max * 1.001 * ldexp(1.0, F) >= 7.0e13) return DUALIP_OK;  // grid-wide high parts must fit 32 bits (2^46 = 7.04e13)
+  double relerr = 0.0;
+  for (int r = 0; r < m; ++r) {
+    const double A = (double)h_sum[r] + (double)h_long[r];
+    if (h_cnt[r] > 0 && A > 0.0) relerr = std::max(relerr, q * sqrt((double)h_cnt[r] / 12.0) / A);
+  }
+  p->fx_bits = F;
+  p->fx_scale = (float)ldexp(1.0, F);
+  p->fx_inv = q;
+  p->fx_bound = bmax;
+  p->fx_relerr = relerr;
+  const bool forced = env && strcmp(env, "fixed") == 0;
+  if (relerr <= 2.4e-7 || forced) p->fixed_point = 1;
+  return DUALIP_OK;
 }
 
 }  // namespace dualip
@@ -1178,6 +1551,8 @@ void dualip_plan_destroy(dualip_plan* p) {
   cudaFree(p->long_row);
   cudaFree(p->classes_dev);
   cudaFree(p->acc);
+  cudaFree(p->acc_lo);
+  cudaFree(p->acc_hi);
   cudaFree(p->acc_scal);
   cudaFree(p->counter);
   cudaFree(p->lambda_stage);
@@ -1238,6 +1613,8 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   memcpy(p->classes_host, d->classes, sizeof(dualip_proj_class) * d->n_classes);
   const char* fb = getenv("DUALIP_FLUSH");
   p->flush_bulk = (fb && strcmp(fb, "atomic") == 0) ? 0 : 1;
+  const char* pf = getenv("DUALIP_PREFETCH");
+  p->prefetch = pf ? atoi(pf) : 0;
 
   auto fail = [&](int rc) {
     dualip_plan_destroy(p);
@@ -1251,20 +1628,29 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   }
   p->n_sms = prop.multiProcessorCount;
 
-  // shared-memory mode and CTA shape: ONE 1024-thread CTA per SM.  lambda and the gradient accumulator are per CTA,
-  // so a single CTA halves their footprint (and the flush traffic) against two 512-thread CTAs, and leaves the rest
-  // of the 256 KB L1/shared array to the L1 that serves the second pass over a slab.
-  p->threads = 1024;
+  // shared-memory mode and CTA shape: ONE CTA per SM.  lambda and the gradient accumulator are per CTA, so a single
+  // CTA halves their footprint (and the flush traffic) against two smaller CTAs; 16 warps with all loads of a slab in
+  // flight at once (plus the L2 prefetch of the next slab) cover the HBM latency.
+  p->threads = kThreads;
   p->n_ctas = p->n_sms;
   const size_t fixed = smem_fixed_bytes(p->n_classes);
   const size_t m_pad = ((size_t)p->m + 3) & ~(size_t)3;
   const size_t stash_bytes = (size_t)(p->threads / 32) * kStashDeg * kSlabW * sizeof(float);
-  const size_t need0 = fixed + 8 * m_pad + stash_bytes;
-  const size_t need1 = fixed + 4 * m_pad + stash_bytes;
+  const size_t stage_bytes = (size_t)(p->threads / 32) * kStageBytes + 128;
+  p->row_bits = (p->m <= 65536) ? 16 : 32;
   const size_t smem_max = std::min<size_t>(kSmemBudget, prop.sharedMemPerBlockOptin) - 1024;  // static smem + slack
-  if (need0 <= smem_max) {
+  const char* env_stage = getenv("DUALIP_STAGE");
+  const bool want_stage = !(env_stage && strcmp(env_stage, "0") == 0);
+  const size_t need1 = fixed + 4 * m_pad + stash_bytes;
+  // mode 0 (register path): lambda + accumulator, plus the per-warp TMA staging buffers when they fit
+  if (p->row_bits == 16 && want_stage && fixed + 8 * m_pad + stage_bytes <= smem_max) {
     p->smode = 0;
-    p->smem_bytes = need0;
+    p->stage = 1;
+    p->smem_bytes = fixed + 8 * m_pad + stage_bytes;
+  } else if (p->row_bits == 16 && fixed + 8 * m_pad + 128 <= smem_max) {
+    p->smode = 0;
+    p->stage = 0;
+    p->smem_bytes = fixed + 8 * m_pad + 128;
   } else if (need1 <= smem_max) {
     p->smode = 1;
     p->smem_bytes = need1;
@@ -1274,7 +1660,6 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   }
   const char* env_ctas = getenv("DUALIP_CTAS");
   if (env_ctas && atoi(env_ctas) > 0) p->n_ctas = atoi(env_ctas);
-  p->row_bits = (p->m <= 65536) ? 16 : 32;
 
 #define DUALIP_TRY_FAIL(expr)                                                                    \
   do {                                                                                           \
@@ -1295,7 +1680,15 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
     const int64_t want = std::max<int64_t>(1, (p->n_slabs + warps_per_cta - 1) / warps_per_cta);
     if (!(env_ctas && atoi(env_ctas) > 0) && want < p->n_ctas) p->n_ctas = (int)want;
   }
+  {
+    int rc = choose_accumulator(p, stream);
+    if (rc != DUALIP_OK) return fail(rc);
+  }
   // small state
+  DUALIP_TRY_FAIL(cudaMalloc(&p->acc_lo, sizeof(int) * (m_pad + 4)));
+  DUALIP_TRY_FAIL(cudaMemset(p->acc_lo, 0, sizeof(int) * (m_pad + 4)));
+  DUALIP_TRY_FAIL(cudaMalloc(&p->acc_hi, sizeof(int) * (m_pad + 4)));
+  DUALIP_TRY_FAIL(cudaMemset(p->acc_hi, 0, sizeof(int) * (m_pad + 4)));
   DUALIP_TRY_FAIL(cudaMalloc(&p->classes_dev, sizeof(dualip_proj_class) * p->n_classes));
   DUALIP_TRY_FAIL(cudaMemcpy(p->classes_dev, p->classes_host, sizeof(dualip_proj_class) * p->n_classes, cudaMemcpyHostToDevice));
   DUALIP_TRY_FAIL(cudaMalloc(&p->acc, sizeof(float) * (m_pad + 4)));
@@ -1332,9 +1725,10 @@ int dualip_plan_info(const dualip_plan* p, int64_t* out, int cap) {
     set_error("null argument");
     return DUALIP_EINVAL;
   }
-  const int64_t v[12] = {p->n_slabs, p->n_long, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
-                         p->smode,   p->rows32 * kSlabW, (p->n_long > 0) ? 2 : 1, (int64_t)p->owned_bytes, p->n_short, p->nnz};
-  for (int i = 0; i < cap && i < 12; ++i) out[i] = v[i];
+  const int64_t v[15] = {p->n_slabs, p->n_long, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
+                         p->smode,   p->rows32 * kSlabW, (p->n_long > 0) ? 2 : 1, (int64_t)p->owned_bytes, p->n_short, p->nnz,
+                         p->fixed_point, p->fx_bits, (int64_t)(p->fx_relerr * 1e12)};
+  for (int i = 0; i < cap && i < 15; ++i) out[i] = v[i];
   return DUALIP_OK;
 }
 

@@ -71,6 +71,11 @@ __device__ __forceinline__ void bulk_reduce_add_f32_s2g(float* dst_gmem, const f
                "r"(smem_u32(src_smem)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void bulk_reduce_add_s32_s2g(int* dst_gmem, const int* src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.s32 [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 

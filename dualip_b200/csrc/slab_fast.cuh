@@ -1,0 +1,401 @@
+// Register-resident processing of one slab (32 columns of equal length D <= kRegDeg), specialised on D.
+// Included by calc.cu after KArgs / make_v.  Reference semantics: matching.py:116-188 per column, with
+// projections/simplex.py:143-236 (batched Duchi with pre-clamp), box.py:16, cone.py:21-28.
+//
+// One load phase: D/4 LDG.128 for a, D/4 LDG.128 for c, D/4 LDG.64 for the uint16 row ids (plus the short tail
+// chunks), everything issued before the first use.  The column then lives in registers: u = max(v, 0), the
+// feasibility / top-2 tests, the threshold search and the scatter all run on fully unrolled register arrays, so
+// there is no second pass over memory, no stash traffic and no per-entry index arithmetic.
+#pragma once
+
+namespace dualip {
+
+constexpr int kRegDeg = 16;  // longest column handled by the register path
+
+// ---- streaming loads: the slab arrays are read exactly once per launch, so they bypass L1 allocation ----
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_stream_f2(const float* p) {
+  float2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float* p) {
+  float v;
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint2 ldg_stream_u2(const void* p) {
+  uint2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u1(const void* p) {
+  uint32_t v;
+  asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_stream_h1(const void* p) {
+  unsigned short v;
+  asm("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return (uint32_t)v;
+}
+// One thread asks the TMA engine to pull a contiguous range into L2 (no register or shared-memory destination).
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ float lds_off(const unsigned char* base, uint32_t byte_off) {
+  return *reinterpret_cast<const float*>(base + byte_off);
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// A value slightly below q (for lower bounds computed with a few rounding errors).
+__device__ __forceinline__ float nudge_down(float q) { return fmaf(-6e-7f, fabsf(q), q) - 1e-37f; }
+
+// Predicated accumulation over the current support {u > t}: one compare plus three predicated updates per entry.
+__device__ __forceinline__ void support_step(float u, float t, float& fsum, float& umin, int& cnt) {
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.gt.f32 p, %3, %4;\n\t"
+      "@p add.f32 %0, %0, %3;\n\t"
+      "@p min.f32 %1, %1, %3;\n\t"
+      "@p add.s32 %2, %2, 1;\n\t}"
+      : "+f"(fsum), "+f"(umin), "+r"(cnt)
+      : "f"(u), "f"(t));
+}
+// Same with the support sum in fp64 (torch's CPU cumsum accumulates float32 in double) and the largest excluded value.
+__device__ __forceinline__ void support_exact(float u, float t, double& ssum, float& umin, float& uout, int& cnt) {
+  asm("{\n\t.reg .pred p;\n\t.reg .f64 d;\n\t"
+      "setp.gt.f32 p, %4, %5;\n\t"
+      "cvt.f64.f32 d, %4;\n\t"
+      "@p add.f64 %0, %0, d;\n\t"
+      "@p min.f32 %1, %1, %4;\n\t"
+      "@!p max.f32 %2, %2, %4;\n\t"
+      "@p add.s32 %3, %3, 1;\n\t}"
+      : "+d"(ssum), "+f"(umin), "+f"(uout), "+r"(cnt)
+      : "f"(u), "f"(t));
+}
+// Pins a value in a register (the compiler would otherwise rematerialise shared-window addresses at every use).
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+
+template <int D>
+struct ColRegs {
+  float a[D], c[D];
+  uint32_t ro[D];  // row * 4: byte offset into an m-float shared-memory array
+};
+
+template <int D>
+__device__ __forceinline__ void load_cols(ColRegs<D>& R, const float* __restrict__ a_s, const float* __restrict__ c_s,
+                                          const unsigned short* __restrict__ r_s, int lane) {
+  // a_s / c_s / r_s point at the slab's first element
+  constexpr int NF = D / 4;
+  float4 va[NF > 0 ? NF : 1], vc[NF > 0 ? NF : 1];
+  uint2 vr[NF > 0 ? NF : 1];
+#pragma unroll
+  for (int q = 0; q < NF; ++q) {
+    va[q] = ldg_stream_f4(a_s + q * 128 + lane * 4);
+    vc[q] = ldg_stream_f4(c_s + q * 128 + lane * 4);
+    vr[q] = ldg_stream_u2(r_s + q * 128 + lane * 4);
+  }
+  float2 ta = make_float2(0.f, 0.f), tc = make_float2(0.f, 0.f);
+  uint32_t tr = 0;
+  if (D & 2) {
+    ta = ldg_stream_f2(a_s + NF * 128 + lane * 2);
+    tc = ldg_stream_f2(c_s + NF * 128 + lane * 2);
+    tr = ldg_stream_u1(r_s + NF * 128 + lane * 2);
+  }
+  float sa = 0.f, sc = 0.f;
+  uint32_t sr = 0;
+  if (D & 1) {
+    sa = ldg_stream_f1(a_s + NF * 128 + (D & 2) * 32 + lane);
+    sc = ldg_stream_f1(c_s + NF * 128 + (D & 2) * 32 + lane);
+    sr = ldg_stream_h1(r_s + NF * 128 + (D & 2) * 32 + lane);
+  }
+#pragma unroll
+  for (int q = 0; q < NF; ++q) {
+    R.a[4 * q + 0] = va[q].x;
+    R.a[4 * q + 1] = va[q].y;
+    R.a[4 * q + 2] = va[q].z;
+    R.a[4 * q + 3] = va[q].w;
+    R.c[4 * q + 0] = vc[q].x;
+    R.c[4 * q + 1] = vc[q].y;
+    R.c[4 * q + 2] = vc[q].z;
+    R.c[4 * q + 3] = vc[q].w;
+    R.ro[4 * q + 0] = (vr[q].x << 2) & 0x3fffcu;
+    R.ro[4 * q + 1] = (vr[q].x >> 14) & 0x3fffcu;
+    R.ro[4 * q + 2] = (vr[q].y << 2) & 0x3fffcu;
+    R.ro[4 * q + 3] = (vr[q].y >> 14) & 0x3fffcu;
+  }
+  if (D & 2) {
+    R.a[4 * NF + 0] = ta.x;
+    R.a[4 * NF + 1] = ta.y;
+    R.c[4 * NF + 0] = tc.x;
+    R.c[4 * NF + 1] = tc.y;
+    R.ro[4 * NF + 0] = (tr << 2) & 0x3fffcu;
+    R.ro[4 * NF + 1] = (tr >> 14) & 0x3fffcu;
+  }
+  if (D & 1) {
+    R.a[D - 1] = sa;
+    R.c[D - 1] = sc;
+    R.ro[D - 1] = sr << 2;
+  }
+}
+
+// Same layout, read from this warp's shared-memory staging buffer (filled by the TMA engine, see stage_issue()):
+// [a: 32*D floats][c: 32*D floats][row: 32*D uint16].  LDS.128 / LDS.64 with lane-contiguous addresses: conflict-free.
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t saddr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u1(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_h1(uint32_t saddr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr) : "memory");
+  return (uint32_t)v;
+}
+template <int D>
+__device__ __forceinline__ void load_cols_staged(ColRegs<D>& R, uint32_t buf, int lane) {
+  constexpr int NF = D / 4;
+  const uint32_t a_s = buf + lane * 16, c_s = buf + 128 * D + lane * 16, r_s = buf + 256 * D + lane * 8;
+#pragma unroll
+  for (int q = 0; q < NF; ++q) {
+    const float4 va = lds_f4(a_s + q * 512);
+    const float4 vc = lds_f4(c_s + q * 512);
+    const uint2 vr = lds_u2(r_s + q * 256);
+    R.a[4 * q + 0] = va.x, R.a[4 * q + 1] = va.y, R.a[4 * q + 2] = va.z, R.a[4 * q + 3] = va.w;
+    R.c[4 * q + 0] = vc.x, R.c[4 * q + 1] = vc.y, R.c[4 * q + 2] = vc.z, R.c[4 * q + 3] = vc.w;
+    R.ro[4 * q + 0] = (vr.x << 2) & 0x3fffcu;
+    R.ro[4 * q + 1] = (vr.x >> 14) & 0x3fffcu;
+    R.ro[4 * q + 2] = (vr.y << 2) & 0x3fffcu;
+    R.ro[4 * q + 3] = (vr.y >> 14) & 0x3fffcu;
+  }
+  if (D & 2) {
+    const float2 ta = lds_f2(buf + NF * 512 + lane * 8);
+    const float2 tc = lds_f2(buf + 128 * D + NF * 512 + lane * 8);
+    const uint32_t tr = lds_u1(buf + 256 * D + NF * 256 + lane * 4);
+    R.a[4 * NF + 0] = ta.x, R.a[4 * NF + 1] = ta.y;
+    R.c[4 * NF + 0] = tc.x, R.c[4 * NF + 1] = tc.y;
+    R.ro[4 * NF + 0] = (tr << 2) & 0x3fffcu;
+    R.ro[4 * NF + 1] = (tr >> 14) & 0x3fffcu;
+  }
+  if (D & 1) {
+    R.a[D - 1] = lds_f1(buf + (NF * 128 + (D & 2) * 32 + lane) * 4);
+    R.c[D - 1] = lds_f1(buf + 128 * D + (NF * 128 + (D & 2) * 32 + lane) * 4);
+    R.ro[D - 1] = lds_h1(buf + 256 * D + (NF * 128 + (D & 2) * 32 + lane) * 2) << 2;
+  }
+}
+
+// Staging of a warp's NEXT slab: one lane arms the warp's mbarrier with the slab's byte count and issues three bulk
+// async copies (TMA engine, SASS UBLKCP) global -> shared; they land while the warp works on the current slab.
+constexpr int kStageBytes = kRegDeg * 32 * 10;  // per warp: a + c + uint16 rows of the longest register-path slab
+__device__ __forceinline__ void stage_issue(unsigned char* buf, uint64_t* bar, const float* a_s, const float* c_s,
+                                            const unsigned short* r_s, int d) {
+  fence_proxy_async_smem();  // the warp's reads of the buffer (generic proxy) precede the engine's writes
+  mbar_expect_tx(bar, (uint32_t)(320 * d));
+  bulk_g2s(buf, a_s, (uint32_t)(128 * d), bar);
+  bulk_g2s(buf + 128 * d, c_s, (uint32_t)(128 * d), bar);
+  bulk_g2s(buf + 256 * d, r_s, (uint32_t)(64 * d), bar);
+}
+
+// Shared tail of both projections: scatter a*x into the CTA's gradient accumulator and form the c.x and ||x||^2
+// partials.  ACC 1: the accumulator is 32-bit fixed point (value * 2^F, F chosen at plan time from a bound on every
+// CTA's row sums): one native fire-and-forget ATOMS.ADD per non-zero, order-independent and therefore bitwise
+// reproducible.  ACC 0: fp32 atomicAdd, which sm_100a implements as a load / add / compare-and-swap loop
+// (ATOMS.CAST.SPIN); kept for unbounded projection classes (open cones), where no overflow bound exists.
+template <int D, int SMODE, int ACC>
+__device__ __forceinline__ void emit_cols(const KArgs& k, const ColRegs<D>& R, const float (&x)[D], uint32_t s_grad_u32,
+                                          float& cxs, float& xxs) {
+#pragma unroll
+  for (int q = 0; q < D; ++q) {
+    const float g = __fmul_rn(R.a[q], x[q]);  // matching.py:153 (A.values * x.values, then row sums)
+    if (ACC == 1) {
+      const int gi = __float2int_rn(g * k.fx_scale);
+      if (gi != 0) asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(s_grad_u32 + R.ro[q]), "r"(gi) : "memory");
+    } else if (g != 0.f) {
+      if (SMODE <= 1)
+        asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(s_grad_u32 + R.ro[q]), "f"(g) : "memory");
+      else
+        atomicAdd(k.acc + (R.ro[q] >> 2), g);
+    }
+    cxs = fmaf(R.c[q], x[q], cxs);
+    xxs = fmaf(x[q], x[q], xxs);
+  }
+}
+
+template <int D, int SMODE>
+__device__ __forceinline__ void make_v_cols(const KArgs& k, const ColRegs<D>& R, const unsigned char* s_lam_b, float s,
+                                            float (&v)[D]) {
+#pragma unroll
+  for (int q = 0; q < D; ++q) {
+    const float lam_s = (SMODE == 0) ? lds_off(s_lam_b, R.ro[q]) : __fmul_rn(s, __ldg(k.lambda + (R.ro[q] >> 2)));
+    v[q] = make_v(R.a[q], lam_s, s, R.c[q]);
+  }
+}
+
+// box / cone / identity (box.py:16, cone.py:21-28): x = min(max(v, lo), hi).
+template <int D, int SMODE>
+__device__ __forceinline__ void fast_clamp(const KArgs& k, const dualip_proj_class& pc, const ColRegs<D>& R, bool active,
+                                           const unsigned char* s_lam_b, float s, float (&x)[D]) {
+  const float lo = active ? pc.lo : 0.f, hi = active ? pc.hi : 0.f;  // padding lanes produce x = 0
+  make_v_cols<D, SMODE>(k, R, s_lam_b, s, x);
+#pragma unroll
+  for (int q = 0; q < D; ++q) x[q] = fminf(fmaxf(x[q], lo), hi);
+}
+
+// simplex / simplex_eq (simplex.py:143-236 per column at its true length).  On return x holds the projection;
+// branch: 0 feasible, 1 top-2 shortcut, 2 sorted scan ("Duchi"); rho: support size for branches 1 and 2.
+template <int D, int SMODE>
+__device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_class& pc, const ColRegs<D>& R, bool active,
+                                             const unsigned char* s_lam_b, float s, float (&u)[D], int& branch, int& rho) {
+  const unsigned FULL = 0xffffffffu;
+  make_v_cols<D, SMODE>(k, R, s_lam_b, s, u);
+  float S = 0.f, m1 = -1.f, m2 = -1.f;
+#pragma unroll
+  for (int q = 0; q < D; ++q) {
+    u[q] = fmaxf(u[q], 0.f);             // simplex.py:148
+    S = __fadd_rn(S, u[q]);              // column sum in entry order
+    m2 = fmaxf(m2, fminf(m1, u[q]));     // second largest (duplicates of the maximum count)
+    m1 = fmaxf(m1, u[q]);
+  }
+  const float z = pc.z;
+  const bool feasible = (pc.kind == DUALIP_PROJ_SIMPLEX) && (S <= pc.z_thr);                          // simplex.py:153-155
+  const bool padded = (D > 1) || !(pc.flags & DUALIP_PROJ_FLAG_D1_UNPADDED);                          // simplex.py:166
+  const float m2p = fmaxf(m2, 0.f);  // the reference's zero padding takes part in its top-2
+  const float un1 = (z == 1.0f) ? m1 : __fdiv_rn(m1, z), un2 = (z == 1.0f) ? m2p : __fdiv_rn(m2p, z);
+  const bool shortcut = !feasible && padded && (__fsub_rn(un1, un2) > 1.0f);                          // simplex.py:172-178
+  branch = feasible ? 0 : (shortcut ? 1 : 2);
+  rho = shortcut ? 1 : 0;
+  float theta = 0.f;
+  const bool need_theta = active && branch == 2;
+
+  if (__any_sync(FULL, need_theta)) {
+    // ---- Michelot fixed point, then alignment with the reference's fp32 conditions (simplex.py:207-231) ----
+    // theta* = max_k (css_k - z)/k over the sorted prefixes, so (S - z)/D, max - z and (top2 - z)/2 are lower bounds
+    // to start from; t <- (sum_{u>t} u - z)/#{u>t} then increases to theta* (Newton from below on
+    // sum max(u - t, 0) = z).  fp32 sums are scaled down by `guard` so that no step overshoots theta*.
+    constexpr float guard = 1.0f - 2.4e-7f * (float)D;
+    float tf = fmaxf(nudge_down((S * guard - z) * (1.0f / (float)D)), nudge_down(m1 - z));
+    if (D >= 2) tf = fmaxf(tf, nudge_down(((m1 + m2) * guard - z) * 0.5f));
+    tf = (tf > 0.f) ? tf : -1.f;
+    int cnt = 0;
+    for (int it = 0; it < 64; ++it) {
+      cnt = 0;
+      float fsum = 0.f, umin = INFINITY;
+#pragma unroll
+      for (int q = 0; q < D; ++q) support_step(u[q], tf, fsum, umin, cnt);
+      // next step; converged when it removes nothing, i.e. the smallest support value stays above it
+      const float tn = nudge_down((fsum * guard - z) * rcp_approx((float)max(cnt, 1)));
+      const bool done = !need_theta || cnt == 0 || !(tn > tf) || umin > tn;
+      if (!done) tf = tn;
+      if (__all_sync(FULL, done)) break;
+    }
+    // exact sums over the support (fp64, like torch's CPU cumsum) and the two boundary values, then the reference's
+    // own conditions cond_rho / cond_{rho+1} in fp32; the support shrinks or grows if rounding disagrees
+    float th = 0.f;
+    for (int fix = 0; fix < 6; ++fix) {
+      double ssum = 0.0;
+      float umin = INFINITY, uout = -INFINITY;
+      cnt = 0;
+#pragma unroll
+      for (int q = 0; q < D; ++q) support_exact(u[q], tf, ssum, umin, uout, cnt);
+      th = __fdiv_rn(__fsub_rn((float)ssum, z), (float)max(cnt, 1));                                 // simplex.py:228-230
+      bool changed = false;
+      if (need_theta && cnt > 1 && !(__fsub_rn(umin, th) > 0.f)) {
+        tf = umin;  // cond_rho fails in the fp32 formula: drop the smallest support value(s)
+        changed = true;
+      } else if (need_theta && uout > -INFINITY) {
+        const float t1 = __fdiv_rn(__fsub_rn((float)(ssum + (double)uout), z), (float)(cnt + 1));
+        if (__fsub_rn(uout, t1) > 0.f) {  // cond_{rho+1} holds: the support grows
+          tf = (uout > 0.f) ? __uint_as_float(__float_as_uint(uout) - 1u) : -1.f;
+          changed = true;
+        }
+      }
+      if (!__any_sync(FULL, changed)) break;
+    }
+    if (need_theta) {
+      theta = th;
+      rho = max(cnt, 1);
+    }
+  }
+  if (__any_sync(FULL, shortcut)) {
+    // x = z at the (unique) maximum, 0 elsewhere (simplex.py:185-190); theta stays 0 so the subtraction below is exact
+#pragma unroll
+    for (int q = 0; q < D; ++q) u[q] = shortcut ? ((u[q] == m1) ? z : 0.f) : u[q];
+  }
+  if (!active) theta = INFINITY;  // padding lanes (and nothing else) produce x = 0
+#pragma unroll
+  for (int q = 0; q < D; ++q) u[q] = fmaxf(__fsub_rn(u[q], theta), 0.f);                             // simplex.py:233
+}
+
+// One slab of column length D, whole life cycle.  a_s/c_s/r_s: the slab's first element in global memory; when
+// `staged` the same bytes are waiting in (or on their way to) the warp's staging buffer.  issue_next() is called as
+// soon as the buffer has been read out, to start the copy of the warp's next slab.
+template <int D, int SMODE, int ACC, typename IssueNext>
+__device__ __forceinline__ void fast_slab(const KArgs& k, const dualip_proj_class& pc, const float* __restrict__ a_s,
+                                          const float* __restrict__ c_s, const unsigned short* __restrict__ r_s, int lane,
+                                          bool active, const unsigned char* s_lam_b, uint32_t s_grad_u32, float s,
+                                          int64_t slab_index, double& cx, double& xx, bool staged,
+                                          const unsigned char* stage_buf, uint64_t* stage_bar, uint32_t& stage_phase,
+                                          IssueNext issue_next) {
+  ColRegs<D> R;
+  if (staged) {
+    mbar_wait(stage_bar, stage_phase);
+    stage_phase ^= 1u;
+    load_cols_staged<D>(R, smem_u32(stage_buf), lane);
+  } else {
+    load_cols<D>(R, a_s, c_s, r_s, lane);
+  }
+  issue_next();
+  float x[D];
+  int branch = -1, rho = 0;
+  if (pc.kind == DUALIP_PROJ_CLAMP)
+    fast_clamp<D, SMODE>(k, pc, R, active, s_lam_b, s, x);
+  else
+    fast_simplex<D, SMODE>(k, pc, R, active, s_lam_b, s, x, branch, rho);
+  if ((k.x_out != nullptr) || (k.diag != nullptr)) {  // save_primal / diagnostics: straight from registers
+    if (active) {
+      const int64_t os = k.orig_start[slab_index * 32 + lane];
+      if (k.x_out) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) k.x_out[os + q] = x[q];
+      }
+      if (k.diag && branch >= 0) k.diag[os] = (uint8_t)(branch | (min(rho, 63) << 2));
+    }
+  }
+  float cxs = 0.f, xxs = 0.f;
+  emit_cols<D, SMODE, ACC>(k, R, x, s_grad_u32, cxs, xxs);
+  cx += (double)cxs;
+  xx += (double)xxs;
+}
+
+}  // namespace dualip

@@ -99,7 +99,9 @@ void dualip_plan_destroy(dualip_plan* plan);
 /* Introspection: fills up to `cap` int64 values:
  * [0] n_slabs [1] n_long_cols [2] n_ctas [3] threads/cta [4] smem bytes/cta [5] row index bits
  * [6] smem mode (0: lambda+grad in smem, 1: grad in smem, 2: neither) [7] stored slab elements (incl. padding)
- * [8] kernel launches per calc  [9] plan-owned device bytes [10] columns stored in slabs [11] nnz */
+ * [8] kernel launches per calc  [9] plan-owned device bytes [10] columns stored in slabs [11] nnz
+ * [12] 1 if the gradient is accumulated in 32-bit fixed point (deterministic), 0 for fp32 atomics
+ * [13] F: fixed-point fraction bits (value * 2^F)  [14] worst-row rounding-error estimate * 1e12 */
 int dualip_plan_info(const dualip_plan* plan, int64_t* out, int cap);
 
 /* One evaluation of the dual at lambda on this shard, epilogue included (single device).
