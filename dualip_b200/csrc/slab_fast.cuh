@@ -51,41 +51,35 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 __device__ __forceinline__ float lds_off(const unsigned char* base, uint32_t byte_off) {
   return *reinterpret_cast<const float*>(base + byte_off);
 }
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-// A value slightly below q (for lower bounds computed with a few rounding errors).
-__device__ __forceinline__ float nudge_down(float q) { return fmaf(-6e-7f, fabsf(q), q) - 1e-37f; }
-
-// Predicated accumulation over the current support {u > t}: one compare plus three predicated updates per entry.
-__device__ __forceinline__ void support_step(float u, float t, float& fsum, float& umin, int& cnt) {
-  asm("{\n\t.reg .pred p;\n\t"
-      "setp.gt.f32 p, %3, %4;\n\t"
-      "@p add.f32 %0, %0, %3;\n\t"
-      "@p min.f32 %1, %1, %3;\n\t"
-      "@p add.s32 %2, %2, 1;\n\t}"
-      : "+f"(fsum), "+f"(umin), "+r"(cnt)
-      : "f"(u), "f"(t));
-}
-// Same with the support sum in fp64 (torch's CPU cumsum accumulates float32 in double) and the largest excluded value.
-__device__ __forceinline__ void support_exact(float u, float t, double& ssum, float& umin, float& uout, int& cnt) {
-  asm("{\n\t.reg .pred p;\n\t.reg .f64 d;\n\t"
-      "setp.gt.f32 p, %4, %5;\n\t"
-      "cvt.f64.f32 d, %4;\n\t"
-      "@p add.f64 %0, %0, d;\n\t"
-      "@p min.f32 %1, %1, %4;\n\t"
-      "@!p max.f32 %2, %2, %4;\n\t"
-      "@p add.s32 %3, %3, 1;\n\t}"
-      : "+d"(ssum), "+f"(umin), "+f"(uout), "+r"(cnt)
-      : "f"(u), "f"(t));
-}
 // Pins a value in a register (the compiler would otherwise rematerialise shared-window addresses at every use).
 __device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
   uint32_t r;
   asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
   return r;
+}
+
+// Sorting networks on register arrays (descending), generated and zero-one verified by tools/gen_sort_networks.py.
+template <int D>
+struct SortNet {
+  static __device__ __forceinline__ void run(float (&)[D]) {}  // D = 1
+};
+#define DUALIP_CS(i, j)                     \
+  {                                         \
+    const float hi_ = fmaxf(w[i], w[j]);    \
+    w[j] = fminf(w[i], w[j]);               \
+    w[i] = hi_;                             \
+  }
+#include "sort_networks.inc"
+#undef DUALIP_CS
+
+// fl32(t / n) for a small positive integer n, correctly rounded without the division routine: q0 = t * fl(1/n),
+// exact residual r = t - q0*n by FMA, q = q0 + r * fl(1/n) (Markstein's correction step).
+template <int N>
+__device__ __forceinline__ float div_by_int(float t) {
+  constexpr float rn = 1.0f / (float)N;
+  const float q0 = __fmul_rn(t, rn);
+  const float r = __fmaf_rn(-q0, (float)N, t);
+  return __fmaf_rn(r, rn, q0);
 }
 
 template <int D>
@@ -240,7 +234,12 @@ __device__ __forceinline__ void emit_cols(const KArgs& k, const ColRegs<D>& R, c
     const float g = __fmul_rn(R.a[q], x[q]);  // matching.py:153 (A.values * x.values, then row sums)
     if (ACC == 1) {
       const int gi = __float2int_rn(g * k.fx_scale);
-      if (gi != 0) asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(s_grad_u32 + R.ro[q]), "r"(gi) : "memory");
+#ifdef DUALIP_COND_ADD
+      if (gi != 0)
+#endif
+      // unconditional: adding 0 is harmless, and ptxas would wrap a conditional ATOMS in a branch (4 instructions
+      // instead of 1); the extra shared-memory wavefronts fit the MIO budget (profiles/: ubench_smem2)
+      asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(s_grad_u32 + R.ro[q]), "r"(gi) : "memory");
     } else if (g != 0.f) {
       if (SMODE <= 1)
         asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(s_grad_u32 + R.ro[q]), "f"(g) : "memory");
@@ -272,6 +271,18 @@ __device__ __forceinline__ void fast_clamp(const KArgs& k, const dualip_proj_cla
   for (int q = 0; q < D; ++q) x[q] = fminf(fmaxf(x[q], lo), hi);
 }
 
+template <int D, int I>
+__device__ __forceinline__ void scan_sorted(const float (&w)[D], float z, double& acc, float& t_sel, int& rho_sel) {
+  if constexpr (I < D) {
+    acc += (double)w[I];
+    const float t = __fsub_rn((float)acc, z);
+    const bool cond = w[I] > div_by_int<I + 1>(t);
+    t_sel = cond ? t : t_sel;
+    rho_sel = cond ? (I + 1) : rho_sel;
+    scan_sorted<D, I + 1>(w, z, acc, t_sel, rho_sel);
+  }
+}
+
 // simplex / simplex_eq (simplex.py:143-236 per column at its true length).  On return x holds the projection;
 // branch: 0 feasible, 1 top-2 shortcut, 2 sorted scan ("Duchi"); rho: support size for branches 1 and 2.
 template <int D, int SMODE>
@@ -299,52 +310,23 @@ __device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_c
   const bool need_theta = active && branch == 2;
 
   if (__any_sync(FULL, need_theta)) {
-    // ---- Michelot fixed point, then alignment with the reference's fp32 conditions (simplex.py:207-231) ----
-    // theta* = max_k (css_k - z)/k over the sorted prefixes, so (S - z)/D, max - z and (top2 - z)/2 are lower bounds
-    // to start from; t <- (sum_{u>t} u - z)/#{u>t} then increases to theta* (Newton from below on
-    // sum max(u - t, 0) = z).  fp32 sums are scaled down by `guard` so that no step overshoots theta*.
-    constexpr float guard = 1.0f - 2.4e-7f * (float)D;
-    float tf = fmaxf(nudge_down((S * guard - z) * (1.0f / (float)D)), nudge_down(m1 - z));
-    if (D >= 2) tf = fmaxf(tf, nudge_down(((m1 + m2) * guard - z) * 0.5f));
-    tf = (tf > 0.f) ? tf : -1.f;
-    int cnt = 0;
-    for (int it = 0; it < 64; ++it) {
-      cnt = 0;
-      float fsum = 0.f, umin = INFINITY;
+    // ---- the reference's sorted scan itself (simplex.py:207-231), on a sorted copy of the column in registers ----
+    //   css_i = fl32(prefix sum accumulated in fp64)            (torch's CPU cumsum of float32 accumulates in double)
+    //   cond_i = u_(i) - fl((css_i - z)/i) > 0  <=>  u_(i) > fl((css_i - z)/i)
+    //   rho = max{i : cond_i},  theta = (css_rho - z)/rho
+    // A sorting network (no branches, no data-dependent trip counts) replaces torch.sort; every lane of the warp runs
+    // it, lanes that do not need theta ignore the result.
+    float w[D];
 #pragma unroll
-      for (int q = 0; q < D; ++q) support_step(u[q], tf, fsum, umin, cnt);
-      // next step; converged when it removes nothing, i.e. the smallest support value stays above it
-      const float tn = nudge_down((fsum * guard - z) * rcp_approx((float)max(cnt, 1)));
-      const bool done = !need_theta || cnt == 0 || !(tn > tf) || umin > tn;
-      if (!done) tf = tn;
-      if (__all_sync(FULL, done)) break;
-    }
-    // exact sums over the support (fp64, like torch's CPU cumsum) and the two boundary values, then the reference's
-    // own conditions cond_rho / cond_{rho+1} in fp32; the support shrinks or grows if rounding disagrees
-    float th = 0.f;
-    for (int fix = 0; fix < 6; ++fix) {
-      double ssum = 0.0;
-      float umin = INFINITY, uout = -INFINITY;
-      cnt = 0;
-#pragma unroll
-      for (int q = 0; q < D; ++q) support_exact(u[q], tf, ssum, umin, uout, cnt);
-      th = __fdiv_rn(__fsub_rn((float)ssum, z), (float)max(cnt, 1));                                 // simplex.py:228-230
-      bool changed = false;
-      if (need_theta && cnt > 1 && !(__fsub_rn(umin, th) > 0.f)) {
-        tf = umin;  // cond_rho fails in the fp32 formula: drop the smallest support value(s)
-        changed = true;
-      } else if (need_theta && uout > -INFINITY) {
-        const float t1 = __fdiv_rn(__fsub_rn((float)(ssum + (double)uout), z), (float)(cnt + 1));
-        if (__fsub_rn(uout, t1) > 0.f) {  // cond_{rho+1} holds: the support grows
-          tf = (uout > 0.f) ? __uint_as_float(__float_as_uint(uout) - 1u) : -1.f;
-          changed = true;
-        }
-      }
-      if (!__any_sync(FULL, changed)) break;
-    }
+    for (int q = 0; q < D; ++q) w[q] = u[q];
+    SortNet<D>::run(w);
+    double acc = 0.0;
+    float t_sel = __fsub_rn(w[0], z);
+    int rho_sel = 1;  // no cond true: torch's max over an all-zero mask gives index 0
+    scan_sorted<D, 0>(w, z, acc, t_sel, rho_sel);
     if (need_theta) {
-      theta = th;
-      rho = max(cnt, 1);
+      theta = __fdiv_rn(t_sel, (float)rho_sel);                                                     // simplex.py:228-230
+      rho = rho_sel;
     }
   }
   if (__any_sync(FULL, shortcut)) {
