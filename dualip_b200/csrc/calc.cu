@@ -549,6 +549,10 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
         DUALIP_FAST_CASE(14)
         DUALIP_FAST_CASE(15)
         DUALIP_FAST_CASE(16)
+        DUALIP_FAST_CASE(17)
+        DUALIP_FAST_CASE(18)
+        DUALIP_FAST_CASE(19)
+        DUALIP_FAST_CASE(20)
 #undef DUALIP_FAST_CASE
         default:
           break;

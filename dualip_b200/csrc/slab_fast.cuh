@@ -10,7 +10,10 @@
 
 namespace dualip {
 
-constexpr int kRegDeg = 16;  // longest column handled by the register path
+constexpr int kRegDeg = 20;   // longest column handled by the register path
+constexpr int kKeepDeg = 16;  // up to here a and c stay in registers across the simplex scan; longer columns drop them
+                              // after u is formed and read them again (L1/L2 hit) for the scatter: the sorted copy,
+                              // u, the row offsets, a and c (5 D registers) would not fit 128 registers
 
 // ---- streaming loads: the slab arrays are read exactly once per launch, so they bypass L1 allocation ----
 __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
@@ -61,6 +64,7 @@ __device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
 // Sorting networks on register arrays (descending), generated and zero-one verified by tools/gen_sort_networks.py.
 template <int D>
 struct SortNet {
+  static_assert(D == 1, "sort_networks.inc must cover 2..kRegDeg (tools/gen_sort_networks.py)");
   static __device__ __forceinline__ void run(float (&)[D]) {}  // D = 1
 };
 #define DUALIP_CS(i, j)                     \
@@ -82,10 +86,39 @@ __device__ __forceinline__ float div_by_int(float t) {
   return __fmaf_rn(r, rn, q0);
 }
 
+// Compile-time loop with the index available as a template constant.
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+// A lane's column.  Row ids are kept as byte offsets (row * 4) into an m-float shared-memory array; columns longer than
+// kKeepDeg keep them packed instead, two uint16 per register as loaded, and unpack at each use (two instructions).
 template <int D>
 struct ColRegs {
+  static constexpr bool PACKED = D > kKeepDeg;
   float a[D], c[D];
-  uint32_t ro[D];  // row * 4: byte offset into an m-float shared-memory array
+  uint32_t rr[PACKED ? (D + 1) / 2 : D];
+  // W-th 32-bit word of the column's row ids (rows 2W and 2W+1)
+  template <int W>
+  __device__ __forceinline__ void set_word(uint32_t word) {
+    if constexpr (PACKED) {
+      rr[W] = word;
+    } else {
+      rr[2 * W] = (word << 2) & 0x3fffcu;
+      if constexpr (2 * W + 1 < D) rr[2 * W + 1] = (word >> 14) & 0x3fffcu;
+    }
+  }
+  template <int Q>
+  __device__ __forceinline__ uint32_t off() const {
+    if constexpr (PACKED)
+      return (Q & 1) ? ((rr[Q / 2] >> 14) & 0x3fffcu) : ((rr[Q / 2] << 2) & 0x3fffcu);
+    else
+      return rr[Q];
+  }
 };
 
 template <int D>
@@ -125,23 +158,46 @@ __device__ __forceinline__ void load_cols(ColRegs<D>& R, const float* __restrict
     R.c[4 * q + 1] = vc[q].y;
     R.c[4 * q + 2] = vc[q].z;
     R.c[4 * q + 3] = vc[q].w;
-    R.ro[4 * q + 0] = (vr[q].x << 2) & 0x3fffcu;
-    R.ro[4 * q + 1] = (vr[q].x >> 14) & 0x3fffcu;
-    R.ro[4 * q + 2] = (vr[q].y << 2) & 0x3fffcu;
-    R.ro[4 * q + 3] = (vr[q].y >> 14) & 0x3fffcu;
   }
-  if (D & 2) {
+  static_for<0, NF>([&](auto qc) {
+    constexpr int q = decltype(qc)::value;
+    R.template set_word<2 * q>(vr[q].x);
+    R.template set_word<2 * q + 1>(vr[q].y);
+  });
+  if constexpr ((D & 2) != 0) {
     R.a[4 * NF + 0] = ta.x;
     R.a[4 * NF + 1] = ta.y;
     R.c[4 * NF + 0] = tc.x;
     R.c[4 * NF + 1] = tc.y;
-    R.ro[4 * NF + 0] = (tr << 2) & 0x3fffcu;
-    R.ro[4 * NF + 1] = (tr >> 14) & 0x3fffcu;
+    R.template set_word<2 * NF>(tr);
   }
-  if (D & 1) {
+  if constexpr ((D & 1) != 0) {
     R.a[D - 1] = sa;
     R.c[D - 1] = sc;
-    R.ro[D - 1] = sr << 2;
+    R.template set_word<(D - 1) / 2>(sr);
+  }
+}
+
+// Second read of a and c (columns longer than kKeepDeg).  volatile: must not be merged with the first read, which
+// would keep the registers alive in between.
+template <int D>
+__device__ __forceinline__ void reload_ac(ColRegs<D>& R, const float* __restrict__ a_s, const float* __restrict__ c_s, int lane) {
+  constexpr int NF = D / 4;
+#pragma unroll
+  for (int q = 0; q < NF; ++q) {
+    float4 va, vc;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(va.x), "=f"(va.y), "=f"(va.z), "=f"(va.w) : "l"(a_s + q * 128 + lane * 4));
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(vc.x), "=f"(vc.y), "=f"(vc.z), "=f"(vc.w) : "l"(c_s + q * 128 + lane * 4));
+    R.a[4 * q + 0] = va.x, R.a[4 * q + 1] = va.y, R.a[4 * q + 2] = va.z, R.a[4 * q + 3] = va.w;
+    R.c[4 * q + 0] = vc.x, R.c[4 * q + 1] = vc.y, R.c[4 * q + 2] = vc.z, R.c[4 * q + 3] = vc.w;
+  }
+  if (D & 2) {
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(R.a[4 * NF]), "=f"(R.a[4 * NF + 1]) : "l"(a_s + NF * 128 + lane * 2));
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(R.c[4 * NF]), "=f"(R.c[4 * NF + 1]) : "l"(c_s + NF * 128 + lane * 2));
+  }
+  if (D & 1) {
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(R.a[D - 1]) : "l"(a_s + NF * 128 + (D & 2) * 32 + lane));
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(R.c[D - 1]) : "l"(c_s + NF * 128 + (D & 2) * 32 + lane));
   }
 }
 
@@ -181,31 +237,27 @@ template <int D>
 __device__ __forceinline__ void load_cols_staged(ColRegs<D>& R, uint32_t buf, int lane) {
   constexpr int NF = D / 4;
   const uint32_t a_s = buf + lane * 16, c_s = buf + 128 * D + lane * 16, r_s = buf + 256 * D + lane * 8;
-#pragma unroll
-  for (int q = 0; q < NF; ++q) {
+  static_for<0, NF>([&](auto qc) {
+    constexpr int q = decltype(qc)::value;
     const float4 va = lds_f4(a_s + q * 512);
     const float4 vc = lds_f4(c_s + q * 512);
     const uint2 vr = lds_u2(r_s + q * 256);
     R.a[4 * q + 0] = va.x, R.a[4 * q + 1] = va.y, R.a[4 * q + 2] = va.z, R.a[4 * q + 3] = va.w;
     R.c[4 * q + 0] = vc.x, R.c[4 * q + 1] = vc.y, R.c[4 * q + 2] = vc.z, R.c[4 * q + 3] = vc.w;
-    R.ro[4 * q + 0] = (vr.x << 2) & 0x3fffcu;
-    R.ro[4 * q + 1] = (vr.x >> 14) & 0x3fffcu;
-    R.ro[4 * q + 2] = (vr.y << 2) & 0x3fffcu;
-    R.ro[4 * q + 3] = (vr.y >> 14) & 0x3fffcu;
-  }
-  if (D & 2) {
+    R.template set_word<2 * q>(vr.x);
+    R.template set_word<2 * q + 1>(vr.y);
+  });
+  if constexpr ((D & 2) != 0) {
     const float2 ta = lds_f2(buf + NF * 512 + lane * 8);
     const float2 tc = lds_f2(buf + 128 * D + NF * 512 + lane * 8);
-    const uint32_t tr = lds_u1(buf + 256 * D + NF * 256 + lane * 4);
     R.a[4 * NF + 0] = ta.x, R.a[4 * NF + 1] = ta.y;
     R.c[4 * NF + 0] = tc.x, R.c[4 * NF + 1] = tc.y;
-    R.ro[4 * NF + 0] = (tr << 2) & 0x3fffcu;
-    R.ro[4 * NF + 1] = (tr >> 14) & 0x3fffcu;
+    R.template set_word<2 * NF>(lds_u1(buf + 256 * D + NF * 256 + lane * 4));
   }
-  if (D & 1) {
+  if constexpr ((D & 1) != 0) {
     R.a[D - 1] = lds_f1(buf + (NF * 128 + (D & 2) * 32 + lane) * 4);
     R.c[D - 1] = lds_f1(buf + 128 * D + (NF * 128 + (D & 2) * 32 + lane) * 4);
-    R.ro[D - 1] = lds_h1(buf + 256 * D + (NF * 128 + (D & 2) * 32 + lane) * 2) << 2;
+    R.template set_word<(D - 1) / 2>(lds_h1(buf + 256 * D + (NF * 128 + (D & 2) * 32 + lane) * 2));
   }
 }
 
@@ -229,8 +281,8 @@ __device__ __forceinline__ void stage_issue(unsigned char* buf, uint64_t* bar, c
 template <int D, int SMODE, int ACC>
 __device__ __forceinline__ void emit_cols(const KArgs& k, const ColRegs<D>& R, const float (&x)[D], uint32_t s_grad_u32,
                                           float& cxs, float& xxs) {
-#pragma unroll
-  for (int q = 0; q < D; ++q) {
+  static_for<0, D>([&](auto qc) {
+    constexpr int q = decltype(qc)::value;
     const float g = __fmul_rn(R.a[q], x[q]);  // matching.py:153 (A.values * x.values, then row sums)
     if (ACC == 1) {
       const int gi = __float2int_rn(g * k.fx_scale);
@@ -238,27 +290,28 @@ __device__ __forceinline__ void emit_cols(const KArgs& k, const ColRegs<D>& R, c
       if (gi != 0)
 #endif
       // unconditional: adding 0 is harmless, and ptxas would wrap a conditional ATOMS in a branch (4 instructions
-      // instead of 1); the extra shared-memory wavefronts fit the MIO budget (profiles/: ubench_smem2)
-      asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(s_grad_u32 + R.ro[q]), "r"(gi) : "memory");
+      // instead of 1); the extra shared-memory wavefronts fit the MIO budget (profiles/r1_ubench_smem2.txt)
+      asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(s_grad_u32 + R.template off<q>()), "r"(gi) : "memory");
     } else if (g != 0.f) {
       if (SMODE <= 1)
-        asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(s_grad_u32 + R.ro[q]), "f"(g) : "memory");
+        asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(s_grad_u32 + R.template off<q>()), "f"(g) : "memory");
       else
-        atomicAdd(k.acc + (R.ro[q] >> 2), g);
+        atomicAdd(k.acc + (R.template off<q>() >> 2), g);
     }
     cxs = fmaf(R.c[q], x[q], cxs);
     xxs = fmaf(x[q], x[q], xxs);
-  }
+  });
 }
 
 template <int D, int SMODE>
 __device__ __forceinline__ void make_v_cols(const KArgs& k, const ColRegs<D>& R, const unsigned char* s_lam_b, float s,
                                             float (&v)[D]) {
-#pragma unroll
-  for (int q = 0; q < D; ++q) {
-    const float lam_s = (SMODE == 0) ? lds_off(s_lam_b, R.ro[q]) : __fmul_rn(s, __ldg(k.lambda + (R.ro[q] >> 2)));
+  static_for<0, D>([&](auto qc) {
+    constexpr int q = decltype(qc)::value;
+    const uint32_t ro = R.template off<q>();
+    const float lam_s = (SMODE == 0) ? lds_off(s_lam_b, ro) : __fmul_rn(s, __ldg(k.lambda + (ro >> 2)));
     v[q] = make_v(R.a[q], lam_s, s, R.c[q]);
-  }
+  });
 }
 
 // box / cone / identity (box.py:16, cone.py:21-28): x = min(max(v, lo), hi).
@@ -286,7 +339,7 @@ __device__ __forceinline__ void scan_sorted(const float (&w)[D], float z, double
 // simplex / simplex_eq (simplex.py:143-236 per column at its true length).  On return x holds the projection;
 // branch: 0 feasible, 1 top-2 shortcut, 2 sorted scan ("Duchi"); rho: support size for branches 1 and 2.
 template <int D, int SMODE>
-__device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_class& pc, const ColRegs<D>& R, bool active,
+__device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_class& pc, ColRegs<D>& R, bool active,
                                              const unsigned char* s_lam_b, float s, float (&u)[D], int& branch, int& rho) {
   const unsigned FULL = 0xffffffffu;
   make_v_cols<D, SMODE>(k, R, s_lam_b, s, u);
@@ -373,6 +426,9 @@ __device__ __forceinline__ void fast_slab(const KArgs& k, const dualip_proj_clas
       }
       if (k.diag && branch >= 0) k.diag[os] = (uint8_t)(branch | (min(rho, 63) << 2));
     }
+  }
+  if constexpr (D > kKeepDeg) {
+    if (pc.kind != DUALIP_PROJ_CLAMP) reload_ac<D>(R, a_s, c_s, lane);
   }
   float cxs = 0.f, xxs = 0.f;
   emit_cols<D, SMODE, ACC>(k, R, x, s_grad_u32, cxs, xxs);
