@@ -340,6 +340,8 @@ def run_native(args):
             "final_dual_objective": result.dual_objective,
             "setup": {"generate_s": info["gen_s"], "plan_s": info["plan_s"], "plan": info["plan"]},
         }
+        if args.kernel_series:
+            line["roofline"]["kernel_ms_series"] = [round(t, 4) for t in kernel_times]
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:
@@ -433,6 +435,7 @@ def main():
     ap.add_argument("--cpu-sample-cols", type=int, default=4_000_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kernel-series", action="store_true", help="add the per-iteration kernel times (ms) to the JSON line")
     args = ap.parse_args()
     n, m, sp, mixed, jac = WORKLOADS[args.workload]
     args.entities = args.entities or n

@@ -124,6 +124,7 @@ struct dualip_plan {
   size_t owned_bytes = 0;
   int flush_bulk = 1;
   int prefetch = 0;
+  unsigned long long* timeline = nullptr;  // debug only
   int stage = 0;               // per-warp TMA staging buffers fit in shared memory
 };
 
@@ -270,6 +271,7 @@ struct KArgs {
   int flush_bulk;
   int do_epilogue;           // 1: calc (grad/scalars), 0: partial (packed sums)
   int stage;                 // 1: TMA-staged slabs (per-warp shared-memory buffer + mbarrier)
+  unsigned long long* timeline;  // debug (DUALIP_TIMELINE=1): per CTA 5 x {clock64, globaltimer}, or null
   int prefetch;              // L2 prefetch of each warp's next slab: 0 off, 1 bulk (TMA engine), 2 per-line
   const float* long_a;
   const float* long_c;
@@ -357,27 +359,66 @@ __device__ __forceinline__ void load_batch(const float* __restrict__ pa0, const 
   }
 }
 
-// m-length tail, executed by one whole CTA.  sum_at(i) = sum_j a_ij x_ij, cxv = c.x, xxv = ||x||^2.
+// m-length tail, executed by one whole CTA.  sum_load(i) = sum_j a_ij x_ij, cxv = c.x, xxv = ||x||^2.
 // Reference: calc_grad (matching.py:25-34) and matching.py:164-178 / :280-299.
-template <typename SumFn>
-__device__ __forceinline__ void cta_epilogue(SumFn sum_at, double cxv, double xxv, const float* lambda, const float* b, int m,
+// sum_load(i) returns the grid-wide sum of row i, sum_clear(i) zeroes its accumulator slot for the next launch.  The loop
+// is unrolled by four with all loads of a round issued before the first store or use: this runs on ONE CTA at the very
+// end of the launch, so its latency is exposed.
+template <typename SumFn, typename ClearFn>
+__device__ __forceinline__ void cta_epilogue(SumFn sum_load, ClearFn sum_clear, double cxv, double xxv, const float* lambda, const float* b, int m,
                                              double gamma, float* grad_out, dualip_scalars* out, double* dscratch,
                                              float* fscratch) {
   double lg = 0.0, sp = 0.0, g2 = 0.0;
   float mx = -INFINITY;
-  for (int i = threadIdx.x; i < m; i += blockDim.x) {
-    const float raw = sum_at(i);
-    const float g = b ? __fsub_rn(raw, b[i]) : raw;
-    grad_out[i] = g;
-    lg = fma((double)lambda[i], (double)g, lg);
-    sp += (double)fmaxf(g, 0.f);
-    g2 = fma((double)g, (double)g, g2);
-    mx = fmaxf(mx, g);
+  const int nt = blockDim.x;
+  for (int base = threadIdx.x; base < m; base += 4 * nt) {
+    float raw[4], bb[4], ll[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * nt;
+      raw[u] = 0.f, bb[u] = 0.f, ll[u] = 0.f;
+      if (i < m) {
+        raw[u] = sum_load(i);
+        bb[u] = b ? __ldg(b + i) : 0.f;
+        ll[u] = lambda[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * nt;
+      if (i < m) {
+        sum_clear(i);
+        const float g = b ? __fsub_rn(raw[u], bb[u]) : raw[u];
+        grad_out[i] = g;
+        lg = fma((double)ll[u], (double)g, lg);
+        sp += (double)fmaxf(g, 0.f);
+        g2 = fma((double)g, (double)g, g2);
+        mx = fmaxf(mx, g);
+      }
+    }
   }
-  lg = block_sum(lg, dscratch);
-  sp = block_sum(sp, dscratch);
-  g2 = block_sum(g2, dscratch);
-  mx = block_max(mx, fscratch);
+  // one combined block reduction (dscratch: 32 doubles, reused three times; fscratch: 32 floats)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  lg = warp_sum(lg);
+  sp = warp_sum(sp);
+  g2 = warp_sum(g2);
+  mx = warp_max(mx);
+  __shared__ double s_red[3][32];
+  __syncthreads();
+  if (lane == 0) {
+    s_red[0][warp] = lg;
+    s_red[1][warp] = sp;
+    s_red[2][warp] = g2;
+    fscratch[warp] = mx;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    lg = warp_sum(lane < nw ? s_red[0][lane] : 0.0);
+    sp = warp_sum(lane < nw ? s_red[1][lane] : 0.0);
+    g2 = warp_sum(lane < nw ? s_red[2][lane] : 0.0);
+    mx = warp_max(lane < nw ? fscratch[lane] : -INFINITY);
+  }
+  (void)dscratch;
   if (threadIdx.x == 0) {
     const double reg = 0.5 * gamma * xxv;
     dualip_scalars r;
@@ -416,6 +457,15 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   const unsigned FULL = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = THREADS / 32;
+  auto stamp = [&](int slot) {  // debug timeline
+    if (k.timeline != nullptr && tid == 0) {
+      unsigned long long g;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+      k.timeline[((size_t)blockIdx.x * 5 + slot) * 2] = (unsigned long long)clock64();
+      k.timeline[((size_t)blockIdx.x * 5 + slot) * 2 + 1] = g;
+    }
+  };
+  stamp(0);
   constexpr bool FAST = ROW16 && (SMODE == 0);  // register path (slab_fast.cuh)
   const uint32_t s_grad_u32 = pin_u32(smem_u32(s_grad));
 
@@ -451,6 +501,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   }
   __syncthreads();
 
+  stamp(1);
   // ---- stream slabs: warp w of the grid takes slabs w, w + W, w + 2W, ... (neighbouring warps read neighbouring
   //      slabs, and every warp sees the same mix of column lengths) ----
   double cx = 0.0, xx = 0.0;
@@ -482,6 +533,10 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     cur_staged = true;
   }
   for (; sl < k.n_slabs; sl += total_warps) {
+    if (k.timeline != nullptr && warp == 0 && lane == 0 && blockIdx.x < 2) {  // debug: per-slab trace
+      const int64_t it = (sl - ((int64_t)blockIdx.x * NW + warp)) / total_warps;
+      if (it < 4096) k.timeline[10 * 4096 + blockIdx.x * 4096 + it] = (unsigned long long)clock64();
+    }
     const uint2 hraw = hnext;
     hnext = hnext2;
     if (sl + 2 * total_warps < k.n_slabs) hnext2 = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl + 2 * total_warps);
@@ -878,6 +933,8 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   }
 
   // ---- flush per-CTA partial sums ----
+  __syncthreads();
+  stamp(2);
   cx = block_sum(cx, dscratch);
   xx = block_sum(xx, dscratch);
   if (tid == 0) {
@@ -939,6 +996,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       }
     }
   }
+  stamp(3);
   // ---- last CTA to finish runs the m-length tail and leaves the accumulators zeroed ----
   __threadfence();
   __syncthreads();
@@ -948,29 +1006,38 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   __threadfence();
   const double cxv = __ldcg(&k.acc_scal[0]);
   const double xxv = __ldcg(&k.acc_scal[1]);
-  auto sum_at = [&](int i) -> float {
+  auto sum_load = [&](int i) -> float {
     if (ACC == 1) {
       const long long v = (long long)__ldcg(k.acc_hi + i) * 65536LL + (long long)__ldcg(k.acc_lo + i);
       return (float)((double)v * k.fx_inv);
     }
     return __ldcg(k.acc + i);
   };
-  if (k.do_epilogue) {
-    cta_epilogue(sum_at, cxv, xxv, k.lambda, k.b, m, k.gamma, k.grad_out, k.scalars_out, dscratch, fscratch);
-  } else {
-    for (int i = tid; i < m; i += THREADS) k.partial_out[i] = sum_at(i);
-    if (tid == 0) {
-      k.partial_out[m] = (float)cxv;
-      k.partial_out[m + 1] = (float)xxv;
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < m; i += THREADS) {
+  auto sum_clear = [&](int i) {  // leaves the accumulators zeroed for the next launch
     if (ACC == 1) {
       k.acc_lo[i] = 0;
       k.acc_hi[i] = 0;
     } else {
       k.acc[i] = 0.f;
+    }
+  };
+  if (k.do_epilogue) {
+    cta_epilogue(sum_load, sum_clear, cxv, xxv, k.lambda, k.b, m, k.gamma, k.grad_out, k.scalars_out, dscratch, fscratch);
+  } else {
+    for (int base = tid; base < m; base += 4 * THREADS) {
+      float raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) raw[u] = (base + u * THREADS < m) ? sum_load(base + u * THREADS) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (base + u * THREADS < m) {
+          sum_clear(base + u * THREADS);
+          k.partial_out[base + u * THREADS] = raw[u];
+        }
+    }
+    if (tid == 0) {
+      k.partial_out[m] = (float)cxv;
+      k.partial_out[m + 1] = (float)xxv;
     }
   }
   if (tid == 0) {
@@ -978,6 +1045,8 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     k.acc_scal[1] = 0.0;
     *k.counter = 0u;
   }
+  __syncthreads();
+  stamp(4);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1108,8 +1177,9 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(const float* sum, int m,
                                                         double gamma, float* grad_out, dualip_scalars* out) {
   __shared__ double dscratch[32];
   __shared__ float fscratch[32];
-  cta_epilogue([&](int i) { return __ldcg(sum + i); }, (double)sum[m], (double)sum[m + 1], lambda, b, m, gamma, grad_out, out,
-               dscratch, fscratch);
+  const double cxv = (double)sum[m], xxv = (double)sum[m + 1];
+  cta_epilogue([&](int i) { return __ldcg(sum + i); }, [](int) {}, cxv, xxv, lambda, b, m, gamma, grad_out, out, dscratch,
+               fscratch);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1225,6 +1295,7 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.flush_bulk = p->flush_bulk;
   k.do_epilogue = do_epilogue;
   k.prefetch = p->prefetch;
+  k.timeline = p->timeline;
   k.stage = p->stage;
   k.long_a = p->long_a;
   k.long_c = p->long_c;
@@ -1556,6 +1627,7 @@ void dualip_plan_destroy(dualip_plan* p) {
   cudaFree(p->classes_dev);
   cudaFree(p->acc);
   cudaFree(p->acc_lo);
+  cudaFree(p->timeline);
   cudaFree(p->acc_hi);
   cudaFree(p->acc_scal);
   cudaFree(p->counter);
@@ -1617,6 +1689,10 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   memcpy(p->classes_host, d->classes, sizeof(dualip_proj_class) * d->n_classes);
   const char* fb = getenv("DUALIP_FLUSH");
   p->flush_bulk = (fb && strcmp(fb, "atomic") == 0) ? 0 : 1;
+  if (getenv("DUALIP_TIMELINE")) {
+    if (cudaMalloc(&p->timeline, sizeof(unsigned long long) * 12 * 4096) != cudaSuccess) p->timeline = nullptr;
+    if (p->timeline) cudaMemset(p->timeline, 0, sizeof(unsigned long long) * 12 * 4096);
+  }
   const char* pf = getenv("DUALIP_PREFETCH");
   p->prefetch = pf ? atoi(pf) : 0;
 
@@ -1721,6 +1797,15 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   DUALIP_TRY_FAIL(cudaDeviceSynchronize());
 #undef DUALIP_TRY_FAIL
   *out = p;
+  return DUALIP_OK;
+}
+
+/* Debug only (not declared in the public header): copies the per-CTA timeline of the last launch, 10 values per CTA. */
+int dualip_debug_timeline(dualip_plan* p, unsigned long long* out_host, int n_ctas) {
+  if (!p || !p->timeline || !out_host) return DUALIP_EINVAL;
+  DeviceGuard g(p->device);
+  DUALIP_CUDA_TRY(cudaDeviceSynchronize());
+  DUALIP_CUDA_TRY(cudaMemcpy(out_host, p->timeline, sizeof(unsigned long long) * (n_ctas < 0 ? 12 * 4096 : 10 * std::min(n_ctas, 4096)), cudaMemcpyDeviceToHost));
   return DUALIP_OK;
 }
 
