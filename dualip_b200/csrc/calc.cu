@@ -125,7 +125,7 @@ struct dualip_plan {
   int flush_bulk = 1;
   int prefetch = 0;
   unsigned long long* timeline = nullptr;  // debug only
-  int stage = 0;               // per-warp TMA staging buffers fit in shared memory
+  int stage = 0;               // longest column whose slab is TMA-staged (0: staging off / does not fit)
 };
 
 namespace dualip {
@@ -270,7 +270,7 @@ struct KArgs {
   float s;                   // fl32(-1/gamma)   (matching.py:136: `-1.0 / self.gamma * dual_val`)
   int flush_bulk;
   int do_epilogue;           // 1: calc (grad/scalars), 0: partial (packed sums)
-  int stage;                 // 1: TMA-staged slabs (per-warp shared-memory buffer + mbarrier)
+  int stage;                 // slabs of up to this many entries per column are TMA-staged (per-warp buffer + mbarrier); 0: off
   unsigned long long* timeline;  // debug (DUALIP_TIMELINE=1): per CTA 5 x {clock64, globaltimer}, or null
   int prefetch;              // L2 prefetch of each warp's next slab: 0 off, 1 bulk (TMA engine), 2 per-line
   const float* long_a;
@@ -517,25 +517,30 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   if (sl + total_warps < k.n_slabs) hnext2 = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl + total_warps);
   // TMA staging (register path): while a warp works on a slab, the engine copies its next slab into the warp's buffer
   const bool use_stage = FAST && (k.stage != 0);
-  unsigned char* my_stage = s_stage + (size_t)warp * kStageBytes;
+  unsigned char* my_stage = s_stage + (size_t)warp * (((size_t)k.stage * 320 + 127) & ~(size_t)127);
   uint64_t* my_bar = wbar + warp;
   uint32_t stage_phase = 0;
   bool cur_staged = false;
-  auto stage_slab = [&](const uint2 h) {  // h: header of a slab with d <= kRegDeg
+  auto stage_slab = [&](const uint2 h) {  // h: header of a slab with d <= k.stage
     if (lane == 0) {
       const size_t nb = (size_t)h.x * kSlabW;
       stage_issue(my_stage, my_bar, k.a_t + nb, k.c_t + nb, reinterpret_cast<const unsigned short*>(k.row_t) + nb,
                   (int)(h.y & 0xffffu));
     }
   };
-  if (use_stage && sl < k.n_slabs && (int)(hnext.y & 0xffffu) <= kRegDeg) {
+  if (use_stage && sl < k.n_slabs && (int)(hnext.y & 0xffffu) <= k.stage) {
     stage_slab(hnext);
     cur_staged = true;
   }
   for (; sl < k.n_slabs; sl += total_warps) {
-    if (k.timeline != nullptr && warp == 0 && lane == 0 && blockIdx.x < 2) {  // debug: per-slab trace
+    unsigned long long* trace = nullptr;
+    if (k.timeline != nullptr && warp == 0 && lane == 0 && blockIdx.x == 0) {  // debug: per-slab trace
       const int64_t it = (sl - ((int64_t)blockIdx.x * NW + warp)) / total_warps;
-      if (it < 4096) k.timeline[10 * 4096 + blockIdx.x * 4096 + it] = (unsigned long long)clock64();
+      if (it < 1024) {
+        k.timeline[10 * 4096 + it] = (unsigned long long)clock64();
+        k.timeline[11 * 4096 + it] = (unsigned long long)hnext.y;
+        trace = k.timeline + 10 * 4096 + 1024 + 4 * it;  // [arrived, projected, -, -]
+      }
     }
     const uint2 hraw = hnext;
     hnext = hnext2;
@@ -569,7 +574,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       }
     }
     const bool have_next = sl + total_warps < k.n_slabs;
-    const bool next_staged = use_stage && have_next && (int)(hnext.y & 0xffffu) <= kRegDeg;
+    const bool next_staged = use_stage && have_next && (int)(hnext.y & 0xffffu) <= k.stage;
     const bool staged = cur_staged;
     cur_staged = next_staged;
     auto issue_next = [&]() {
@@ -586,7 +591,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
 #define DUALIP_FAST_CASE(DD)                                                                              \
   case DD:                                                                                                \
     fast_slab<DD, SMODE, ACC>(k, pc, pa, pcv, pr16, lane, active, s_lam_b, s_grad_u32, s, sl, cx, xx,    \
-                              staged, my_stage, my_bar, stage_phase, issue_next);                        \
+                              staged, my_stage, my_bar, stage_phase, issue_next, trace);                 \
     break;
         DUALIP_FAST_CASE(1)
         DUALIP_FAST_CASE(2)
@@ -1716,16 +1721,20 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   const size_t fixed = smem_fixed_bytes(p->n_classes);
   const size_t m_pad = ((size_t)p->m + 3) & ~(size_t)3;
   const size_t stash_bytes = (size_t)(p->threads / 32) * kStashDeg * kSlabW * sizeof(float);
-  const size_t stage_bytes = (size_t)(p->threads / 32) * kStageBytes + 128;
+  // TMA staging of the register-path slabs pays off on large shards only: measured on B200 (profiles/r1_stage_sweep.txt),
+  // staged vs plain vector loads is 0.67 vs 0.70 of the roofline at 1e8 nonzeros, 0.78 vs 0.72 at 2e8, 0.90 vs 0.76 at 1e9.
+  const char* env_stage = getenv("DUALIP_STAGE");
+  int stage_deg = env_stage ? atoi(env_stage) : (p->nnz >= kStageMinNnz ? kRegDeg : 0);
+  stage_deg = std::max(0, std::min(stage_deg, kRegDeg));
+  const size_t stage_bytes = (size_t)(p->threads / 32) * (((size_t)stage_deg * 320 + 127) & ~(size_t)127) + 128;
   p->row_bits = (p->m <= 65536) ? 16 : 32;
   const size_t smem_max = std::min<size_t>(kSmemBudget, prop.sharedMemPerBlockOptin) - 1024;  // static smem + slack
-  const char* env_stage = getenv("DUALIP_STAGE");
-  const bool want_stage = !(env_stage && strcmp(env_stage, "0") == 0);
+  const bool want_stage = stage_deg > 0;
   const size_t need1 = fixed + 4 * m_pad + stash_bytes;
   // mode 0 (register path): lambda + accumulator, plus the per-warp TMA staging buffers when they fit
   if (p->row_bits == 16 && want_stage && fixed + 8 * m_pad + stage_bytes <= smem_max) {
     p->smode = 0;
-    p->stage = 1;
+    p->stage = stage_deg;
     p->smem_bytes = fixed + 8 * m_pad + stage_bytes;
   } else if (p->row_bits == 16 && fixed + 8 * m_pad + 128 <= smem_max) {
     p->smode = 0;
@@ -1737,6 +1746,9 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   } else {
     p->smode = 2;
     p->smem_bytes = fixed + stash_bytes;
+  }
+  if (const char* pad = getenv("DUALIP_SMEM_PAD")) {  // experiments: shrink L1 by requesting unused shared memory
+    p->smem_bytes = std::min(smem_max, p->smem_bytes + (size_t)atoi(pad));
   }
   const char* env_ctas = getenv("DUALIP_CTAS");
   if (env_ctas && atoi(env_ctas) > 0) p->n_ctas = atoi(env_ctas);

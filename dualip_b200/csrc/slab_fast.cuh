@@ -263,7 +263,7 @@ __device__ __forceinline__ void load_cols_staged(ColRegs<D>& R, uint32_t buf, in
 
 // Staging of a warp's NEXT slab: one lane arms the warp's mbarrier with the slab's byte count and issues three bulk
 // async copies (TMA engine, SASS UBLKCP) global -> shared; they land while the warp works on the current slab.
-constexpr int kStageBytes = kRegDeg * 32 * 10;  // per warp: a + c + uint16 rows of the longest register-path slab
+constexpr long long kStageMinNnz = 150000000LL;  // shards with fewer nonzeros use plain vector loads (see calc.cu)
 __device__ __forceinline__ void stage_issue(unsigned char* buf, uint64_t* bar, const float* a_s, const float* c_s,
                                             const unsigned short* r_s, int d) {
   fence_proxy_async_smem();  // the warp's reads of the buffer (generic proxy) precede the engine's writes
@@ -401,7 +401,7 @@ __device__ __forceinline__ void fast_slab(const KArgs& k, const dualip_proj_clas
                                           bool active, const unsigned char* s_lam_b, uint32_t s_grad_u32, float s,
                                           int64_t slab_index, double& cx, double& xx, bool staged,
                                           const unsigned char* stage_buf, uint64_t* stage_bar, uint32_t& stage_phase,
-                                          IssueNext issue_next) {
+                                          IssueNext issue_next, unsigned long long* trace) {
   ColRegs<D> R;
   if (staged) {
     mbar_wait(stage_bar, stage_phase);
@@ -413,10 +413,24 @@ __device__ __forceinline__ void fast_slab(const KArgs& k, const dualip_proj_clas
   issue_next();
   float x[D];
   int branch = -1, rho = 0;
+  if (trace) {  // debug: time at which the loaded data has arrived
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < D; ++q) t += R.a[q] + R.c[q];
+    if (t == 123.456f) trace[3] = 1;
+    trace[0] = (unsigned long long)clock64();
+  }
   if (pc.kind == DUALIP_PROJ_CLAMP)
     fast_clamp<D, SMODE>(k, pc, R, active, s_lam_b, s, x);
   else
     fast_simplex<D, SMODE>(k, pc, R, active, s_lam_b, s, x, branch, rho);
+  if (trace) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < D; ++q) t += x[q];
+    if (t == 123.456f) trace[3] = 1;
+    trace[1] = (unsigned long long)clock64();
+  }
   if ((k.x_out != nullptr) || (k.diag != nullptr)) {  // save_primal / diagnostics: straight from registers
     if (active) {
       const int64_t os = k.orig_start[slab_index * 32 + lane];

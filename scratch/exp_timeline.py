@@ -35,8 +35,17 @@ print("globaltimer ns rel. to first CTA start: start max %d | main-loop end min 
 
 big = (ctypes.c_uint64 * (12 * 4096))()
 assert fn(obj._plan, big, -1) == 0
-tr = np.frombuffer(big, dtype=np.uint64)[10 * 4096: 11 * 4096].astype(np.int64)
-tr = tr[tr > 0]
-d = np.diff(tr)
-print("warp0/cta0 slabs", tr.size, "cycles per slab: first 5", d[:5], " mean[5:20] %.0f mean[20:60] %.0f mean[60:100] %.0f mean[100:] %.0f" % (d[5:20].mean(), d[20:60].mean(), d[60:100].mean(), d[100:].mean()))
-print("per-slab cycles by decile:", [int(x.mean()) for x in np.array_split(d, 10)])
+arr = np.frombuffer(big, dtype=np.uint64).astype(np.int64)
+tr = arr[10 * 4096: 10 * 4096 + 1024]; hy = arr[11 * 4096: 11 * 4096 + 1024]
+ph = arr[10 * 4096 + 1024: 10 * 4096 + 1024 + 4096].reshape(1024, 4)
+nz = tr > 0
+tr, hy, ph = tr[nz], hy[nz], ph[nz]
+tot = np.diff(tr); dd = (hy & 0xffff)[:-1]; cls = ((hy >> 16) & 0xff)[:-1]
+wait = (ph[:, 0] - tr)[:-1]; proj = (ph[:, 1] - ph[:, 0])[:-1]; emit = tr[1:] - ph[:-1, 1]
+print("slab trace (warp 0 of CTA 0): d:total(wait/project/emit) x count")
+for c in np.unique(cls):
+    line = f"class {c}: "
+    for dv in np.unique(dd[cls == c]):
+        sel = (cls == c) & (dd == dv)
+        line += f"d{dv}:{int(tot[sel].mean())}({int(wait[sel].mean())}/{int(proj[sel].mean())}/{int(emit[sel].mean())})x{sel.sum()} "
+    print(line)

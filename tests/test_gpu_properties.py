@@ -102,3 +102,31 @@ def test_linearity_of_partial_sums_over_shards(big):
         o.launch_partial(lam.data_ptr(), 1e-3, pk.data_ptr())
         total += pk.double()
     assert torch.allclose(total, part.double(), rtol=1e-5, atol=1e-5 * float(part.abs().max()))
+
+
+def test_fixed_point_gradient_is_reproducible_and_agrees_with_fp32_atomics(big, monkeypatch):
+    """Bounded projection classes accumulate the dual gradient in 32-bit fixed point with native shared-memory integer
+    adds: the result does not depend on the order of the adds (bitwise reproducible) and agrees with the fp32-atomics
+    build of the same plan to fp32 accuracy.  Open cones have no overflow bound and keep fp32 atomics."""
+    from dualip_b200.objectives.matching import MatchingInputArgs, MatchingSolverDualObjectiveFunction
+    from dualip_b200.projections import create_projection_map
+
+    m = big["m"]
+    lam = torch.rand(m, device=DEV) * 60
+    fx = _objective(big)
+    info = fx.plan_info()
+    assert info["fixed_point"] == 1 and info["fixed_point_relerr_e12"] <= 240_000  # <= 2.4e-7 (4 fp32 ulps)
+    g1 = fx.calculate(lam).dual_gradient.clone()
+    for _ in range(3):
+        assert torch.equal(fx.calculate(lam).dual_gradient, g1)
+    monkeypatch.setenv("DUALIP_ACCUM", "f32")
+    f32 = _objective(big)
+    assert f32.plan_info()["fixed_point"] == 0
+    r32, rfx = f32.calculate(lam), fx.calculate(lam)
+    scale = float(rfx.dual_gradient.abs().max())
+    assert torch.allclose(r32.dual_gradient, rfx.dual_gradient, rtol=2e-6, atol=2e-6 * scale)
+    assert abs(float(r32.scalars64[0]) - float(rfx.scalars64[0])) <= 1e-6 * abs(float(rfx.scalars64[0]))
+    monkeypatch.delenv("DUALIP_ACCUM")
+    cone = MatchingSolverDualObjectiveFunction(
+        MatchingInputArgs(big["A"], big["C"], create_projection_map("cone", {"lower": 0.0}, big["n"]), big["b"]), gamma=1e-3)
+    assert cone.plan_info()["fixed_point"] == 0
