@@ -106,6 +106,16 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic_bytes(workload_id: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/r1_ncu_traffic.json), or None if there is none."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as fh:
+            return float(json.load(fh)[workload_id]["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def mixed_projection_map(n_local: int, col_start: int, device):
     """simplex(z=1) on even global entities, box[0,1] on odd ones (our choice of mixed map)."""
     import torch
@@ -332,11 +342,14 @@ def run_native(args):
             "gpu_launches": launches_per_step * K,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.ncu_traffic_bytes, "kernel": "matching_slab_kernel", "kernel_ms": kernel_ms,
+                         "traffic": args.ncu_traffic_bytes if args.ncu_traffic_bytes is not None
+                         else (ncu_traffic_bytes(args.workload) if world == 1 and args.entities == WORKLOADS[args.workload][0] else None),
+                         "kernel": "matching_slab_kernel", "kernel_ms": kernel_ms,
                          "kernel_ms_min": min(kernel_times), "kernel_ms_max": max(kernel_times),
                          "algorithmic_bytes": b_alg, "peak_source": peak_src,
                          "note": ("rank-0 shard; " if world > 1 else "") + "average over the K launches of the timed region "
-                                 "(the kernel's cost depends on the iterate: how many columns need the threshold search)"},
+                                 "(the kernel's cost depends on the iterate: how many simplex columns take the sorted scan); "
+                                 "traffic: ncu --set full capture of this workload (profiles/r1_ncu_c3_full_summary.txt)"},
             "final_dual_objective": result.dual_objective,
             "setup": {"generate_s": info["gen_s"], "plan_s": info["plan_s"], "plan": info["plan"]},
         }
