@@ -30,6 +30,14 @@ class CscDesc(C.Structure):
                 ("device", C.c_int32)]
 
 
+class LpDesc(C.Structure):
+    _fields_ = [("m", C.c_int32), ("n", C.c_int32), ("nnz", C.c_int64),
+                ("csr_rowptr_dev", C.c_void_p), ("csr_col_dev", C.c_void_p), ("csr_val_dev", C.c_void_p),
+                ("csc_colptr_dev", C.c_void_p), ("csc_row_dev", C.c_void_p), ("csc_val_dev", C.c_void_p),
+                ("c_dev", C.c_void_p), ("b_dev", C.c_void_p), ("lo_dev", C.c_void_p), ("hi_dev", C.c_void_p),
+                ("row_scale_dev", C.c_void_p), ("device", C.c_int32)]
+
+
 class Scalars(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("dual_objective", "primal_objective", "reg_penalty", "dual_val_times_grad",
                                           "max_pos_slack", "sum_pos_slack", "x_sq_norm", "grad_sq_norm")]
@@ -50,6 +58,8 @@ SIGNATURES = {
                                           C.c_uint32, C.c_void_p]),
     "dualip_matching_epilogue": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
                                            C.c_void_p, C.c_void_p]),
+    "dualip_lp_calc": (C.c_int, [C.POINTER(LpDesc), C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
     "dualip_matching_calc_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                             C.c_void_p]),
     "dualip_agd_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double,

@@ -1195,9 +1195,16 @@ template <typename RowT>
 __global__ void cta_row_bound_kernel(const float* __restrict__ a_t, const RowT* __restrict__ row_t,
                                      const SlabHdr* __restrict__ hdr, int64_t n_slabs, const float* __restrict__ cls_xmax,
                                      int m, float* __restrict__ table, unsigned int* __restrict__ row_cnt) {
+  extern __shared__ __align__(16) unsigned char bound_smem[];
+  float* s_bound = reinterpret_cast<float*>(bound_smem);              // m floats: this CTA's row bounds
+  unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_bound + m);  // m counters
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    s_bound[i] = 0.f;
+    s_cnt[i] = 0u;
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
   const int64_t total_warps = (int64_t)gridDim.x * NW;
-  float* my = table + (size_t)blockIdx.x * m;
   for (int64_t sl = (int64_t)blockIdx.x * NW + warp; sl < n_slabs; sl += total_warps) {
     const SlabHdr h = hdr[sl];
     if (lane >= (int)h.ncols) continue;
@@ -1206,9 +1213,15 @@ __global__ void cta_row_bound_kernel(const float* __restrict__ a_t, const RowT* 
     for (int k = 0; k < (int)h.d; ++k) {
       const size_t idx = base + slab_elem(k, (int)h.d, lane);
       const uint32_t r = (uint32_t)row_t[idx];
-      atomicAdd(&my[r], fabsf(a_t[idx]) * xmax);
-      atomicAdd(&row_cnt[r], 1u);
+      atomicAdd(&s_bound[r], fabsf(a_t[idx]) * xmax);
+      atomicAdd(&s_cnt[r], 1u);
     }
+  }
+  __syncthreads();
+  float* my = table + (size_t)blockIdx.x * m;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    my[i] = s_bound[i];
+    if (s_cnt[i]) atomicAdd(&row_cnt[i], s_cnt[i]);
   }
 }
 
@@ -1561,9 +1574,12 @@ static int choose_accumulator(dualip_plan* p, cudaStream_t stream) {
   CA_TRY(cudaMemsetAsync(table, 0, sizeof(float) * tab, stream));
   CA_TRY(cudaMemsetAsync(long_bound, 0, sizeof(float) * m, stream));
   CA_TRY(cudaMemsetAsync(row_cnt, 0, sizeof(unsigned int) * m, stream));
-  if (p->n_slabs > 0)
-    cta_row_bound_kernel<unsigned short><<<p->n_ctas, p->threads, 0, stream>>>(
+  if (p->n_slabs > 0) {
+    const size_t bsm = 8 * (size_t)m;  // fits: mode 0 already keeps 8*m bytes of lambda + accumulator in shared memory
+    CA_TRY(cudaFuncSetAttribute((const void*)cta_row_bound_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    cta_row_bound_kernel<unsigned short><<<p->n_ctas, p->threads, bsm, stream>>>(
         p->a_t, reinterpret_cast<const unsigned short*>(p->row_t), p->hdr, p->n_slabs, xmax_d, m, table, row_cnt);
+  }
   if (p->n_long > 0) {
     const int blocks = (int)std::min<int64_t>((p->n_long + 7) / 8, (int64_t)p->n_sms * 8);
     long_row_bound_kernel<<<blocks, 256, 0, stream>>>(p->longcols, p->n_long, p->long_a, p->long_row, xmax_d, long_bound, row_cnt);

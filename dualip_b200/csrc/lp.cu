@@ -6,6 +6,7 @@
 // The shipped MIPLIB instance is tiny (150 variables x 7822 rows), so this path is latency-bound; it exists so that the
 // second ObjectiveFunction of the reference runs on the device behind the same Maximizer.
 #include <math.h>
+#include <algorithm>
 
 #include "common.cuh"
 

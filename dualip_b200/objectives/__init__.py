@@ -5,5 +5,7 @@ from .matching import (
     MatchingSolverDualObjectiveFunctionDistributed,
 )
 
+from .miplib import MIPLIB2017ObjectiveFunction, MIPLIBInputArgs
+
 __all__ = ["BaseInputArgs", "BaseObjective", "MatchingInputArgs", "MatchingSolverDualObjectiveFunction",
-           "MatchingSolverDualObjectiveFunctionDistributed"]
+           "MatchingSolverDualObjectiveFunctionDistributed", "MIPLIBInputArgs", "MIPLIB2017ObjectiveFunction"]

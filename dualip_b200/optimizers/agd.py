@@ -122,8 +122,11 @@ class AcceleratedGradientDescent:
             return False
         if isinstance(f, MatchingSolverDualObjectiveFunctionDistributed):
             return f.device == initial_value.device
-        return (isinstance(f, MatchingSolverDualObjectiveFunction) and not f.is_distributed
-                and f.device == initial_value.device)
+        if isinstance(f, MatchingSolverDualObjectiveFunction):
+            return not f.is_distributed and f.device == initial_value.device
+        from dualip_b200.objectives.miplib import MIPLIB2017ObjectiveFunction
+
+        return isinstance(f, MIPLIB2017ObjectiveFunction) and f.device == initial_value.device
 
     # -- fused device-resident loop ------------------------------------------------------------------------
     def _maximize_fused(self, f, initial_value: torch.Tensor, rank: int) -> SolverResult:
@@ -254,7 +257,7 @@ class FusedAscentLoop:
                 f.launch_epilogue(self.partial.data_ptr(), self.x_ptr, gamma_i, self.grad.data_ptr(), self.scal.data_ptr())
             else:
                 if last_primal:
-                    self.primal = torch.empty(f.nnz, dtype=torch.float32, device=self.device)
+                    self.primal = torch.empty(getattr(f, "primal_size", f.nnz), dtype=torch.float32, device=self.device)
                 f.launch_calc(self.x_ptr, gamma_i, self.grad.data_ptr(), self.scal.data_ptr(),
                               self.primal.data_ptr() if last_primal else None)
                 if ev is not None:

@@ -61,7 +61,9 @@ def build_objective(input_args: BaseInputArgs, solver_args: SolverArgs, compute_
             local_matching_input_args=local_args, b_vec=input_args.b_vec, gamma=solver_args.gamma,
             host_device=compute_args.host_device, **kwargs)
     if objective_type == "miplib2017":
-        raise NotImplementedError("the generic-LP (miplib2017) objective is outside this round's hot path (DESIGN.md)")
+        from dualip_b200.objectives.miplib import MIPLIB2017ObjectiveFunction
+
+        return MIPLIB2017ObjectiveFunction(miplib_input_args=input_args, **kwargs)
     raise ValueError(f"Objective type {objective_type} not supported")
 
 
@@ -93,4 +95,8 @@ def run_solver(input_args: BaseInputArgs, solver_args: SolverArgs, compute_args:
     else:
         initial_dual = torch.zeros_like(input_args.b_vec, device="cpu")
     initial_dual = initial_dual.to(device=device, dtype=torch.float32)
-    return solver.maximize(objective, initial_dual, rank=rank)
+    result = solver.maximize(objective, initial_dual, rank=rank)
+    if getattr(objective, "use_jacobi_precondition", False) and hasattr(objective, "invert_jacobi_precondition"):
+        # the reference calls a method it never defines here (run_solver.py:136-144)
+        result.dual_val = objective.invert_jacobi_precondition(result.dual_val)
+    return result

@@ -133,6 +133,36 @@ int dualip_matching_epilogue(const float* partial_sum_dev, int32_t m, const floa
 int dualip_matching_calc_host(dualip_plan* plan, const float* lambda_host, const float* b_dev, double gamma,
                               float* grad_out_host, dualip_scalars* scalars_out_host, void* stream);
 
+/* ---- generic (non-block) LP objective: reference src/dualip/objectives/miplib.py:60-109 ----
+ * A is given twice (CSR for A x, CSC for A^T lambda), int32 indices; all arrays are BORROWED device pointers that must
+ * stay alive while the description is in use.  lo/hi: per-variable bounds, -INFINITY / +INFINITY for open sides (the
+ * box / cone entries of the reference's projection_map, miplib.py:80-90).  row_scale: 1/||A_r||_2 per row when the
+ * objective was built with use_jacobi_precondition (miplib.py:48-58,73-74,92-95), else NULL. */
+typedef struct dualip_lp_desc {
+  int32_t m;                      /* constraints (rows of A, length of lambda)            */
+  int32_t n;                      /* variables                                             */
+  int64_t nnz;
+  const int32_t* csr_rowptr_dev;  /* m+1 */
+  const int32_t* csr_col_dev;     /* nnz */
+  const float* csr_val_dev;       /* nnz */
+  const int32_t* csc_colptr_dev;  /* n+1 */
+  const int32_t* csc_row_dev;     /* nnz */
+  const float* csc_val_dev;       /* nnz */
+  const float* c_dev;             /* n   */
+  const float* b_dev;             /* m   */
+  const float* lo_dev;            /* n   */
+  const float* hi_dev;            /* n   */
+  const float* row_scale_dev;     /* m or NULL */
+  int32_t device;
+} dualip_lp_desc;
+
+/* One evaluation of the dual of the generic LP at lambda: x_out = clamp(-(A^T lambda' + c)/gamma, lo, hi),
+ * grad_out = row_scale * (A x - b), scalars as for the matching objective (dual_val_times_grad = lambda'.(Ax-b) with
+ * lambda' = row_scale * lambda).  scratch_dev: 8 doubles, zero on first use (the call leaves them zeroed).
+ * Replaces MIPLIB2017ObjectiveFunction.calculate.  Asynchronous on `stream`, CUDA-graph capturable. */
+int dualip_lp_calc(const dualip_lp_desc* desc, const float* lambda_dev, double gamma, float* x_out_dev,
+                   float* grad_out_dev, dualip_scalars* scalars_out_dev, double* scratch_dev, void* stream);
+
 /* ---- device-resident Maximizer state (reference optimizers/agd.py:121-229, agd_utils.py:4-89) ---- */
 typedef struct dualip_agd dualip_agd;
 

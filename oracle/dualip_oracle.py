@@ -342,3 +342,26 @@ def jacobi_precondition(a: np.ndarray, row: np.ndarray, b: np.ndarray, n_rows: i
     norms = np.sqrt(sq.astype(dt))
     rec = dt.type(1) / norms
     return a * rec[row], b * rec, norms
+
+
+# --------------------------------------------------------------------------------------
+# generic (non-block) LP objective: objectives/miplib.py:60-109
+# --------------------------------------------------------------------------------------
+def lp_calculate(A: np.ndarray, c: np.ndarray, b: np.ndarray, lower: np.ndarray, upper: np.ndarray, lam: np.ndarray,
+                 gamma: float, row_norms: Optional[np.ndarray] = None, dtype=np.float32):
+    """Dense restatement of MIPLIB2017ObjectiveFunction.calculate.  lower/upper: per-variable clamp bounds (-inf/+inf =
+    open), i.e. the box / cone entries of the projection map applied element-wise (miplib.py:80-90).
+
+    Returns (grad, dual_obj, reg, x, primal_obj)."""
+    A = np.asarray(A, dtype=dtype)
+    c, b, lam = np.asarray(c, dtype=dtype), np.asarray(b, dtype=dtype), np.asarray(lam, dtype=dtype)
+    if row_norms is not None:
+        lam = (dtype(1.0) / np.asarray(row_norms, dtype=dtype)) * lam                      # :73-74
+    z = dtype(-1.0 / gamma) * (A.T @ lam + c)                                              # :76
+    x = np.minimum(np.maximum(z, np.asarray(lower, dtype=dtype)), np.asarray(upper, dtype=dtype))
+    resid = A @ x - b
+    grad = resid if row_norms is None else (dtype(1.0) / np.asarray(row_norms, dtype=dtype)) * resid   # :92-95
+    reg = dtype(gamma / 2.0) * dtype(np.linalg.norm(x.astype(np.float64))) ** 2            # :97
+    primal = float(c.astype(np.float64) @ x.astype(np.float64))
+    dual_obj = primal + float(reg) + float(lam.astype(np.float64) @ resid.astype(np.float64))   # :99
+    return grad, dual_obj, float(reg), x, primal

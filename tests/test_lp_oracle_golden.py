@@ -1,0 +1,56 @@
+"""not gpu: the numpy restatement of the generic-LP objective (oracle/dualip_oracle.py: lp_calculate) against outputs of
+the reference's MIPLIB2017ObjectiveFunction (tests/golden/lp_*.npz, written by tests/golden/make_golden_lp.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dualip_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["lp_miplib", "lp_eq_cone"])
+def test_lp_oracle_matches_reference_outputs(name):
+    d = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    A, c, b = d["A"], d["c"], d["b"]
+    gamma, jacobi = float(d["gamma"]), bool(d["jacobi"])
+    row_norms = None
+    if jacobi:
+        row_norms = np.linalg.norm(A.astype(np.float32), axis=1).astype(np.float32)
+        row_norms[row_norms == 0] = 1.0
+    for k, lam in enumerate(d["lams"]):
+        grad, obj, reg, x, primal = O.lp_calculate(A, c, b, d["lower"], d["upper"], lam, gamma, row_norms)
+        assert np.allclose(x, d[f"x{k}"], rtol=1e-5, atol=1e-5)
+        assert np.array_equal(x == d["lower"], d[f"x{k}"] == d["lower"]) and np.array_equal(x == d["upper"], d[f"x{k}"] == d["upper"])
+        scale = max(1.0, float(np.abs(d[f"grad{k}"]).max()))
+        assert np.allclose(grad, d[f"grad{k}"], rtol=1e-5, atol=1e-5 * scale)
+        ref_obj, ref_reg, ref_primal = d[f"scal{k}"]
+        assert abs(obj - ref_obj) <= 1e-5 * max(1.0, abs(ref_obj))
+        assert abs(reg - ref_reg) <= 1e-5 * max(1.0, abs(ref_reg)) and abs(primal - ref_primal) <= 1e-5 * max(1.0, abs(ref_primal))
+
+
+@pytest.mark.parametrize("name", ["lp_miplib", "lp_eq_cone"])
+def test_lp_oracle_ascent_trace_matches_reference_run(name):
+    d = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    A, c, b = d["A"], d["c"], d["b"]
+    jacobi = bool(d["jacobi"])
+    row_norms = None
+    if jacobi:
+        row_norms = np.linalg.norm(A.astype(np.float32), axis=1).astype(np.float32)
+        row_norms[row_norms == 0] = 1.0
+    eq = d["eq_mask"] if d["eq_mask"].size else None
+    steps, factor = int(d["decay"][0]), float(d["decay"][1])
+
+    def calc(lam, gamma):
+        grad, obj, *_ = O.lp_calculate(A, c, b, d["lower"], d["upper"], lam, gamma, row_norms)
+        return grad, obj
+
+    y, obj_log, step_log, _ = O.agd_maximize(calc, np.zeros(b.size, dtype=np.float32), int(d["iters"]), float(d["gamma"]), 1e-3, 0.1,
+                                             gamma_decay_type="step" if steps else None,
+                                             gamma_decay_params={"decay_steps": steps, "decay_factor": factor}, equality_mask=eq)
+    ref, got = d["obj_log"], np.array(obj_log)
+    # the ascent on these LPs amplifies rounding differences (clamp pattern switches, Lipschitz step from differences of
+    # gradients): the first iterations agree to fp32 accuracy, the full trace to a few per cent of its range
+    assert np.allclose(got[:12], ref[:12], rtol=1e-4, atol=1e-4 * np.abs(ref[:12]).max())
+    assert np.abs(got - ref).max() <= 5e-2 * np.abs(ref).max()
