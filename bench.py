@@ -217,7 +217,7 @@ def run_native(args):
     import torch
     import torch.distributed as dist
 
-    from dualip_b200.optimizers.agd import AcceleratedGradientDescent, FusedAscentLoop
+    from dualip_b200.optimizers.agd import AcceleratedGradientDescent, FusedAscentLoop, no_iteration_callback
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -252,7 +252,7 @@ def run_native(args):
 
     # ---- device-resident loop: W warm-up + K timed iterations ----
     solver = AcceleratedGradientDescent(max_iter=W + K, gamma=GAMMA, initial_step_size=INITIAL_STEP, max_step_size=MAX_STEP,
-                                        iteration_callback=lambda i, r: None)
+                                        iteration_callback=no_iteration_callback)
     loop = FusedAscentLoop(solver, obj, torch.zeros(m, dtype=torch.float32, device=device), rank)
     for i in range(1, W + 1):
         loop.step(i)
@@ -276,7 +276,7 @@ def run_native(args):
     result = loop.finish()
     lam_now = loop.current_dual()
     loop.close()
-    launches_per_step = info["plan"]["launches_per_calc"] + 1 + (1 if world > 1 else 0)
+    launches_per_step = info["plan"]["launches_per_calc"] + 1  # objective kernel(s) + update (the all-reduce is NCCL's)
 
     # ---- dominant kernel, for the roofline: CUDA events around every launch of the timed region ----
     torch.cuda.synchronize(device)

@@ -70,6 +70,8 @@ SIGNATURES = {
     "dualip_agd_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dualip_agd_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_double, C.c_int32,
                                   C.c_void_p]),
+    "dualip_agd_step_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_float,
+                                          C.c_int32, C.c_double, C.c_int32, C.c_void_p]),
     "dualip_agd_read_log": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dualip_agd_reserve_log": (C.c_int, [C.c_void_p, C.c_int32]),
     "dualip_row_sq_norms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,

@@ -30,36 +30,122 @@ struct dualip_agd {
 
 namespace dualip {
 
+// One CTA.  FROM_PARTIAL: `grad` points at the all-reduced packed sums [sum_j a_rj x_rj (m) | c.x | ||x||^2] of the sharded
+// path; the kernel then also does the m-length tail of the objective (grad = sum - b, lambda.grad, slacks, dual objective:
+// matching.py:280-299), writes grad_out / scal_out, and saves the separate epilogue launch.  Both loops are unrolled by
+// four with every load of a round issued before the first use: a single CTA has no other warps to hide L2 latency.
+template <bool FROM_PARTIAL>
 __global__ void __launch_bounds__(1024) agd_step_kernel(float* __restrict__ x, float* __restrict__ y, float* __restrict__ gh,
                                                         float* __restrict__ yh, float* __restrict__ ratios,
                                                         long long* __restrict__ pushes, double* __restrict__ dstate,
                                                         const uint8_t* __restrict__ eqmask, const float* __restrict__ grad,
                                                         const dualip_scalars* __restrict__ scal, int m, int H, float beta,
                                                         int decay_now, double decay_factor, double* log_obj,
-                                                        double* log_step, int iter_index) {
-  __shared__ double dscratch[32];
+                                                        double* log_step, int iter_index, const float* __restrict__ b,
+                                                        double gamma, float* __restrict__ grad_out,
+                                                        dualip_scalars* __restrict__ scal_out) {
+  __shared__ double s_red[5][32];
+  __shared__ float s_mx[32];
   __shared__ double s_step;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
   const long long t = *pushes;  // index of the entry pushed now
   const int slot = (int)(t % H);
   const int prev = (int)((t + H - 1) % H);
-  // 1) push (grad, y) and measure the newest pair                      agd_utils.py:11-27, :30-41
-  double dg2 = 0.0, dy2 = 0.0;
-  for (int i = tid; i < m; i += blockDim.x) {
-    const float g = grad[i], yy = y[i];
-    gh[(size_t)slot * m + i] = g;
-    yh[(size_t)slot * m + i] = yy;
-    if (t > 0) {
-      const float dg = __fsub_rn(gh[(size_t)prev * m + i], g);
-      const float dy = __fsub_rn(yh[(size_t)prev * m + i], yy);
-      dg2 = fma((double)dg, (double)dg, dg2);
-      dy2 = fma((double)dy, (double)dy, dy2);
+  const bool have_prev = t > 0;
+  // 1) gradient (sharded path: the objective's tail), push (grad, y), measure the newest pair
+  //    agd_utils.py:11-27, :30-41 ; matching.py:280-299
+  double dg2 = 0.0, dy2 = 0.0, lg = 0.0, sp = 0.0, g2 = 0.0;
+  float mx = -INFINITY;
+  for (int base = tid; base < m; base += 4 * nt) {
+    float g4[4], y4[4], gp4[4], yp4[4], b4[4], x4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * nt;
+      g4[u] = y4[u] = gp4[u] = yp4[u] = b4[u] = x4[u] = 0.f;
+      if (i < m) {
+        g4[u] = grad[i];
+        y4[u] = y[i];
+        if (have_prev) {
+          gp4[u] = gh[(size_t)prev * m + i];
+          yp4[u] = yh[(size_t)prev * m + i];
+        }
+        if (FROM_PARTIAL) {
+          b4[u] = b ? b[i] : 0.f;
+          x4[u] = x[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * nt;
+      if (i < m) {
+        float g = g4[u];
+        if (FROM_PARTIAL) {
+          g = b ? __fsub_rn(g, b4[u]) : g;
+          grad_out[i] = g;
+          lg = fma((double)x4[u], (double)g, lg);
+          sp += (double)fmaxf(g, 0.f);
+          g2 = fma((double)g, (double)g, g2);
+          mx = fmaxf(mx, g);
+        }
+        gh[(size_t)slot * m + i] = g;
+        yh[(size_t)slot * m + i] = y4[u];
+        if (have_prev) {
+          const float dg = __fsub_rn(gp4[u], g);
+          const float dy = __fsub_rn(yp4[u], y4[u]);
+          dg2 = fma((double)dg, (double)dg, dg2);
+          dy2 = fma((double)dy, (double)dy, dy2);
+        }
+      }
     }
   }
-  dg2 = block_sum(dg2, dscratch);
-  dy2 = block_sum(dy2, dscratch);
+  dg2 = warp_sum(dg2);
+  dy2 = warp_sum(dy2);
+  if (FROM_PARTIAL) {
+    lg = warp_sum(lg);
+    sp = warp_sum(sp);
+    g2 = warp_sum(g2);
+    mx = warp_max(mx);
+  }
+  if (lane == 0) {
+    s_red[0][warp] = dg2;
+    s_red[1][warp] = dy2;
+    if (FROM_PARTIAL) {
+      s_red[2][warp] = lg;
+      s_red[3][warp] = sp;
+      s_red[4][warp] = g2;
+      s_mx[warp] = mx;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    dg2 = warp_sum(lane < nw ? s_red[0][lane] : 0.0);
+    dy2 = warp_sum(lane < nw ? s_red[1][lane] : 0.0);
+    if (FROM_PARTIAL) {
+      lg = warp_sum(lane < nw ? s_red[2][lane] : 0.0);
+      sp = warp_sum(lane < nw ? s_red[3][lane] : 0.0);
+      g2 = warp_sum(lane < nw ? s_red[4][lane] : 0.0);
+      mx = warp_max(lane < nw ? s_mx[lane] : -INFINITY);
+    }
+  }
   if (tid == 0) {
-    if (t > 0) ratios[(t - 1) % (H - 1)] = __fdiv_rn((float)sqrt(dg2), (float)sqrt(dy2));
+    double dual_obj = scal ? scal->dual_objective : 0.0;
+    if (FROM_PARTIAL) {
+      const double cxv = (double)grad[m], xxv = (double)grad[m + 1];
+      dualip_scalars r;
+      r.primal_objective = cxv;
+      r.reg_penalty = 0.5 * gamma * xxv;
+      r.dual_val_times_grad = lg;
+      r.dual_objective = cxv + r.reg_penalty + lg;
+      r.max_pos_slack = (double)fmaxf(mx, 0.f);
+      r.sum_pos_slack = sp;
+      r.x_sq_norm = xxv;
+      r.grad_sq_norm = g2;
+      *scal_out = r;
+      dual_obj = r.dual_objective;
+    }
+    if (have_prev) ratios[(t - 1) % (H - 1)] = __fdiv_rn((float)sqrt(dg2), (float)sqrt(dy2));
     // 2) step size                                                      agd_utils.py:44-62
     const long long n_pairs = t < (long long)(H - 1) ? t : (long long)(H - 1);
     const double max_step = dstate[0], init_step = dstate[1];
@@ -78,7 +164,7 @@ __global__ void __launch_bounds__(1024) agd_step_kernel(float* __restrict__ x, f
       }
     }
     s_step = step;
-    if (log_obj) log_obj[iter_index] = scal ? scal->dual_objective : 0.0;
+    if (log_obj) log_obj[iter_index] = dual_obj;
     if (log_step) log_step[iter_index] = step;
     if (decay_now) dstate[0] = step * decay_factor;  // agd.py:107
     *pushes = t + 1;
@@ -87,12 +173,32 @@ __global__ void __launch_bounds__(1024) agd_step_kernel(float* __restrict__ x, f
   // 3) ascent step, projection on the dual cone, momentum              agd.py:181-185, :13-21
   const float step32 = (float)s_step;
   const float omb = __fsub_rn(1.0f, beta);
-  for (int i = tid; i < m; i += blockDim.x) {
-    const float xi = x[i], yi = y[i];
-    float yn = __fadd_rn(xi, __fmul_rn(grad[i], step32));
-    if (!(eqmask && eqmask[i])) yn = fmaxf(yn, 0.f);
-    x[i] = __fadd_rn(__fmul_rn(yn, omb), __fmul_rn(yi, beta));
-    y[i] = yn;
+  const float* gsrc = FROM_PARTIAL ? grad_out : grad;
+  for (int base = tid; base < m; base += 4 * nt) {
+    float g4[4], y4[4], x4[4];
+    uint8_t e4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * nt;
+      g4[u] = y4[u] = x4[u] = 0.f;
+      e4[u] = 0;
+      if (i < m) {
+        g4[u] = gsrc[i];
+        y4[u] = y[i];
+        x4[u] = x[i];
+        e4[u] = eqmask ? eqmask[i] : (uint8_t)0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * nt;
+      if (i < m) {
+        float yn = __fadd_rn(x4[u], __fmul_rn(g4[u], step32));
+        if (!e4[u]) yn = fmaxf(yn, 0.f);
+        x[i] = __fadd_rn(__fmul_rn(yn, omb), __fmul_rn(y4[u], beta));
+        y[i] = yn;
+      }
+    }
   }
 }
 
@@ -215,10 +321,25 @@ int dualip_agd_step(dualip_agd* a, const float* grad_dev, const dualip_scalars* 
     return DUALIP_EINVAL;
   }
   const bool log = iter_index >= 0 && iter_index < a->log_cap;
-  agd_step_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a->x, a->y, a->gh, a->yh, a->ratios, a->pushes, a->dstate, a->eqmask,
-                                                        grad_dev, scalars_dev, a->m, a->H, beta, decay_now, decay_factor,
-                                                        log ? a->log_obj : nullptr, log ? a->log_step : nullptr,
-                                                        log ? iter_index : 0);
+  agd_step_kernel<false><<<1, 1024, 0, (cudaStream_t)stream>>>(
+      a->x, a->y, a->gh, a->yh, a->ratios, a->pushes, a->dstate, a->eqmask, grad_dev, scalars_dev, a->m, a->H, beta, decay_now,
+      decay_factor, log ? a->log_obj : nullptr, log ? a->log_step : nullptr, log ? iter_index : 0, nullptr, 0.0, nullptr, nullptr);
+  DUALIP_CUDA_TRY(cudaGetLastError());
+  return DUALIP_OK;
+}
+
+int dualip_agd_step_sharded(dualip_agd* a, const float* partial_sum_dev, const float* b_dev, double gamma, float* grad_out_dev,
+                            dualip_scalars* scalars_out_dev, float beta, int32_t decay_now, double decay_factor,
+                            int32_t iter_index, void* stream) {
+  if (!a || !partial_sum_dev || !grad_out_dev || !scalars_out_dev) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  const bool log = iter_index >= 0 && iter_index < a->log_cap;
+  agd_step_kernel<true><<<1, 1024, 0, (cudaStream_t)stream>>>(
+      a->x, a->y, a->gh, a->yh, a->ratios, a->pushes, a->dstate, a->eqmask, partial_sum_dev, nullptr, a->m, a->H, beta, decay_now,
+      decay_factor, log ? a->log_obj : nullptr, log ? a->log_step : nullptr, log ? iter_index : 0, b_dev, gamma, grad_out_dev,
+      scalars_out_dev);
   DUALIP_CUDA_TRY(cudaGetLastError());
   return DUALIP_OK;
 }

@@ -53,6 +53,11 @@ def format_objective_result_summary(iteration: int, objective_result: ObjectiveR
     return " | ".join(p for p in parts if p is not None)
 
 
+def no_iteration_callback(iteration: int, objective_result: ObjectiveResult) -> None:
+    """Pass as `iteration_callback` to run without per-iteration reporting: the fused loop then never materialises an
+    ObjectiveResult per iteration (and, sharded, takes the objective's tail and the update in one launch)."""
+
+
 class AcceleratedGradientDescent:
     def __init__(
         self,
@@ -96,7 +101,7 @@ class AcceleratedGradientDescent:
             self.max_step_size = step_size * factor
 
     def _user_callback_active(self) -> bool:
-        return True
+        return self.iteration_callback is not no_iteration_callback
 
     def _default_iteration_callback(self, iteration: int, objective_result: ObjectiveResult) -> None:
         try:
@@ -246,6 +251,10 @@ class FusedAscentLoop:
             if self.kernel_events is not None and 0 <= i - self.kernel_events_base < len(self.kernel_events):
                 ev = self.kernel_events[i - self.kernel_events_base]
                 ev[0].record()
+            decay_now, factor = 0, 1.0
+            if self.decay and i % solver.gamma_decay_params["decay_steps"] == 0:
+                decay_now, factor = 1, float(solver.gamma_decay_params["decay_factor"])
+            callback = self.rank == 0 and solver._user_callback_active()
             if self.sharded:
                 from dualip_b200.objectives.matching import reduce_partials
 
@@ -254,7 +263,19 @@ class FusedAscentLoop:
                 if ev is not None:
                     ev[1].record()
                 reduce_partials(self.partial)
-                f.launch_epilogue(self.partial.data_ptr(), self.x_ptr, gamma_i, self.grad.data_ptr(), self.scal.data_ptr())
+                if callback:
+                    # the callback wants the result before the update: separate epilogue launch, then the plain step
+                    f.launch_epilogue(self.partial.data_ptr(), self.x_ptr, gamma_i, self.grad.data_ptr(), self.scal.data_ptr())
+                    solver.iteration_callback(i, solver._view_result(self.grad, self.scal, None))
+                    _native.check(self.lib.dualip_agd_step(self.handle, self.grad.data_ptr(), self.scal.data_ptr(),
+                                                           float(self.beta[i - 1]), decay_now, factor, i - 1, stream),
+                                  "dualip_agd_step")
+                else:
+                    # objective tail (grad = sum - b, scalars) and optimizer update in ONE launch
+                    _native.check(self.lib.dualip_agd_step_sharded(
+                        self.handle, self.partial.data_ptr(), f.b_vec.data_ptr(), float(gamma_i), self.grad.data_ptr(),
+                        self.scal.data_ptr(), float(self.beta[i - 1]), decay_now, factor, i - 1, stream),
+                        "dualip_agd_step_sharded")
             else:
                 if last_primal:
                     self.primal = torch.empty(getattr(f, "primal_size", f.nnz), dtype=torch.float32, device=self.device)
@@ -262,15 +283,13 @@ class FusedAscentLoop:
                               self.primal.data_ptr() if last_primal else None)
                 if ev is not None:
                     ev[1].record()
-            if self.rank == 0 and solver._user_callback_active():
-                solver.iteration_callback(i, solver._view_result(self.grad, self.scal, self.primal if last_primal else None))
-            decay_now, factor = 0, 1.0
-            if self.decay and i % solver.gamma_decay_params["decay_steps"] == 0:
-                decay_now, factor = 1, float(solver.gamma_decay_params["decay_factor"])
+                if callback:
+                    solver.iteration_callback(i, solver._view_result(self.grad, self.scal, self.primal if last_primal else None))
+                _native.check(self.lib.dualip_agd_step(self.handle, self.grad.data_ptr(), self.scal.data_ptr(),
+                                                       float(self.beta[i - 1]), decay_now, factor, i - 1, stream),
+                              "dualip_agd_step")
+            if decay_now:
                 solver.gamma = solver.gamma * factor
-            _native.check(self.lib.dualip_agd_step(self.handle, self.grad.data_ptr(), self.scal.data_ptr(),
-                                                   float(self.beta[i - 1]), decay_now, factor, i - 1, stream),
-                          "dualip_agd_step")
         self.steps_done = max(self.steps_done, i)
 
     def current_dual(self) -> torch.Tensor:

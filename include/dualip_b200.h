@@ -183,6 +183,12 @@ int dualip_agd_get(dualip_agd* agd, float* x_out_dev, float* y_out_dev, void* st
  * Writes (dual_objective from scalars_dev, step) to log slot `iter_index` if 0 <= iter_index < capacity.  No host sync. */
 int dualip_agd_step(dualip_agd* agd, const float* grad_dev, const dualip_scalars* scalars_dev, float beta,
                     int32_t decay_now, double decay_factor, int32_t iter_index, void* stream);
+/* Sharded path: the same step taken directly from the all-reduced packed sums of dualip_matching_partial
+ * ([sum_j a_rj x_rj (m) | c.x | ||x||^2]); also performs dualip_matching_epilogue's m-length tail at the evaluation point x
+ * (grad_out_dev, scalars_out_dev are written), saving that launch.  Replaces matching.py:280-299 + agd.py:163-187. */
+int dualip_agd_step_sharded(dualip_agd* agd, const float* partial_sum_dev, const float* b_dev, double gamma,
+                            float* grad_out_dev, dualip_scalars* scalars_out_dev, float beta, int32_t decay_now,
+                            double decay_factor, int32_t iter_index, void* stream);
 /* Copies log entries [0,count) to host: dual_objective and step size per iteration. Synchronises. */
 int dualip_agd_read_log(dualip_agd* agd, int32_t count, double* dual_obj_host, double* step_host, void* stream);
 int dualip_agd_reserve_log(dualip_agd* agd, int32_t capacity);
