@@ -1,0 +1,95 @@
+"""-m gpu: the CUDA path on fixtures shaped like BASELINE.json's configurations, against outputs of the unmodified reference
+(tests/golden/make_golden_configs.py).  configs[0]: MovieLens-shaped (a == 1, ratings, columns of 20..2600 entries: the
+generic and the warp-per-column kernels).  configs[1..3]: the reference's synthetic generator, simplex, batching on and
+off, the Maximizer from zero, Jacobi row scaling, and a warm start through run_solver(initial_dual_path=...)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from dualip_b200.objectives.matching import MatchingInputArgs, MatchingSolverDualObjectiveFunction
+from dualip_b200.optimizers.agd import AcceleratedGradientDescent
+from dualip_b200.preprocessing.precondition import jacobi_precondition
+from dualip_b200.projections import create_projection_map
+from dualip_b200.run_solver import run_solver
+from dualip_b200.types import ComputeArgs, ObjectiveArgs, SolverArgs
+from test_config_golden import CFG1_MAPS, _check_trace
+from test_gpu_parity import DEV, _csc
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_calc(r, d, tag):
+    assert np.array_equal(r.primal_var.cpu().numpy(), d[f"x_{tag}"]), "primal x differs from the reference"
+    scal, got = d[f"scal_{tag}"], r.scalars64.cpu().numpy()  # reference order: dual_obj, reg, primal_obj, lam.grad, max, sum
+    assert abs(got[0] - scal[0]) <= 1e-5 * abs(scal[0])
+    assert abs(got[2] - scal[1]) <= 1e-5 * abs(scal[1]) + 1e-9
+    assert abs(got[1] - scal[2]) <= 1e-5 * abs(scal[2])
+    assert abs(got[4] - scal[4]) <= 1e-5 * max(1.0, abs(scal[4]))
+    assert abs(got[5] - scal[5]) <= 1e-5 * max(1.0, abs(scal[5]))
+    g, ref = r.dual_gradient.cpu().numpy(), d[f"grad_{tag}"]
+    assert np.abs(g - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
+def _solve(A, C, pm, b, gamma, iters, start=None):
+    obj = MatchingSolverDualObjectiveFunction(MatchingInputArgs(A, C, pm, b), gamma=gamma, batching=False)
+    solver = AcceleratedGradientDescent(max_iter=iters, gamma=gamma, initial_step_size=1e-3, max_step_size=1e-1,
+                                        iteration_callback=lambda i, r: None)
+    res = solver.maximize(obj, torch.zeros(b.numel(), device=DEV) if start is None else start)
+    return res.dual_val.cpu().numpy(), res.dual_objective_log, res.step_size_log
+
+
+@pytest.mark.parametrize("tag", ["box", "simplex"])
+def test_movielens_shaped(tag):
+    d = np.load(f"{GOLDEN}/cfg1_movielens_shaped.npz")
+    ptype, params = CFG1_MAPS[tag]
+    n, gamma = d["ccol"].size - 1, float(d["gamma"])
+    A, C = _csc(d)
+    b = torch.from_numpy(d["b"]).to(DEV)
+    pm = create_projection_map(ptype, params, n)
+    obj = MatchingSolverDualObjectiveFunction(MatchingInputArgs(A, C, pm, b), gamma=gamma)
+    info = obj.plan_info()
+    assert info["n_long_cols"] == 2 and info["launches_per_calc"] == 2
+    _check_calc(obj.calculate(torch.from_numpy(d["lam"]).to(DEV), save_primal=True), d, tag)
+    y, obj_log, step_log = _solve(A, C, pm, b, gamma, 30)
+    _check_trace(y, obj_log, step_log, d, tag)
+
+
+@pytest.mark.parametrize("batching", [True, False])
+def test_reference_generator_calculate(batching):
+    d = np.load(f"{GOLDEN}/cfg2_synthetic.npz")
+    n, m, gamma = d["ccol"].size - 1, int(d["n_rows"]), float(d["gamma"])
+    A, C = _csc(d)
+    obj = MatchingSolverDualObjectiveFunction(
+        MatchingInputArgs(A, C, create_projection_map("simplex", {"z": 1.0}, n), torch.from_numpy(d["b"]).to(DEV)),
+        gamma=gamma, batching=batching)
+    btag = "b1" if batching else "b0"
+    _check_calc(obj.calculate(torch.zeros(m, device=DEV), save_primal=True), d, f"zero_{btag}")
+    _check_calc(obj.calculate(torch.from_numpy(d["lam"]).to(DEV), save_primal=True), d, f"rand_{btag}")
+
+
+def test_reference_generator_ascent_warm_start_and_jacobi(tmp_path):
+    d = np.load(f"{GOLDEN}/cfg2_synthetic.npz")
+    n, gamma = d["ccol"].size - 1, float(d["gamma"])
+    A, C = _csc(d)
+    b = torch.from_numpy(d["b"]).to(DEV)
+    pm = create_projection_map("simplex", {"z": 1.0}, n)
+    y, obj_log, step_log = _solve(A, C, pm, b, gamma, 40)
+    _check_trace(y, obj_log, step_log, d, "plain")
+    # configs[3]: warm start from the reference's own saved dual, through run_solver like the reference (run_solver.py:121-126)
+    path = str(tmp_path / "dual.pt")
+    torch.save(torch.from_numpy(d["plain_dual"].copy()), path)
+    res = run_solver(MatchingInputArgs(A.cpu(), C.cpu(), pm, b.cpu()),
+                     SolverArgs(max_iter=20, gamma=gamma, initial_step_size=1e-3, max_step_size=1e-1, initial_dual_path=path),
+                     ComputeArgs(host_device=DEV), ObjectiveArgs(objective_type="matching", objective_kwargs={"batching": False}))
+    _check_trace(res.dual_val.cpu().numpy(), res.dual_objective_log, res.step_size_log, d, "warm")
+    # configs[2]: Jacobi row scaling on the device, then the same ascent
+    A2, _ = _csc(d)
+    b2 = b.clone()
+    norms = jacobi_precondition(A2, b2)
+    assert np.allclose(norms.cpu().numpy(), d["jacobi_norms"], rtol=2e-6)
+    assert np.allclose(A2.values().cpu().numpy(), d["jacobi_a"], rtol=2e-6) and np.allclose(b2.cpu().numpy(), d["jacobi_b"], rtol=2e-6)
+    # the ascent itself from the reference's scaled values, so that the trace comparison starts from identical inputs
+    A3, _ = _csc(dict(ccol=d["ccol"], row=d["row"], a=d["jacobi_a"], c=d["c"], n_rows=d["n_rows"]))
+    y, obj_log, step_log = _solve(A3, C, pm, torch.from_numpy(d["jacobi_b"]).to(DEV), gamma, 40)
+    _check_trace(y, obj_log, step_log, d, "jacobi", tight=26)
