@@ -232,6 +232,7 @@ def run_native(args):
     if args.gpus != world:
         log(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
 
+    os.environ["DUALIP_PEER_EXCHANGE"] = "1" if args.exchange == "peer" else "0"
     obj, local, b, shard, info = build_problem(args, rank, world, device)
     if rank == 0:
         log(f"[bench] problem ready: {info}")
@@ -276,7 +277,10 @@ def run_native(args):
     result = loop.finish()
     lam_now = loop.current_dual()
     loop.close()
-    launches_per_step = info["plan"]["launches_per_calc"] + 1  # objective kernel(s) + update (the all-reduce is NCCL's)
+    launches_per_step = info["plan"]["launches_per_calc"] + 1  # objective kernel(s) + update (an all-reduce would be NCCL's)
+    exchange = "none (single GPU)" if world == 1 else (
+        "peer memory: partial sums read over NVLink inside the update kernel, no collective call" if loop.peer is not None
+        else "one NCCL all_reduce of m+2 floats per iteration")
 
     # ---- dominant kernel, for the roofline: CUDA events around every launch of the timed region ----
     torch.cuda.synchronize(device)
@@ -333,7 +337,7 @@ def run_native(args):
                                    f"{'simplex(z=1) even / box[0,1] odd' if args.mixed else 'simplex(z=1)'}, "
                                    f"{'Jacobi precond, ' if args.jacobi else ''}Nesterov AGD, gamma={GAMMA}",
                        "workload_id": args.workload, "entities": args.entities, "duals": args.duals, "nnz": info["nnz_total"],
-                       "parallelism": f"entity-sharded x{world}" if world > 1 else "single GPU",
+                       "parallelism": f"entity-sharded x{world}" if world > 1 else "single GPU", "exchange": exchange,
                        "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush between iterations" % (b_alg / 1e9)
                        if b_alg > 2 * L2_BYTES else "inputs fit in L2: numbers are L2-resident, not a roofline claim",
                        "index_dtype": "int64 inputs, uint16 row ids in the plan"},
@@ -448,6 +452,8 @@ def main():
     ap.add_argument("--cpu-sample-cols", type=int, default=4_000_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
+                    help="sharded runs: read the partial sums from peer memory inside the update kernel (default), or NCCL all_reduce")
     ap.add_argument("--kernel-series", action="store_true", help="add the per-iteration kernel times (ms) to the JSON line")
     args = ap.parse_args()
     n, m, sp, mixed, jac = WORKLOADS[args.workload]

@@ -16,6 +16,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 OK, EINVAL, ECUDA, ENOMEM, ERANGE = 0, -1, -2, -3, -4
 PROJ_CLAMP, PROJ_SIMPLEX, PROJ_SIMPLEX_EQ = 0, 1, 2
 PROJ_FLAG_D1_UNPADDED = 1
+PEER_HANDLE_BYTES, PEER_MAX_WORLD = 64, 16
 
 
 class ProjClass(C.Structure):
@@ -72,6 +73,16 @@ SIGNATURES = {
                                   C.c_void_p]),
     "dualip_agd_step_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_float,
                                           C.c_int32, C.c_double, C.c_int32, C.c_void_p]),
+    "dualip_peer_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "dualip_peer_destroy": (None, [C.c_void_p]),
+    "dualip_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dualip_peer_connect_ipc": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dualip_peer_connect_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dualip_peer_window": (C.c_void_p, [C.c_void_p]),
+    "dualip_peer_next_slot": (C.c_void_p, [C.c_void_p]),
+    "dualip_peer_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
+    "dualip_agd_step_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_float,
+                                       C.c_int32, C.c_double, C.c_int32, C.c_void_p]),
     "dualip_agd_read_log": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dualip_agd_reserve_log": (C.c_int, [C.c_void_p, C.c_int32]),
     "dualip_row_sq_norms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
@@ -88,7 +99,7 @@ _lock = threading.Lock()
 
 def build(verbose: bool = False) -> str:
     """Compile the CUDA sources for sm_100a into dualip_b200/_lib/ (nvcc cross-compiles without a GPU)."""
-    res = subprocess.run(["make", "-C", CSRC_DIR], capture_output=True, text=True)
+    res = subprocess.run(["make", "-j4", "-C", CSRC_DIR], capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)
         print(res.stderr)

@@ -5,6 +5,8 @@
 // the device.  The reference recomputes all <=14 ratios every iteration (agd_utils.py:86-88); they only depend on
 // stored history entries, so caching them and computing the newest pair gives the same numbers.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 #include <new>
 
 #include "common.cuh"
@@ -34,16 +36,51 @@ namespace dualip {
 // path; the kernel then also does the m-length tail of the objective (grad = sum - b, lambda.grad, slacks, dual objective:
 // matching.py:280-299), writes grad_out / scal_out, and saves the separate epilogue launch.  Both loops are unrolled by
 // four with every load of a round issued before the first use: a single CTA has no other warps to hide L2 latency.
+struct AgdStepArgs {
+  float* x;
+  float* y;
+  float* gh;
+  float* yh;
+  float* ratios;
+  long long* pushes;
+  double* dstate;
+  const uint8_t* eqmask;
+  const float* grad;  // FROM_PARTIAL: packed sums, m+2 floats
+  const dualip_scalars* scal;
+  int m, H;
+  float beta;
+  int decay_now;
+  double decay_factor;
+  double* log_obj;
+  double* log_step;
+  int iter_index;
+  const float* b;
+  double gamma;
+  float* grad_out;
+  dualip_scalars* scal_out;
+};
+
 template <bool FROM_PARTIAL>
-__global__ void __launch_bounds__(1024) agd_step_kernel(float* __restrict__ x, float* __restrict__ y, float* __restrict__ gh,
-                                                        float* __restrict__ yh, float* __restrict__ ratios,
-                                                        long long* __restrict__ pushes, double* __restrict__ dstate,
-                                                        const uint8_t* __restrict__ eqmask, const float* __restrict__ grad,
-                                                        const dualip_scalars* __restrict__ scal, int m, int H, float beta,
-                                                        int decay_now, double decay_factor, double* log_obj,
-                                                        double* log_step, int iter_index, const float* __restrict__ b,
-                                                        double gamma, float* __restrict__ grad_out,
-                                                        dualip_scalars* __restrict__ scal_out) {
+__device__ __forceinline__ void agd_step_body(const AgdStepArgs& A) {
+  float* __restrict__ x = A.x;
+  float* __restrict__ y = A.y;
+  float* __restrict__ gh = A.gh;
+  float* __restrict__ yh = A.yh;
+  float* __restrict__ ratios = A.ratios;
+  long long* __restrict__ pushes = A.pushes;
+  double* __restrict__ dstate = A.dstate;
+  const uint8_t* __restrict__ eqmask = A.eqmask;
+  const float* grad = A.grad;
+  const dualip_scalars* __restrict__ scal = A.scal;
+  const int m = A.m, H = A.H;
+  const float beta = A.beta;
+  const int decay_now = A.decay_now, iter_index = A.iter_index;
+  const double decay_factor = A.decay_factor, gamma = A.gamma;
+  double* log_obj = A.log_obj;
+  double* log_step = A.log_step;
+  const float* __restrict__ b = A.b;
+  float* grad_out = A.grad_out;
+  dualip_scalars* __restrict__ scal_out = A.scal_out;
   __shared__ double s_red[5][32];
   __shared__ float s_mx[32];
   __shared__ double s_step;
@@ -202,6 +239,98 @@ __global__ void __launch_bounds__(1024) agd_step_kernel(float* __restrict__ x, f
   }
 }
 
+template <bool FROM_PARTIAL>
+__global__ void __launch_bounds__(1024) agd_step_kernel(const AgdStepArgs A) {
+  agd_step_body<FROM_PARTIAL>(A);
+}
+
+// ---- peer-memory exchange: arrival flags and slots in every rank's window (include/dualip_b200.h) ----
+constexpr int kPeerFlagBytes = 256;  // DUALIP_PEER_MAX_WORLD x 8-byte arrival flags, padded
+
+struct PeerArgs {
+  unsigned char* win[DUALIP_PEER_MAX_WORLD];  // window base of every rank, as mapped in this process
+  int rank, world;
+  unsigned long long seq;  // number of this step (1, 2, ...): the flag value, and seq & 1 the slot
+  size_t slot_bytes;
+  unsigned long long timeout_ns;
+  float* sum;   // local m+2 floats: the reduced packed sums
+  int* status;  // local word: set to 1 when a wait timed out
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// One CTA.  Arrive at every peer, wait for every peer, sum the W slots in rank order (identical on all ranks), then the
+// sharded step.  The partial sums of this rank were written by the preceding kernel on the same stream.
+__global__ void __launch_bounds__(1024) agd_step_peer_kernel(const AgdStepArgs A, const PeerArgs P) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int m2 = A.m + 2;
+  if (tid < P.world) {
+    __threadfence_system();
+    // flags[r] of rank t's window is written by rank r only
+    st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.win[tid]) + P.rank, P.seq);
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(P.win[P.rank]) + tid;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys_u64(mine) < P.seq) {
+      if (global_timer_ns() - t0 > P.timeout_ns) {
+        *P.status = 1;
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  const size_t slot_off = (size_t)kPeerFlagBytes + (size_t)(P.seq & 1ull) * P.slot_bytes;
+  for (int base = tid; base < m2; base += 4 * nt) {
+    // every load of the round (W peers x 4 elements) is issued before the first use: one NVLink round trip per round
+    float v[DUALIP_PEER_MAX_WORLD][4];
+#pragma unroll
+    for (int r = 0; r < DUALIP_PEER_MAX_WORLD; ++r) {
+      if (r < P.world) {
+        const float* slot = reinterpret_cast<const float*>(P.win[r] + slot_off);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = base + u * nt;
+          v[r][u] = i < m2 ? ld_relaxed_sys_f32(slot + i) : 0.f;
+        }
+      }
+    }
+    float acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = v[0][u];
+#pragma unroll
+    for (int r = 1; r < DUALIP_PEER_MAX_WORLD; ++r) {  // rank order: every rank adds the same numbers in the same order
+      if (r < P.world) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = __fadd_rn(acc[u], v[r][u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * nt;
+      if (i < m2) P.sum[i] = acc[u];
+    }
+  }
+  __syncthreads();  // P.sum is read below by other threads of this CTA
+  agd_step_body<true>(A);
+}
+
 }  // namespace dualip
 
 extern "C" {
@@ -314,16 +443,44 @@ int dualip_agd_get(dualip_agd* a, float* x_out_dev, float* y_out_dev, void* stre
   return DUALIP_OK;
 }
 
+static AgdStepArgs step_args(dualip_agd* a, const float* grad, const dualip_scalars* scal, float beta, int decay_now,
+                             double decay_factor, int iter_index, const float* b, double gamma, float* grad_out,
+                             dualip_scalars* scal_out) {
+  const bool log = iter_index >= 0 && iter_index < a->log_cap;
+  AgdStepArgs A;
+  A.x = a->x;
+  A.y = a->y;
+  A.gh = a->gh;
+  A.yh = a->yh;
+  A.ratios = a->ratios;
+  A.pushes = a->pushes;
+  A.dstate = a->dstate;
+  A.eqmask = a->eqmask;
+  A.grad = grad;
+  A.scal = scal;
+  A.m = a->m;
+  A.H = a->H;
+  A.beta = beta;
+  A.decay_now = decay_now;
+  A.decay_factor = decay_factor;
+  A.log_obj = log ? a->log_obj : nullptr;
+  A.log_step = log ? a->log_step : nullptr;
+  A.iter_index = log ? iter_index : 0;
+  A.b = b;
+  A.gamma = gamma;
+  A.grad_out = grad_out;
+  A.scal_out = scal_out;
+  return A;
+}
+
 int dualip_agd_step(dualip_agd* a, const float* grad_dev, const dualip_scalars* scalars_dev, float beta,
                     int32_t decay_now, double decay_factor, int32_t iter_index, void* stream) {
   if (!a || !grad_dev) {
     set_error("null argument");
     return DUALIP_EINVAL;
   }
-  const bool log = iter_index >= 0 && iter_index < a->log_cap;
   agd_step_kernel<false><<<1, 1024, 0, (cudaStream_t)stream>>>(
-      a->x, a->y, a->gh, a->yh, a->ratios, a->pushes, a->dstate, a->eqmask, grad_dev, scalars_dev, a->m, a->H, beta, decay_now,
-      decay_factor, log ? a->log_obj : nullptr, log ? a->log_step : nullptr, log ? iter_index : 0, nullptr, 0.0, nullptr, nullptr);
+      step_args(a, grad_dev, scalars_dev, beta, decay_now, decay_factor, iter_index, nullptr, 0.0, nullptr, nullptr));
   DUALIP_CUDA_TRY(cudaGetLastError());
   return DUALIP_OK;
 }
@@ -335,11 +492,168 @@ int dualip_agd_step_sharded(dualip_agd* a, const float* partial_sum_dev, const f
     set_error("null argument");
     return DUALIP_EINVAL;
   }
-  const bool log = iter_index >= 0 && iter_index < a->log_cap;
-  agd_step_kernel<true><<<1, 1024, 0, (cudaStream_t)stream>>>(
-      a->x, a->y, a->gh, a->yh, a->ratios, a->pushes, a->dstate, a->eqmask, partial_sum_dev, nullptr, a->m, a->H, beta, decay_now,
-      decay_factor, log ? a->log_obj : nullptr, log ? a->log_step : nullptr, log ? iter_index : 0, b_dev, gamma, grad_out_dev,
-      scalars_out_dev);
+  agd_step_kernel<true><<<1, 1024, 0, (cudaStream_t)stream>>>(step_args(
+      a, partial_sum_dev, nullptr, beta, decay_now, decay_factor, iter_index, b_dev, gamma, grad_out_dev, scalars_out_dev));
+  DUALIP_CUDA_TRY(cudaGetLastError());
+  return DUALIP_OK;
+}
+
+// ---- exchange windows ----
+struct dualip_peer {
+  int device = 0, m = 0, rank = 0, world = 1;
+  size_t slot_bytes = 0, window_bytes = 0;
+  unsigned char* window = nullptr;                    // own window (cudaMalloc: exportable through CUDA IPC)
+  unsigned char* win[DUALIP_PEER_MAX_WORLD] = {};     // all windows as mapped here
+  bool opened[DUALIP_PEER_MAX_WORLD] = {};            // mapped with cudaIpcOpenMemHandle
+  bool connected = false;
+  float* sum = nullptr;
+  int* status = nullptr;
+  unsigned long long seq = 0;  // steps taken
+  unsigned long long timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;  // DUALIP_PEER_TIMEOUT_MS overrides
+};
+
+void dualip_peer_destroy(dualip_peer* p) {
+  if (!p) return;
+  DeviceGuard g(p->device);
+  for (int r = 0; r < DUALIP_PEER_MAX_WORLD; ++r)
+    if (p->opened[r]) cudaIpcCloseMemHandle(p->win[r]);
+  cudaFree(p->window);
+  cudaFree(p->sum);
+  cudaFree(p->status);
+  delete p;
+}
+
+int dualip_peer_create(dualip_peer** out, int32_t m, int32_t rank, int32_t world, int32_t device) {
+  if (!out || m <= 0 || world < 1 || world > DUALIP_PEER_MAX_WORLD || rank < 0 || rank >= world) {
+    set_error("bad argument (world must be 1..%d)", DUALIP_PEER_MAX_WORLD);
+    return DUALIP_EINVAL;
+  }
+  *out = nullptr;
+  DeviceGuard g(device);
+  if (!g.ok) {
+    set_error("cannot select CUDA device %d", device);
+    return DUALIP_ECUDA;
+  }
+  dualip_peer* p = new (std::nothrow) dualip_peer();
+  if (!p) return DUALIP_ENOMEM;
+  p->device = device;
+  p->m = m;
+  p->rank = rank;
+  p->world = world;
+  if (const char* env = getenv("DUALIP_PEER_TIMEOUT_MS")) {
+    const long long ms = atoll(env);
+    if (ms > 0) p->timeout_ns = (unsigned long long)ms * 1000000ull;
+  }
+  p->slot_bytes = (sizeof(float) * (size_t)(m + 2) + 127) & ~(size_t)127;
+  p->window_bytes = kPeerFlagBytes + 2 * p->slot_bytes;
+  cudaError_t e = cudaMalloc(&p->window, p->window_bytes);
+  if (e == cudaSuccess) e = cudaMemset(p->window, 0, p->window_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&p->sum, sizeof(float) * (m + 2));
+  if (e == cudaSuccess) e = cudaMalloc(&p->status, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(p->status, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error("allocating the exchange window failed: %s", cudaGetErrorString(e));
+    dualip_peer_destroy(p);
+    return DUALIP_ECUDA;
+  }
+  p->win[rank] = p->window;
+  p->connected = world == 1;
+  *out = p;
+  return DUALIP_OK;
+}
+
+int dualip_peer_export(dualip_peer* p, uint8_t* handle_out) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == DUALIP_PEER_HANDLE_BYTES, "IPC handle size");
+  if (!p || !handle_out) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  DeviceGuard g(p->device);
+  cudaIpcMemHandle_t h;
+  DUALIP_CUDA_TRY(cudaIpcGetMemHandle(&h, p->window));
+  memcpy(handle_out, &h, sizeof(h));
+  return DUALIP_OK;
+}
+
+int dualip_peer_connect_ipc(dualip_peer* p, const uint8_t* handles) {
+  if (!p || !handles) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  DeviceGuard g(p->device);
+  for (int r = 0; r < p->world; ++r) {
+    if (r == p->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * DUALIP_PEER_HANDLE_BYTES, sizeof(h));
+    void* ptr = nullptr;
+    DUALIP_CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->win[r] = static_cast<unsigned char*>(ptr);
+    p->opened[r] = true;
+  }
+  p->connected = true;
+  return DUALIP_OK;
+}
+
+int dualip_peer_connect_ptrs(dualip_peer* p, void* const* windows) {
+  if (!p || !windows) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  for (int r = 0; r < p->world; ++r) {
+    if (r == p->rank) continue;
+    if (!windows[r]) {
+      set_error("window %d is null", r);
+      return DUALIP_EINVAL;
+    }
+    p->win[r] = static_cast<unsigned char*>(windows[r]);
+  }
+  p->connected = true;
+  return DUALIP_OK;
+}
+
+void* dualip_peer_window(dualip_peer* p) { return p ? p->window : nullptr; }
+
+float* dualip_peer_next_slot(dualip_peer* p) {
+  if (!p) return nullptr;
+  return reinterpret_cast<float*>(p->window + kPeerFlagBytes + (size_t)((p->seq + 1) & 1ull) * p->slot_bytes);
+}
+
+int dualip_peer_status(dualip_peer* p, int32_t* status_out, void* stream) {
+  if (!p || !status_out) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  DeviceGuard g(p->device);
+  int v = 0;
+  DUALIP_CUDA_TRY(cudaMemcpyAsync(&v, p->status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  DUALIP_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  *status_out = v;
+  return DUALIP_OK;
+}
+
+int dualip_agd_step_peer(dualip_agd* a, dualip_peer* p, const float* b_dev, double gamma, float* grad_out_dev,
+                         dualip_scalars* scalars_out_dev, float beta, int32_t decay_now, double decay_factor,
+                         int32_t iter_index, void* stream) {
+  if (!a || !p || !grad_out_dev || !scalars_out_dev) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  if (!p->connected || p->m != a->m || p->device != a->device) {
+    set_error("exchange window is not connected or does not match the optimizer state");
+    return DUALIP_EINVAL;
+  }
+  PeerArgs P;
+  for (int r = 0; r < DUALIP_PEER_MAX_WORLD; ++r) P.win[r] = r < p->world ? p->win[r] : nullptr;
+  P.rank = p->rank;
+  P.world = p->world;
+  P.seq = ++p->seq;
+  P.slot_bytes = p->slot_bytes;
+  P.timeout_ns = p->timeout_ns;
+  P.sum = p->sum;
+  P.status = p->status;
+  agd_step_peer_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+      step_args(a, p->sum, nullptr, beta, decay_now, decay_factor, iter_index, b_dev, gamma, grad_out_dev, scalars_out_dev), P);
   DUALIP_CUDA_TRY(cudaGetLastError());
   return DUALIP_OK;
 }

@@ -319,6 +319,19 @@ class MatchingSolverDualObjectiveFunctionDistributed(BaseObjective):
         self.device = self.local_objective.device
         self.m = self.local_objective.m
         self.b_vec = b_vec.to(device=self.device, dtype=torch.float32).contiguous()
+        self._peer = None
+        self._peer_tried = False
+
+    def peer_exchange(self):
+        """The NVLink exchange windows of this objective (dualip_b200.utils.peer_exchange), set up on first use.
+        COLLECTIVE: every rank must call it at the same point.  None when the ranks cannot map each other's memory (not
+        one host, not NCCL, DUALIP_PEER_EXCHANGE=0); the fused loop then uses the NCCL all-reduce."""
+        if not self._peer_tried:
+            from dualip_b200.utils.peer_exchange import PeerExchange
+
+            self._peer_tried = True
+            self._peer = PeerExchange.over_process_group(self.m, self.device)
+        return self._peer
 
     def host_io_bytes(self) -> tuple:
         return 4 * self.m, 4 * self.m + 8 * len(_native.SCALAR_FIELDS)

@@ -236,6 +236,9 @@ class FusedAscentLoop:
             self.grad = torch.empty(self.m, dtype=torch.float32, device=self.device)
             self.scal = torch.zeros(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=self.device)
             self.partial = torch.empty(self.m + 2, dtype=torch.float32, device=self.device) if self.sharded else None
+        # sharded, no per-iteration callback: the partial sums are exchanged through peer memory inside the update kernel
+        # (the choice must not depend on the rank: every rank takes the same path)
+        self.peer = f.peer_exchange() if (self.sharded and not solver._user_callback_active()) else None
         self.primal = None
         self.kernel_events = None  # optional list of (start, end) CUDA events per step, for measurement
         self.kernel_events_base = 1
@@ -255,7 +258,16 @@ class FusedAscentLoop:
             if self.decay and i % solver.gamma_decay_params["decay_steps"] == 0:
                 decay_now, factor = 1, float(solver.gamma_decay_params["decay_factor"])
             callback = self.rank == 0 and solver._user_callback_active()
-            if self.sharded:
+            if self.sharded and self.peer is not None:
+                # shard kernel -> update kernel that reads every peer's partial sums over NVLink: no collective call
+                f.local_objective.gamma = gamma_i
+                f.local_objective.launch_partial(self.x_ptr, gamma_i, self.peer.next_slot())
+                if ev is not None:
+                    ev[1].record()
+                _native.check(self.lib.dualip_agd_step_peer(
+                    self.handle, self.peer.handle, f.b_vec.data_ptr(), float(gamma_i), self.grad.data_ptr(),
+                    self.scal.data_ptr(), float(self.beta[i - 1]), decay_now, factor, i - 1, stream), "dualip_agd_step_peer")
+            elif self.sharded:
                 from dualip_b200.objectives.matching import reduce_partials
 
                 f.local_objective.gamma = gamma_i
@@ -308,6 +320,13 @@ class FusedAscentLoop:
             _native.check(self.lib.dualip_agd_read_log(self.handle, n, obj_log, step_log, stream), "dualip_agd_read_log")
             y = self.current_dual()
             torch.cuda.synchronize(self.device)
+            if self.peer is not None:
+                timed_out = self.peer.status()
+                if dist.is_available() and dist.is_initialized() and self.peer.world == dist.get_world_size():
+                    dist.barrier()  # nobody frees or reuses a window a peer may still be reading
+                if timed_out:
+                    raise RuntimeError("peer exchange: a rank did not arrive within the time-out (ranks out of step?); "
+                                       "results of this run are invalid.  DUALIP_PEER_EXCHANGE=0 selects the NCCL path")
         dual_obj_log = [float(v) for v in obj_log[:n]]
         step_size_log = [float(v) for v in step_log[:n]]
         if self.decay and step_size_log:

@@ -1,0 +1,119 @@
+"""Exchange windows of the sharded path: the packed partial sums are read from the peers' memory over NVLink inside the
+update kernel (include/dualip_b200.h, dualip_peer_* / dualip_agd_step_peer) instead of going through a collective call.
+
+The reference reduces with three dist.reduce + a barrier and broadcasts the iterate twice per iteration
+(src/dualip/objectives/matching.py:272-277, optimizers/agd.py:204-206).  Here torch.distributed only carries the 64-byte
+CUDA IPC handles at setup time; per iteration there is no collective call at all.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import socket
+import zlib
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from dualip_b200 import _native
+
+
+class PeerExchange:
+    """This rank's exchange window plus the mapped windows of its peers."""
+
+    def __init__(self, m: int, rank: int, world: int, device: torch.device):
+        self.m, self.rank, self.world, self.device = m, rank, world, torch.device(device)
+        self.lib = _native.lib()
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.dualip_peer_create(ctypes.byref(self.handle), m, rank, world, self.device.index),
+                          "dualip_peer_create")
+
+    # -- wiring -------------------------------------------------------------------------------------------
+    def export_handle(self) -> bytes:
+        buf = (ctypes.c_uint8 * _native.PEER_HANDLE_BYTES)()
+        _native.check(self.lib.dualip_peer_export(self.handle, buf), "dualip_peer_export")
+        return bytes(buf)
+
+    def connect_ipc(self, handles: Sequence[bytes]) -> None:
+        blob = b"".join(handles)
+        assert len(blob) == self.world * _native.PEER_HANDLE_BYTES
+        buf = (ctypes.c_uint8 * len(blob)).from_buffer_copy(blob)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.dualip_peer_connect_ipc(self.handle, buf), "dualip_peer_connect_ipc")
+
+    @property
+    def window(self) -> int:
+        return self.lib.dualip_peer_window(self.handle)
+
+    @staticmethod
+    def connect_local(exchanges: Sequence["PeerExchange"]) -> None:
+        """Wires windows that live in ONE process (several shards per process; tests on a single GPU)."""
+        ptrs = (ctypes.c_void_p * len(exchanges))(*[e.window for e in exchanges])
+        for e in exchanges:
+            _native.check(e.lib.dualip_peer_connect_ptrs(e.handle, ptrs), "dualip_peer_connect_ptrs")
+
+    @classmethod
+    def over_process_group(cls, m: int, device: torch.device, group=None) -> Optional["PeerExchange"]:
+        """Collective over `group`: allocates a window per rank and maps every peer's.  Returns None (on EVERY rank) when the
+        ranks are not all on one host, the world is larger than the window's flag array, DUALIP_PEER_EXCHANGE=0, or any
+        rank fails to map a peer window; the caller then keeps the NCCL all-reduce."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        want = os.environ.get("DUALIP_PEER_EXCHANGE", "1") != "0" and 1 < world <= _native.PEER_MAX_WORLD
+        if dist.get_backend(group) != "nccl":
+            want = False
+        device = torch.device(device)
+        with torch.cuda.device(device):
+            host = zlib.crc32(socket.gethostname().encode())
+            mine = torch.tensor([1 if want else 0, host], dtype=torch.int64, device=device)
+            every = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine, group=group)
+            every = torch.stack(every).cpu()
+            if not bool((every[:, 0] == 1).all()) or not bool((every[:, 1] == every[0, 1]).all()):
+                return None
+            ex, ok = None, 1
+            try:
+                ex = cls(m, rank, world, device)
+                h = torch.frombuffer(bytearray(ex.export_handle()), dtype=torch.uint8).to(device)
+            except Exception:
+                ok, h = 0, torch.zeros(_native.PEER_HANDLE_BYTES, dtype=torch.uint8, device=device)
+            hs = [torch.empty_like(h) for _ in range(world)]
+            dist.all_gather(hs, h, group=group)
+            if ok:
+                try:
+                    ex.connect_ipc([bytes(t.cpu().numpy().tobytes()) for t in hs])
+                except Exception:
+                    ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) != 1:
+                if ex is not None:
+                    ex.close()
+                return None
+        return ex
+
+    # -- per step -----------------------------------------------------------------------------------------
+    def next_slot(self) -> int:
+        """Device address the partial sums of the upcoming step must be written to."""
+        return self.lib.dualip_peer_next_slot(self.handle)
+
+    def status(self) -> int:
+        out = ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.dualip_peer_status(self.handle, ctypes.byref(out),
+                                                      torch.cuda.current_stream(self.device).cuda_stream), "dualip_peer_status")
+        return int(out.value)
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.dualip_peer_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -189,6 +189,37 @@ int dualip_agd_step(dualip_agd* agd, const float* grad_dev, const dualip_scalars
 int dualip_agd_step_sharded(dualip_agd* agd, const float* partial_sum_dev, const float* b_dev, double gamma,
                             float* grad_out_dev, dualip_scalars* scalars_out_dev, float beta, int32_t decay_now,
                             double decay_factor, int32_t iter_index, void* stream);
+/* ---- peer-memory exchange of the sharded path (one process per GPU, NVLink / NVSwitch) ----
+ * Replaces the collective of the sharded path (the reference's three dist.reduce + barrier, matching.py:272-277; this
+ * library's single NCCL all-reduce) by loads from the peers' memory inside the update kernel: every rank owns an exchange
+ * window {arrival flags | two slots of m+2 floats}; dualip_matching_partial writes the shard's packed sums into the slot
+ * of the upcoming step (dualip_peer_next_slot); dualip_agd_step_peer then (1) stores its step number into every peer's
+ * flag array (st.release.sys over NVLink), (2) waits until all peers have arrived (ld.acquire.sys on its own flags),
+ * (3) sums the W slots in rank order -- so every rank obtains bit-identical sums -- and (4) runs the objective's tail
+ * and the accelerated update (as dualip_agd_step_sharded).  Two slots suffice: a slot is rewritten two steps later, after
+ * a barrier that every reader of the old contents has passed.  The wait is bounded (20 s, or DUALIP_PEER_TIMEOUT_MS): on time-out the status word
+ * is set (dualip_peer_status) and the kernel proceeds, it never hangs.  All ranks must take the same number of steps. */
+typedef struct dualip_peer dualip_peer;
+#define DUALIP_PEER_HANDLE_BYTES 64
+#define DUALIP_PEER_MAX_WORLD 16
+int dualip_peer_create(dualip_peer** out, int32_t m, int32_t rank, int32_t world, int32_t device);
+void dualip_peer_destroy(dualip_peer* peer);
+/* CUDA IPC handle of this rank's window (DUALIP_PEER_HANDLE_BYTES bytes) for the caller to all-gather. */
+int dualip_peer_export(dualip_peer* peer, uint8_t* handle_out);
+/* Opens the windows of all ranks: world x DUALIP_PEER_HANDLE_BYTES bytes in rank order (the own entry is ignored). */
+int dualip_peer_connect_ipc(dualip_peer* peer, const uint8_t* handles);
+/* Same with device pointers the caller obtained itself (windows of several ranks living in one process, symmetric-memory
+ * allocators): world pointers in rank order, each a dualip_peer_window() of that rank. */
+int dualip_peer_connect_ptrs(dualip_peer* peer, void* const* windows);
+void* dualip_peer_window(dualip_peer* peer);
+/* Where dualip_matching_partial must write the packed sums consumed by the NEXT dualip_agd_step_peer (m+2 floats). */
+float* dualip_peer_next_slot(dualip_peer* peer);
+/* 0 = fine, 1 = a wait timed out (results after that step are invalid).  Synchronises the stream. */
+int dualip_peer_status(dualip_peer* peer, int32_t* status_out, void* stream);
+int dualip_agd_step_peer(dualip_agd* agd, dualip_peer* peer, const float* b_dev, double gamma, float* grad_out_dev,
+                         dualip_scalars* scalars_out_dev, float beta, int32_t decay_now, double decay_factor,
+                         int32_t iter_index, void* stream);
+
 /* Copies log entries [0,count) to host: dual_objective and step size per iteration. Synchronises. */
 int dualip_agd_read_log(dualip_agd* agd, int32_t count, double* dual_obj_host, double* step_host, void* stream);
 int dualip_agd_reserve_log(dualip_agd* agd, int32_t capacity);

@@ -57,6 +57,30 @@ def main():
     gathered = [torch.empty_like(lam) for _ in range(world)]
     dist.all_gather(gathered, lam)
     assert all(torch.equal(g, gathered[0]) for g in gathered), "replicated optimizer state diverged across ranks"
+    # 3) the same shard through both exchange paths: partial sums read from peer memory inside the update kernel (no
+    #    per-iteration callback) vs the NCCL all-reduce (DUALIP_PEER_EXCHANGE=0)
+    from dualip_b200.optimizers.agd import no_iteration_callback
+
+    a_s, c_s, index_map = split_tensors_to_devices(A, C, ["cpu"] * world)
+    runs = {}
+    for tag, env in (("peer", "1"), ("nccl", "0")):
+        os.environ["DUALIP_PEER_EXCHANGE"] = env
+        local = MatchingInputArgs(a_s[rank].to(dev), c_s[rank].to(dev), global_to_local_projection_map(args.projection_map, index_map[rank]), None, None)
+        f = MatchingSolverDualObjectiveFunctionDistributed(local_matching_input_args=local, b_vec=args.b_vec, gamma=gamma, host_device=dev)
+        solver = AcceleratedGradientDescent(max_iter=40, gamma=gamma, initial_step_size=1e-3, max_step_size=0.1,
+                                            gamma_decay_type="step", gamma_decay_params={"decay_steps": 9, "decay_factor": 0.5},
+                                            iteration_callback=no_iteration_callback)
+        runs[tag] = solver.maximize(f, torch.zeros(m, device=dev), rank=rank)
+        assert (f._peer is not None) == (tag == "peer"), f"exchange path {tag}: peer windows {'missing' if tag == 'peer' else 'unexpected'}"
+        again = solver.__class__(max_iter=5, gamma=gamma, iteration_callback=no_iteration_callback).maximize(f, runs[tag].dual_val, rank=rank)
+        assert len(again.dual_objective_log) == 5  # a second loop on the same objective keeps the windows' step counter
+    assert np.allclose(runs["peer"].dual_objective_log, runs["nccl"].dual_objective_log, rtol=1e-6)
+    assert np.allclose(runs["peer"].step_size_log, runs["nccl"].step_size_log, rtol=1e-3)
+    assert torch.allclose(runs["peer"].dual_val, runs["nccl"].dual_val, rtol=1e-4, atol=1e-5)
+    lam = runs["peer"].dual_val.clone()
+    gathered = [torch.empty_like(lam) for _ in range(world)]
+    dist.all_gather(gathered, lam)
+    assert all(torch.equal(g, gathered[0]) for g in gathered), "peer path: replicas must be bit-identical"
     dist.barrier()
     if rank == 0:
         print("DIST_WORKER_OK", world)

@@ -1,0 +1,135 @@
+"""-m gpu: the peer-memory exchange (dualip_peer_* / dualip_agd_step_peer) on ONE GPU: two shards of a problem, two
+optimizer states and two exchange windows live in one process, wired by pointer (dualip_peer_connect_ptrs); each "rank"
+runs on its own stream, so the two update kernels wait for each other exactly as two processes on two GPUs would.  The
+two-process version over CUDA IPC runs in tests/dist_worker.py (needs 2 GPUs)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import random_problem
+from dualip_b200 import _native
+from dualip_b200.objectives.matching import MatchingInputArgs, MatchingSolverDualObjectiveFunction
+from dualip_b200.optimizers.agd import AcceleratedGradientDescent
+from dualip_b200.projections import create_projection_map
+from dualip_b200.utils.dist_utils import global_to_local_projection_map, split_tensors_to_devices
+from dualip_b200.utils.peer_exchange import PeerExchange
+from test_gpu_parity import DEV, _csc
+
+pytestmark = pytest.mark.gpu
+N_SCAL = len(_native.SCALAR_FIELDS)
+
+
+class _Rank:
+    def __init__(self, objective, m, initial_step, max_step):
+        self.obj = objective
+        self.stream = torch.cuda.Stream(device=DEV)
+        self.agd = ctypes.c_void_p()
+        lib = _native.lib()
+        _native.check(lib.dualip_agd_create(ctypes.byref(self.agd), m, 0, None, None, initial_step, max_step, 15))
+        _native.check(lib.dualip_agd_reserve_log(self.agd, 64))
+        self.x_ptr = lib.dualip_agd_x(self.agd)
+        self.grad = torch.empty(m, device=DEV)
+        self.scal = torch.zeros(N_SCAL, dtype=torch.float64, device=DEV)
+        self.partial = torch.empty(m + 2, device=DEV)
+
+    def logs(self, n):
+        o, s = (ctypes.c_double * n)(), (ctypes.c_double * n)()
+        _native.check(_native.lib().dualip_agd_read_log(self.agd, n, o, s, torch.cuda.current_stream().cuda_stream))
+        return np.array(o[:n]), np.array(s[:n])
+
+    def dual(self):
+        y = torch.empty_like(self.grad)
+        _native.check(_native.lib().dualip_agd_get(self.agd, None, y.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        return y
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_peer_step_matches_summed_partials(world, monkeypatch):
+    monkeypatch.setenv("DUALIP_PEER_TIMEOUT_MS", "3000")
+    lib = _native.lib()
+    p = random_problem(23, 6001, 96, 8.0, scale_c=10.0, lam_scale=0.5)
+    n, m, gamma, iters = p["n_cols"], p["n_rows"], 2e-2, 40
+    A, C = _csc(p)
+    b = torch.from_numpy(p["b"]).to(DEV)
+    pm = create_projection_map("simplex", {"z": 1.0}, n)
+    a_s, c_s, index_map = split_tensors_to_devices(A, C, [DEV] * world)
+    beta = AcceleratedGradientDescent(max_iter=iters, gamma=gamma).beta_seq.tolist()
+
+    def shards():
+        return [MatchingSolverDualObjectiveFunction(
+            MatchingInputArgs(a_s[k], c_s[k], global_to_local_projection_map(pm, index_map[k]), None), gamma) for k in range(world)]
+
+    # (a) peer path: every rank on its own stream, no host-side reduction
+    ranks = [_Rank(o, m, 1e-3, 0.1) for o in shards()]
+    ex = [PeerExchange(m, k, world, torch.device(DEV)) for k in range(world)]
+    PeerExchange.connect_local(ex)
+    torch.cuda.synchronize()
+    for i in range(iters):
+        decay = 1 if (i + 1) % 9 == 0 else 0
+        g_i = gamma * 0.5 ** (i // 9)
+        for k, r in enumerate(ranks):  # all shard kernels first: they never wait, the update kernels do
+            with torch.cuda.stream(r.stream):
+                r.obj.launch_partial(r.x_ptr, g_i, ex[k].next_slot())
+        for k, r in enumerate(ranks):
+            with torch.cuda.stream(r.stream):
+                _native.check(lib.dualip_agd_step_peer(r.agd, ex[k].handle, b.data_ptr(), g_i, r.grad.data_ptr(), r.scal.data_ptr(),
+                                                       beta[i], decay, 0.5, i, r.stream.cuda_stream))
+    torch.cuda.synchronize()
+    assert [e.status() for e in ex] == [0] * world
+    peer_logs = [r.logs(iters) for r in ranks]
+    peer_duals = [r.dual() for r in ranks]
+    for k in range(1, world):  # replicas add the same numbers in the same order: bit-identical state
+        assert np.array_equal(peer_logs[k][0], peer_logs[0][0]) and np.array_equal(peer_logs[k][1], peer_logs[0][1])
+        assert torch.equal(peer_duals[k], peer_duals[0])
+
+    # (b) what a collective would do: partial sums added in rank order on the host side, then dualip_agd_step_sharded
+    ref = _Rank(None, m, 1e-3, 0.1)
+    objs = shards()
+    parts = [torch.empty(m + 2, device=DEV) for _ in range(world)]
+    st = torch.cuda.current_stream().cuda_stream
+    for i in range(iters):
+        decay = 1 if (i + 1) % 9 == 0 else 0
+        g_i = gamma * 0.5 ** (i // 9)
+        for k, o in enumerate(objs):
+            o.launch_partial(ref.x_ptr, g_i, parts[k].data_ptr())
+        total = parts[0].clone()
+        for k in range(1, world):
+            total += parts[k]
+        _native.check(lib.dualip_agd_step_sharded(ref.agd, total.data_ptr(), b.data_ptr(), g_i, ref.grad.data_ptr(),
+                                                  ref.scal.data_ptr(), beta[i], decay, 0.5, i, st))
+    torch.cuda.synchronize()
+    ref_obj, ref_step = ref.logs(iters)
+    if all(o.plan_info()["fixed_point"] == 1 for o in objs):
+        # fixed-point shard sums are order-independent, and both paths add the shards in rank order: same bits
+        assert np.array_equal(peer_logs[0][0], ref_obj) and np.array_equal(peer_logs[0][1], ref_step)
+        assert torch.equal(peer_duals[0], ref.dual())
+    else:  # fp32 atomics inside a shard: summation order varies from launch to launch
+        assert np.allclose(peer_logs[0][0], ref_obj, rtol=1e-5) and np.allclose(peer_logs[0][1], ref_step, rtol=3e-2)
+        assert torch.allclose(peer_duals[0], ref.dual(), rtol=1e-3, atol=1e-3)
+    for r in ranks + [ref]:
+        lib.dualip_agd_destroy(r.agd)
+    for e in ex:
+        e.close()
+
+
+def test_peer_wait_is_bounded(monkeypatch):
+    """A rank whose peer never arrives sets the status word after the time-out instead of hanging."""
+    monkeypatch.setenv("DUALIP_PEER_TIMEOUT_MS", "200")
+    lib = _native.lib()
+    m = 64
+    ex = [PeerExchange(m, k, 2, torch.device(DEV)) for k in range(2)]
+    PeerExchange.connect_local(ex)
+    r = _Rank(None, m, 1e-3, 0.1)
+    b = torch.zeros(m, device=DEV)
+    torch.cuda.synchronize()
+    _native.check(lib.dualip_agd_step_peer(r.agd, ex[0].handle, b.data_ptr(), 1e-2, r.grad.data_ptr(), r.scal.data_ptr(), 0.0, 0, 1.0, 0,
+                                           torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert ex[0].status() == 1 and ex[1].status() == 0
+    with pytest.raises(ValueError):
+        PeerExchange(m, 0, _native.PEER_MAX_WORLD + 1, torch.device(DEV))
+    lib.dualip_agd_destroy(r.agd)
