@@ -20,6 +20,7 @@ from dualip_b200.run_solver import run_solver
 from dualip_b200.types import ComputeArgs, ObjectiveArgs, ObjectiveResult, SolverArgs, SolverResult
 from dualip_b200.utils.dist_utils import global_to_local_projection_map, shard_sizes, split_tensors_to_devices
 from dualip_b200.utils.sparse_utils import split_csc_by_cols
+from conftest import GOLDEN
 from oracle import dualip_oracle as O
 
 
@@ -190,3 +191,54 @@ def test_install_as_alias():
     assert mod.MatchingInputArgs is MatchingInputArgs
     for k in [k for k in sys.modules if k.startswith("dualip_alias_for_test")]:
         del sys.modules[k]
+
+
+def test_reference_cache_layout_shard_direct_reader(tmp_path):
+    """dualip_b200.utils.data_cache against the cache layout of the reference's generator
+    (benchmark/generate_synthetic_data.py:172-342): metadata identical to what the reference itself wrote for this
+    problem (kept in the fixture), shards read directly by column range, rebased, c negated."""
+    import json
+    import os
+    import sys
+
+    from dualip_b200.utils import data_cache
+
+    d = np.load(os.path.join(GOLDEN, "cfg2_synthetic.npz"))
+    ref_meta = json.loads(str(d["meta_json"]))
+    n, m = ref_meta["num_sources"], ref_meta["num_destinations"]
+    key = dict(num_sources=n, num_destinations=m, target_sparsity=ref_meta["target_sparsity"], dtype=torch.float32, seed=ref_meta["seed"])
+    assert data_cache.cache_prefix(**key) + "_meta.json" == str(d["meta_name"])
+    # the reference stores c positive (float64 from its numpy generator) and negates on load (:448)
+    c_pos = (-d["c"]).astype(np.dtype(ref_meta["array_dtypes"]["c_vals"]))
+    a = d["a"].astype(np.dtype(ref_meta["array_dtypes"]["A_vals"]))
+    b = d["b"].astype(np.dtype(ref_meta["array_dtypes"]["b_vec"]))
+    prefix = data_cache.save_cache(str(tmp_path), key, d["ccol"], d["row"], a, c_pos, b)
+    assert json.load(open(tmp_path / f"{prefix}_meta.json")) == ref_meta
+    whole = data_cache.load_shard(str(tmp_path), prefix)
+    assert torch.equal(whole.ccol, torch.from_numpy(d["ccol"])) and torch.equal(whole.row, torch.from_numpy(d["row"]))
+    assert torch.equal(whole.a, torch.from_numpy(d["a"])) and torch.equal(whole.c, torch.from_numpy(d["c"]))
+    assert torch.equal(whole.b, torch.from_numpy(d["b"])) and whole.a.dtype == torch.float32
+    world, parts = 3, []
+    for r in range(world):
+        s = data_cache.load_shard(str(tmp_path), prefix, rank=r, world=world)
+        assert int(s.ccol[0]) == 0 and s.ccol.numel() == shard_sizes(n, world)[r] + 1
+        A, C = s.csc()
+        assert A.shape == (m, s.col_end - s.col_start) and torch.equal(A.ccol_indices(), C.ccol_indices())
+        parts.append(s)
+    assert torch.equal(torch.cat([s.row for s in parts]), whole.row) and torch.equal(torch.cat([s.c for s in parts]), whole.c)
+    assert [s.col_start for s in parts] == [0, 6667, 13334] and parts[-1].col_end == n
+    with pytest.raises(ValueError):
+        data_cache.load_shard(str(tmp_path), prefix, col_range=(5, n + 1))
+    if os.path.isdir("/root/reference/benchmark"):  # build container only: the reference's own loader accepts our files
+        sys.path.insert(0, "/root/reference")
+        sys.path.insert(0, "/root/reference/src")
+        try:
+            from benchmark import generate_synthetic_data as ref_gen
+        except Exception:
+            ref_gen = None
+        finally:
+            sys.path.remove("/root/reference")
+            sys.path.remove("/root/reference/src")
+        if ref_gen is not None and hasattr(ref_gen, "_load_cached_numpy"):
+            got = ref_gen._load_cached_numpy(ref_gen._get_cache_key(n, m, key["target_sparsity"], torch.float32, key["seed"]), str(tmp_path))
+            assert got is not None and np.array_equal(got[0], d["ccol"]) and np.array_equal(got[3], c_pos)
