@@ -820,7 +820,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
           }
           // exact sums over the support and the two boundary values, then the reference's own conditions
           float th = 0.f;
-          for (int fix = 0; fix < 6; ++fix) {
+          for (int fix = 0; fix < 64; ++fix) {
             double ssum = 0.0;
             float umin = INFINITY, uout = -INFINITY;
             cnt = 0;
@@ -836,7 +836,11 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
             th = __fdiv_rn(__fsub_rn((float)ssum, z), (float)max(cnt, 1));
             bool changed = false;
             if (need_theta && cnt > 1 && !(__fsub_rn(umin, th) > 0.f)) {
-              tf = umin;  // cond_rho fails in the fp32 formula: drop the smallest support value(s)
+              // cond_rho fails in the fp32 formula: every support value <= th goes (a Michelot step with exact sums; th >= umin
+              // here, and the largest value stays in: th < max unless rounding at huge magnitudes, hence the clamp).  Dropping
+              // only the smallest value per round needs one round per value within the guard band below theta, which long
+              // columns with closely spaced values (ratings data) exceed.
+              tf = fmaxf(umin, fminf(th, __uint_as_float(__float_as_uint(m1) - 1u)));
               changed = true;
             } else if (need_theta && uout > -INFINITY) {
               const float t1 = __fdiv_rn(__fsub_rn((float)(ssum + (double)uout), z), (float)(cnt + 1));

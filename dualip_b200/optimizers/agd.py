@@ -161,7 +161,7 @@ class AcceleratedGradientDescent:
 
     # -- generic host-driven loop (user objectives, CPU tensors) -------------------------------------------
     def _maximize_generic(self, f, initial_value: torch.Tensor, rank: int) -> SolverResult:
-        grad_history, dual_history = [], []
+        grad_history, dual_history, lipschitz_cache = [], [], []
         dual_obj_log, step_size_log = [], []
         x = initial_value.clone()
         y = initial_value.clone()
@@ -181,7 +181,8 @@ class AcceleratedGradientDescent:
                 dual_obj = objective_result.dual_objective.cpu().item()
                 dual_obj_log.append(dual_obj)
                 step_size = calculate_step_size(objective_result.dual_gradient, y, grad_history, dual_history,
-                                                initial_step_size=self.initial_step_size, max_step_size=self.max_step_size)
+                                                initial_step_size=self.initial_step_size, max_step_size=self.max_step_size,
+                                                lipschitz_cache=lipschitz_cache)
                 step_size_log.append(step_size)
                 y_new = project_on_nn_cone(x + objective_result.dual_gradient * step_size, equality_mask)
                 b_i = self.beta_seq[i - 1]

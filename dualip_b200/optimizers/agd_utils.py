@@ -43,11 +43,24 @@ def step_size_from_lipschitz_constants(lipschitz_constants: list, max_history_le
 
 
 def calculate_step_size(dual_grad, dual_val, grad_history: list, dual_history: list, max_history_length: int = 15,
-                        initial_step_size: float = 1e-5, max_step_size: float = 0.1) -> float:
-    """Pushes the newest (gradient, dual) pair and returns the step (reference agd_utils.py:65-89)."""
+                        initial_step_size: float = 1e-5, max_step_size: float = 0.1, lipschitz_cache: list = None) -> float:
+    """Pushes the newest (gradient, dual) pair and returns the step (reference agd_utils.py:65-89).
+
+    The reference recomputes every ||g_{k+1}-g_k|| / ||y_{k+1}-y_k|| of the ring on each call (:86-88) although only the
+    newest pair changed.  With `lipschitz_cache` (a list owned by the caller, one entry per adjacent pair of the ring)
+    the old estimates are reused: same numbers, one estimate per call instead of fourteen."""
+    if lipschitz_cache is None:
+        update_dual_gradient_history(dual_grad, dual_val, grad_history, dual_history, max_history_length)
+        estimates = [
+            estimate_lipschitz_constant(grad_history[k], grad_history[k + 1], dual_history[k], dual_history[k + 1])
+            for k in range(len(grad_history) - 1)
+        ]
+        return step_size_from_lipschitz_constants(estimates, max_history_length, initial_step_size, max_step_size)
+    before = len(grad_history)
     update_dual_gradient_history(dual_grad, dual_val, grad_history, dual_history, max_history_length)
-    estimates = [
-        estimate_lipschitz_constant(grad_history[k], grad_history[k + 1], dual_history[k], dual_history[k + 1])
-        for k in range(len(grad_history) - 1)
-    ]
-    return step_size_from_lipschitz_constants(estimates, max_history_length, initial_step_size, max_step_size)
+    dropped = before + 1 - len(grad_history)  # entries evicted from the front of the ring
+    del lipschitz_cache[:dropped]
+    if len(grad_history) >= 2:
+        lipschitz_cache.append(float(estimate_lipschitz_constant(grad_history[-2], grad_history[-1], dual_history[-2], dual_history[-1])))
+    del lipschitz_cache[: max(0, len(lipschitz_cache) - (len(grad_history) - 1))]
+    return step_size_from_lipschitz_constants(lipschitz_cache, max_history_length, initial_step_size, max_step_size)
