@@ -658,6 +658,130 @@ int dualip_agd_step_peer(dualip_agd* a, dualip_peer* p, const float* b_dev, doub
   return DUALIP_OK;
 }
 
+// ---- host-resident twin of the optimizer state: the same update for callers that keep the iterate in host memory ----
+struct dualip_agd_host {
+  int m = 0, H = 15;
+  float* x = nullptr;   // pinned when a CUDA device is present (the caller copies it host->device every iteration)
+  float* y = nullptr;
+  bool pinned = false;
+  float* gh = nullptr;
+  float* yh = nullptr;
+  float ratios[64] = {};
+  long long pushes = 0;
+  double max_step = 0.1, init_step = 1e-5;
+  uint8_t* eqmask = nullptr;
+};
+
+void dualip_agd_host_destroy(dualip_agd_host* h) {
+  if (!h) return;
+  if (h->pinned) {
+    cudaFreeHost(h->x);
+  } else {
+    free(h->x);
+  }
+  free(h->y);
+  free(h->gh);
+  free(h->yh);
+  free(h->eqmask);
+  delete h;
+}
+
+int dualip_agd_host_create(dualip_agd_host** out, int32_t m, const float* initial_host, const uint8_t* equality_mask_host,
+                           double initial_step_size, double max_step_size, int32_t history_len) {
+  if (!out || m <= 0 || history_len < 2 || history_len > 64) {
+    set_error("bad argument");
+    return DUALIP_EINVAL;
+  }
+  *out = nullptr;
+  dualip_agd_host* h = new (std::nothrow) dualip_agd_host();
+  if (!h) return DUALIP_ENOMEM;
+  h->m = m;
+  h->H = history_len;
+  h->max_step = max_step_size;
+  h->init_step = initial_step_size;
+  void* px = nullptr;
+  if (cudaHostAlloc(&px, sizeof(float) * m, cudaHostAllocDefault) == cudaSuccess) {
+    h->x = static_cast<float*>(px);
+    h->pinned = true;
+  } else {
+    cudaGetLastError();  // no device / no driver: plain memory (the update itself needs no GPU)
+    h->x = static_cast<float*>(malloc(sizeof(float) * m));
+  }
+  h->y = static_cast<float*>(malloc(sizeof(float) * m));
+  h->gh = static_cast<float*>(malloc(sizeof(float) * (size_t)m * h->H));
+  h->yh = static_cast<float*>(malloc(sizeof(float) * (size_t)m * h->H));
+  if (equality_mask_host) h->eqmask = static_cast<uint8_t*>(malloc(m));
+  if (!h->x || !h->y || !h->gh || !h->yh || (equality_mask_host && !h->eqmask)) {
+    dualip_agd_host_destroy(h);
+    set_error("out of host memory");
+    return DUALIP_ENOMEM;
+  }
+  for (int i = 0; i < m; ++i) h->x[i] = h->y[i] = initial_host ? initial_host[i] : 0.f;
+  if (equality_mask_host) memcpy(h->eqmask, equality_mask_host, m);
+  *out = h;
+  return DUALIP_OK;
+}
+
+float* dualip_agd_host_x(dualip_agd_host* h) { return h ? h->x : nullptr; }
+float* dualip_agd_host_y(dualip_agd_host* h) { return h ? h->y : nullptr; }
+
+// Same arithmetic as agd_step_kernel<false>: float32 differences and iterates, norms accumulated in double.
+int dualip_agd_host_step(dualip_agd_host* h, const float* grad_host, float beta, int32_t decay_now, double decay_factor,
+                         double* step_out) {
+  if (!h || !grad_host) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  const int m = h->m, H = h->H;
+  const long long t = h->pushes;
+  const int slot = (int)(t % H), prev = (int)((t + H - 1) % H);
+  float* gs = h->gh + (size_t)slot * m;
+  float* ys = h->yh + (size_t)slot * m;
+  const float* gp = h->gh + (size_t)prev * m;
+  const float* yp = h->yh + (size_t)prev * m;
+  double dg2 = 0.0, dy2 = 0.0;
+  if (t > 0) {
+    for (int i = 0; i < m; ++i) {
+      const float g = grad_host[i], yv = h->y[i];
+      const float dg = gp[i] - g, dy = yp[i] - yv;
+      dg2 += (double)dg * (double)dg;
+      dy2 += (double)dy * (double)dy;
+      gs[i] = g;
+      ys[i] = yv;
+    }
+    h->ratios[(t - 1) % (H - 1)] = (float)sqrt(dg2) / (float)sqrt(dy2);
+  } else {
+    memcpy(gs, grad_host, sizeof(float) * m);
+    memcpy(ys, h->y, sizeof(float) * m);
+  }
+  const long long n_pairs = t < (long long)(H - 1) ? t : (long long)(H - 1);
+  double step = h->init_step;
+  if (n_pairs >= H - 1) {
+    const long long j0 = t - (H - 1);
+    float lmax = h->ratios[j0 % (H - 1)];
+    for (long long j = j0 + 1; j < t; ++j) {
+      const float v = h->ratios[j % (H - 1)];
+      if (v > lmax) lmax = v;
+    }
+    if (!(isnan(lmax) || isinf(lmax))) {
+      const double cand = (lmax != 0.f) ? 1.0 / (double)lmax : h->max_step;
+      step = cand < h->max_step ? cand : h->max_step;
+    }
+  }
+  if (decay_now) h->max_step = step * decay_factor;
+  h->pushes = t + 1;
+  const float step32 = (float)step, omb = 1.0f - beta;
+  for (int i = 0; i < m; ++i) {
+    float yn = h->x[i] + grad_host[i] * step32;
+    if (!(h->eqmask && h->eqmask[i])) yn = yn > 0.f ? yn : 0.f;
+    const float a = yn * omb, b = h->y[i] * beta;
+    h->x[i] = a + b;
+    h->y[i] = yn;
+  }
+  if (step_out) *step_out = step;
+  return DUALIP_OK;
+}
+
 int dualip_agd_read_log(dualip_agd* a, int32_t count, double* dual_obj_host, double* step_host, void* stream) {
   if (!a || count < 0 || count > a->log_cap) {
     set_error("bad log range");

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Callable, Optional
 
 import torch
@@ -161,6 +162,67 @@ class AcceleratedGradientDescent:
 
     # -- generic host-driven loop (user objectives, CPU tensors) -------------------------------------------
     def _maximize_generic(self, f, initial_value: torch.Tensor, rank: int) -> SolverResult:
+        distributed = dist.is_available() and dist.is_initialized()
+        everyone = bool(getattr(f, "result_on_all_ranks", False))
+        if (isinstance(initial_value, torch.Tensor) and initial_value.device.type == "cpu" and initial_value.dtype == torch.float32
+                and initial_value.dim() == 1 and (everyone or not distributed) and os.environ.get("DUALIP_HOST_STEP", "native") != "torch"):
+            return self._maximize_host_native(f, initial_value, rank)
+        return self._maximize_host_torch(f, initial_value, rank)
+
+    def _maximize_host_native(self, f, initial_value: torch.Tensor, rank: int) -> SolverResult:
+        """Host-driven loop with the update done by dualip_agd_host_step (one native call per iteration): float32 CPU
+        iterates, any objective with `calculate` / `equality_mask`.  The evaluation point handed to `f.calculate` is a view
+        of the optimizer's (pinned) host buffer."""
+        import numpy as np
+
+        lib = _native.lib()
+        m = initial_value.numel()
+        init = initial_value.detach().contiguous()
+        eq = f.equality_mask
+        eq_u8 = eq.detach().to(device="cpu", dtype=torch.uint8).contiguous() if eq is not None else None
+        handle = ctypes.c_void_p()
+        _native.check(lib.dualip_agd_host_create(ctypes.byref(handle), m, init.data_ptr(), eq_u8.data_ptr() if eq_u8 is not None else None,
+                                                 float(self.initial_step_size), float(self.max_step_size), 15), "dualip_agd_host_create")
+        try:
+            def view(ptr):
+                return torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)), shape=(m,)))
+
+            x, y = view(lib.dualip_agd_host_x(handle)), view(lib.dualip_agd_host_y(handle))
+            beta = self.beta_seq.tolist()
+            decay = self.gamma is not None and self.gamma_decay_type is not None
+            if decay and self.gamma_decay_type != "step":
+                raise ValueError(f"Unsupported gamma decay type: {self.gamma_decay_type}")
+            dual_obj_log, step_size_log = [], []
+            step = ctypes.c_double(0.0)
+            dual_obj, objective_result = 0.0, None
+            for i in range(1, self.max_iter + 1):
+                kwargs = {"gamma": self.gamma} if self.gamma is not None else {}
+                if i == self.max_iter and self.save_primal:
+                    kwargs["save_primal"] = self.save_primal
+                objective_result = f.calculate(dual_val=x, rank=rank, **kwargs)
+                if rank == 0:
+                    self.iteration_callback(i, objective_result)
+                dual_obj = float(objective_result.dual_objective)
+                dual_obj_log.append(dual_obj)
+                grad = objective_result.dual_gradient
+                if grad.device.type != "cpu" or grad.dtype != torch.float32 or not grad.is_contiguous():
+                    grad = grad.detach().to(device="cpu", dtype=torch.float32).contiguous()
+                decay_now, factor = 0, 1.0
+                if decay and i % self.gamma_decay_params["decay_steps"] == 0:
+                    decay_now, factor = 1, float(self.gamma_decay_params["decay_factor"])
+                _native.check(lib.dualip_agd_host_step(handle, grad.data_ptr(), float(beta[i - 1]), decay_now, factor,
+                                                       ctypes.byref(step)), "dualip_agd_host_step")
+                step_size_log.append(step.value)
+                if decay_now:  # agd.py:102-109
+                    self.gamma = self.gamma * factor
+                    self.max_step_size = step.value * factor
+            return SolverResult(dual_val=y.clone(), dual_objective=dual_obj, objective_result=objective_result,
+                                dual_objective_log=dual_obj_log, step_size_log=step_size_log)
+        finally:
+            lib.dualip_agd_host_destroy(handle)
+
+    def _maximize_host_torch(self, f, initial_value: torch.Tensor, rank: int) -> SolverResult:
+        """The reference's loop op for op (any device / dtype; rank-0 update + broadcasts for reference-style objectives)."""
         grad_history, dual_history, lipschitz_cache = [], [], []
         dual_obj_log, step_size_log = [], []
         x = initial_value.clone()

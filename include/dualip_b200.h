@@ -220,6 +220,19 @@ int dualip_agd_step_peer(dualip_agd* agd, dualip_peer* peer, const float* b_dev,
                          dualip_scalars* scalars_out_dev, float beta, int32_t decay_now, double decay_factor,
                          int32_t iter_index, void* stream);
 
+/* ---- host-resident twin of the Maximizer state: for callers that keep the dual iterate in host memory and hand it to
+ * dualip_matching_calc_host every iteration (the host-buffer path).  Same update as dualip_agd_step (agd.py:163-187,
+ * agd_utils.py:4-89) in one call instead of ~25 tensor operations; needs no GPU.  x (the evaluation point) lives in
+ * pinned memory when a CUDA device is present. */
+typedef struct dualip_agd_host dualip_agd_host;
+int dualip_agd_host_create(dualip_agd_host** out, int32_t m, const float* initial_host, const uint8_t* equality_mask_host,
+                           double initial_step_size, double max_step_size, int32_t history_len /* 15, <= 64 */);
+void dualip_agd_host_destroy(dualip_agd_host* agd);
+float* dualip_agd_host_x(dualip_agd_host* agd);
+float* dualip_agd_host_y(dualip_agd_host* agd);
+int dualip_agd_host_step(dualip_agd_host* agd, const float* grad_host, float beta, int32_t decay_now, double decay_factor,
+                         double* step_out);
+
 /* Copies log entries [0,count) to host: dual_objective and step size per iteration. Synchronises. */
 int dualip_agd_read_log(dualip_agd* agd, int32_t count, double* dual_obj_host, double* step_host, void* stream);
 int dualip_agd_reserve_log(dualip_agd* agd, int32_t capacity);

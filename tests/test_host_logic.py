@@ -145,6 +145,51 @@ def test_agd_known_answers_on_cpu_objective():
     assert abs(float(one.maximize(_Quadratic2D(), torch.tensor([0.0, 0.0])).dual_val[0]) - 0.6) < 1e-6
 
 
+
+class _RandomConcave:
+    """Concave quadratic with a fixed random curvature; rows 0..4 are equalities (free multipliers)."""
+
+    def __init__(self, m=300):
+        g = torch.Generator().manual_seed(5)
+        self.q = torch.rand(m, generator=g) * 40 + 0.5
+        self.t = torch.randn(m, generator=g)
+        self.equality_mask = torch.zeros(m, dtype=torch.bool)
+        self.equality_mask[:5] = True
+
+    def calculate(self, dual_val, gamma=None, **kwargs):
+        scale = 1.0 if gamma is None else gamma / 1e-2
+        d = dual_val - self.t
+        return ObjectiveResult(dual_gradient=-(self.q * d) * scale, dual_objective=-0.5 * (self.q * d * d).sum() * scale)
+
+
+@pytest.mark.parametrize("decay", [False, True])
+def test_native_host_step_matches_reference_style_loop(decay, monkeypatch):
+    """dualip_agd_host_step (one native call per iteration) against the reference's tensor-op loop and the numpy oracle:
+    history ring, first-14-iterations rule, step cap on gamma decay, equality rows, momentum."""
+    f = _RandomConcave()
+    kw = dict(gamma_decay_type="step", gamma_decay_params={"decay_steps": 7, "decay_factor": 0.5}) if decay else {}
+    runs = {}
+    for mode in ("native", "torch"):
+        monkeypatch.setenv("DUALIP_HOST_STEP", mode)
+        solver = AcceleratedGradientDescent(max_iter=45, gamma=1e-2, initial_step_size=1e-3, max_step_size=0.1,
+                                            iteration_callback=lambda i, r: None, **kw)
+        runs[mode] = (solver.maximize(f, torch.zeros(300)), solver.gamma, solver.max_step_size)
+    (a, ga, ma), (b, gb, mb) = runs["native"], runs["torch"]
+    assert ga == gb and abs(ma - mb) <= 1e-6 * mb
+    assert np.allclose(a.step_size_log, b.step_size_log, rtol=1e-5)
+    assert np.allclose(a.dual_objective_log, b.dual_objective_log, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(a.dual_val, b.dual_val, rtol=1e-4, atol=1e-5)
+    assert bool((a.dual_val[5:] >= 0).all()) and bool((a.dual_val[:5] < 0).any())  # equality rows stay free
+
+    def calc(lam, g):
+        r = f.calculate(torch.from_numpy(lam), gamma=g)
+        return r.dual_gradient.numpy(), np.float32(r.dual_objective)
+
+    y, obj_log, step_log, _ = O.agd_maximize(calc, np.zeros(300, np.float32), 45, 1e-2, 1e-3, 0.1,
+                                             equality_mask=f.equality_mask.numpy(), **kw)
+    assert np.allclose(a.step_size_log, step_log, rtol=1e-5) and np.allclose(a.dual_val.numpy(), y, rtol=1e-4, atol=1e-5)
+
+
 def test_beta_sequence_and_cone_projection():
     s = AcceleratedGradientDescent(max_iter=50, gamma=1e-3)
     assert np.array_equal(s.beta_seq.numpy(), O.compute_beta_seq(50))
