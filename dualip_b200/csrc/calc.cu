@@ -1846,10 +1846,10 @@ int dualip_plan_info(const dualip_plan* p, int64_t* out, int cap) {
     set_error("null argument");
     return DUALIP_EINVAL;
   }
-  const int64_t v[15] = {p->n_slabs, p->n_long, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
+  const int64_t v[16] = {p->n_slabs, p->n_long, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
                          p->smode,   p->rows32 * kSlabW, (p->n_long > 0) ? 2 : 1, (int64_t)p->owned_bytes, p->n_short, p->nnz,
-                         p->fixed_point, p->fx_bits, (int64_t)(p->fx_relerr * 1e12)};
-  for (int i = 0; i < cap && i < 15; ++i) out[i] = v[i];
+                         p->fixed_point, p->fx_bits, (int64_t)(p->fx_relerr * 1e12), p->stage};
+  for (int i = 0; i < cap && i < 16; ++i) out[i] = v[i];
   return DUALIP_OK;
 }
 

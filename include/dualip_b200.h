@@ -101,7 +101,8 @@ void dualip_plan_destroy(dualip_plan* plan);
  * [6] smem mode (0: lambda+grad in smem, 1: grad in smem, 2: neither) [7] stored slab elements (incl. padding)
  * [8] kernel launches per calc  [9] plan-owned device bytes [10] columns stored in slabs [11] nnz
  * [12] 1 if the gradient is accumulated in 32-bit fixed point (deterministic), 0 for fp32 atomics
- * [13] F: fixed-point fraction bits (value * 2^F)  [14] worst-row rounding-error estimate * 1e12 */
+ * [13] F: fixed-point fraction bits (value * 2^F)  [14] worst-row rounding-error estimate * 1e12
+ * [15] longest column whose slab is staged through shared memory by the TMA engine (0: plain vector loads) */
 int dualip_plan_info(const dualip_plan* plan, int64_t* out, int cap);
 
 /* One evaluation of the dual at lambda on this shard, epilogue included (single device).

@@ -130,3 +130,23 @@ def test_fixed_point_gradient_is_reproducible_and_agrees_with_fp32_atomics(big, 
     cone = MatchingSolverDualObjectiveFunction(
         MatchingInputArgs(big["A"], big["C"], create_projection_map("cone", {"lower": 0.0}, big["n"]), big["b"]), gamma=1e-3)
     assert cone.plan_info()["fixed_point"] == 0
+
+
+@pytest.mark.parametrize("stage", [20, 12, 7])
+def test_tma_staged_slabs_are_bit_identical_to_plain_loads(big, monkeypatch, stage):
+    """Staging (per-warp shared-memory buffer filled by cp.async.bulk while the previous slab is processed) only changes how
+    a slab reaches the registers: x and the fixed-point gradient must not change by a bit, whatever mix of staged and
+    unstaged slabs a warp sees (the degrees move the boundary through the column-length range)."""
+    lam = torch.rand(big["m"], device=DEV) * 40
+    monkeypatch.setenv("DUALIP_STAGE", "0")
+    plain = _objective(big)
+    assert plain.plan_info()["staged_degree"] == 0
+    r0 = plain.calculate(lam, save_primal=True)
+    monkeypatch.setenv("DUALIP_STAGE", str(stage))
+    staged = _objective(big)
+    assert staged.plan_info()["staged_degree"] == stage
+    for _ in range(2):
+        r1 = staged.calculate(lam, save_primal=True)
+        assert torch.equal(r1.primal_var, r0.primal_var)
+        assert torch.equal(r1.dual_gradient, r0.dual_gradient)
+        assert abs(float(r1.scalars64[0]) - float(r0.scalars64[0])) <= 1e-9 * abs(float(r0.scalars64[0]))
