@@ -253,7 +253,8 @@ struct PeerArgs {
   unsigned long long seq;  // number of this step (1, 2, ...): the flag value, and seq & 1 the slot
   size_t slot_bytes;
   unsigned long long timeout_ns;
-  float* sum;   // local m+2 floats: the reduced packed sums
+  unsigned int* ticket;  // local word, 0 between steps: which CTA of the step kernel finishes last
+  float* sum;   // local m+2 floats (padded to a multiple of 4): the reduced packed sums
   int* status;  // local word: set to 1 when a wait timed out
 };
 
@@ -276,58 +277,79 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
-// One CTA.  Arrive at every peer, wait for every peer, sum the W slots in rank order (identical on all ranks), then the
-// sharded step.  The partial sums of this rank were written by the preceding kernel on the same stream.
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+// ceil((m+2) / 4096) CTAs of 1024 threads.  CTA 0 tells every peer that this rank's partial sums (written by the preceding
+// kernel on the same stream) are in their slot; every CTA waits until all peers have said the same, then each thread
+// fetches ONE float4 from every rank's slot -- all W loads in flight together, a single NVLink round trip -- and adds
+// them in rank order, so that every rank computes bit-identical sums.  The CTA that finishes last (atomic ticket) runs the
+// objective's tail and the accelerated update on the reduced vector.
 __global__ void __launch_bounds__(1024) agd_step_peer_kernel(const AgdStepArgs A, const PeerArgs P) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
   const int m2 = A.m + 2;
   if (tid < P.world) {
-    __threadfence_system();
-    // flags[r] of rank t's window is written by rank r only
-    st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.win[tid]) + P.rank, P.seq);
+    // flags[r] of rank t's window is written by rank r only; the release makes the slot visible before the flag
+    if (blockIdx.x == 0) st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.win[tid]) + P.rank, P.seq);
     const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(P.win[P.rank]) + tid;
     const unsigned long long t0 = global_timer_ns();
-    while (ld_acquire_sys_u64(mine) < P.seq) {
+    while (ld_relaxed_sys_u64(mine) < P.seq) {
       if (global_timer_ns() - t0 > P.timeout_ns) {
         *P.status = 1;
         break;
       }
-      __nanosleep(64);
     }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");  // the peers' slots are read after their flags
   }
   __syncthreads();
   const size_t slot_off = (size_t)kPeerFlagBytes + (size_t)(P.seq & 1ull) * P.slot_bytes;
-  for (int base = tid; base < m2; base += 4 * nt) {
-    // every load of the round (W peers x 4 elements) is issued before the first use: one NVLink round trip per round
-    float v[DUALIP_PEER_MAX_WORLD][4];
+  const int i4 = (blockIdx.x * 1024 + tid) * 4;  // slots are padded to 128 bytes: a float4 never leaves the slot
+  if (i4 < m2) {
+    float4 v[DUALIP_PEER_MAX_WORLD];
 #pragma unroll
-    for (int r = 0; r < DUALIP_PEER_MAX_WORLD; ++r) {
+    for (int r = 0; r < DUALIP_PEER_MAX_WORLD; ++r)
+      if (r < P.world) v[r] = ld_relaxed_sys_f4(reinterpret_cast<const float*>(P.win[r] + slot_off) + i4);
+    float4 acc = v[0];
+#pragma unroll
+    for (int r = 1; r < DUALIP_PEER_MAX_WORLD; ++r) {
       if (r < P.world) {
-        const float* slot = reinterpret_cast<const float*>(P.win[r] + slot_off);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = base + u * nt;
-          v[r][u] = i < m2 ? ld_relaxed_sys_f32(slot + i) : 0.f;
-        }
+        acc.x = __fadd_rn(acc.x, v[r].x);
+        acc.y = __fadd_rn(acc.y, v[r].y);
+        acc.z = __fadd_rn(acc.z, v[r].z);
+        acc.w = __fadd_rn(acc.w, v[r].w);
       }
     }
-    float acc[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] = v[0][u];
-#pragma unroll
-    for (int r = 1; r < DUALIP_PEER_MAX_WORLD; ++r) {  // rank order: every rank adds the same numbers in the same order
-      if (r < P.world) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = __fadd_rn(acc[u], v[r][u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = base + u * nt;
-      if (i < m2) P.sum[i] = acc[u];
+    if (i4 + 3 < m2) {
+      *reinterpret_cast<float4*>(P.sum + i4) = acc;
+    } else {
+      P.sum[i4] = acc.x;
+      if (i4 + 1 < m2) P.sum[i4 + 1] = acc.y;
+      if (i4 + 2 < m2) P.sum[i4 + 2] = acc.z;
     }
   }
-  __syncthreads();  // P.sum is read below by other threads of this CTA
+  if (gridDim.x > 1) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int ticket = atomicAdd(P.ticket, 1u);
+      s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+      if (s_last) *P.ticket = 0u;  // ready for the next step
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+  } else {
+    __syncthreads();  // P.sum is read below by other threads of this CTA
+  }
   agd_step_body<true>(A);
 }
 
@@ -507,7 +529,7 @@ struct dualip_peer {
   bool opened[DUALIP_PEER_MAX_WORLD] = {};            // mapped with cudaIpcOpenMemHandle
   bool connected = false;
   float* sum = nullptr;
-  int* status = nullptr;
+  int* status = nullptr;  // [0] status, [1] ticket of the step kernel
   unsigned long long seq = 0;  // steps taken
   unsigned long long timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;  // DUALIP_PEER_TIMEOUT_MS overrides
 };
@@ -548,9 +570,9 @@ int dualip_peer_create(dualip_peer** out, int32_t m, int32_t rank, int32_t world
   p->window_bytes = kPeerFlagBytes + 2 * p->slot_bytes;
   cudaError_t e = cudaMalloc(&p->window, p->window_bytes);
   if (e == cudaSuccess) e = cudaMemset(p->window, 0, p->window_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&p->sum, sizeof(float) * (m + 2));
-  if (e == cudaSuccess) e = cudaMalloc(&p->status, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemset(p->status, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&p->sum, sizeof(float) * (m + 8));
+  if (e == cudaSuccess) e = cudaMalloc(&p->status, 2 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(p->status, 0, 2 * sizeof(int));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     set_error("allocating the exchange window failed: %s", cudaGetErrorString(e));
@@ -652,7 +674,9 @@ int dualip_agd_step_peer(dualip_agd* a, dualip_peer* p, const float* b_dev, doub
   P.timeout_ns = p->timeout_ns;
   P.sum = p->sum;
   P.status = p->status;
-  agd_step_peer_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+  P.ticket = reinterpret_cast<unsigned int*>(p->status + 1);
+  const int n_ctas = (a->m + 2 + 4095) / 4096;
+  agd_step_peer_kernel<<<n_ctas, 1024, 0, (cudaStream_t)stream>>>(
       step_args(a, p->sum, nullptr, beta, decay_now, decay_factor, iter_index, b_dev, gamma, grad_out_dev, scalars_out_dev), P);
   DUALIP_CUDA_TRY(cudaGetLastError());
   return DUALIP_OK;

@@ -47,11 +47,13 @@ class _Rank:
         return y
 
 
-@pytest.mark.parametrize("world", [1, 2, 3])
-def test_peer_step_matches_summed_partials(world, monkeypatch):
+@pytest.mark.parametrize("world,n_rows", [(1, 96), (2, 96), (3, 96), (2, 9001), (3, 4095)])
+def test_peer_step_matches_summed_partials(world, n_rows, monkeypatch):
+    """n_rows 9001 / 4095: the update kernel runs as 3 / 2 CTAs (one float4 per thread and peer), the last one to finish
+    takes the step; 96: a single CTA."""
     monkeypatch.setenv("DUALIP_PEER_TIMEOUT_MS", "3000")
     lib = _native.lib()
-    p = random_problem(23, 6001, 96, 8.0, scale_c=10.0, lam_scale=0.5)
+    p = random_problem(23, 6001 if n_rows == 96 else 30011, n_rows, 8.0, scale_c=10.0, lam_scale=0.5)
     n, m, gamma, iters = p["n_cols"], p["n_rows"], 2e-2, 40
     A, C = _csc(p)
     b = torch.from_numpy(p["b"]).to(DEV)
