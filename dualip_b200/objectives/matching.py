@@ -45,7 +45,47 @@ def _indices_to_device(indices, device) -> torch.Tensor:
     return torch.as_tensor(np.asarray(indices, dtype=np.int64), device=device)
 
 
-def _build_class_table(ccol: torch.Tensor, n_cols: int, projection_map, batching: bool):
+class _BlockEntry:
+    """A projection entry the fused kernel does not implement (a user-registered operator): its columns are projected
+    through zero-padded [L x K] blocks, bucketed by column length exactly like the reference (matching.py:87-114,
+    utils/sparse_utils.py:133-220).  Index tensors are built once."""
+
+    def __init__(self, key, entry, cols: torch.Tensor, ccol: torch.Tensor, n_rows: int, batching: bool):
+        self.key, self.proj_type, self.proj_params = key, entry.proj_type, entry.proj_params
+        device = ccol.device
+        lengths_all = ccol[1:] - ccol[:-1]
+        if batching:
+            thresholds, i = [0], 1
+            while 2**i <= n_rows:
+                thresholds.append(2**i)
+                i += 1
+            thresholds.append(n_rows + 1)
+            ids = torch.bucketize(lengths_all[cols], torch.tensor(thresholds, dtype=lengths_all.dtype, device=device))
+            groups = [cols[ids == j] for j in range(1, len(thresholds))]
+        else:
+            groups = [cols]
+        self.buckets = []  # (offset into this entry's entry list, count, idx_in_col, cols_rep, L, K)
+        flat, offset = [], 0
+        for g in groups:
+            K = g.numel()
+            if K == 0:
+                continue
+            starts = ccol[g]
+            lengths = ccol[g + 1] - starts
+            total = int(lengths.sum().item())
+            if total == 0:
+                continue
+            L = int(lengths.max().item())
+            cols_rep = torch.arange(K, device=device).repeat_interleave(lengths)
+            prefix = lengths.cumsum(0) - lengths
+            idx_in_col = torch.arange(total, device=device) - prefix[cols_rep]
+            flat.append(starts[cols_rep] + idx_in_col)
+            self.buckets.append((offset, total, idx_in_col, cols_rep, L, K))
+            offset += total
+        self.entries = torch.cat(flat) if flat else torch.zeros(0, dtype=torch.int64, device=device)
+
+
+def _build_class_table(ccol: torch.Tensor, n_cols: int, projection_map, batching: bool, n_rows: int = 0, block_entries=None):
     """Turns the reference's projection_map (dict of ProjectionEntry) into the C-ABI class table and a per-column
     class id.  Returns (classes ctypes array, n_classes, col_class uint8 tensor or None when one entry covers all).
 
@@ -71,8 +111,16 @@ def _build_class_table(ccol: torch.Tensor, n_cols: int, projection_map, batching
         col_class = torch.zeros(n_cols, dtype=torch.uint8, device=device)
     for key, entry in entries:
         op = project(entry.proj_type, **entry.proj_params)  # raises ValueError for unknown names, like the reference
-        cls = op.native_class()
+        cls = op.native_class() if hasattr(op, "native_class") else None
         idx = None if single_full else _indices_to_device(entry.indices, device)
+        if cls is None:
+            # not implemented by the fused kernel: its columns produce x = 0 there (clamp to [0, 0]) and are projected
+            # through padded blocks by the objective (_BlockEntry)
+            if block_entries is None:
+                raise ValueError(f"projection '{entry.proj_type}' has no native class")
+            cols = torch.arange(n_cols, dtype=torch.int64, device=device) if idx is None else idx
+            block_entries.append(_BlockEntry(key, entry, cols, ccol, n_rows, batching))
+            cls = _native.ProjClass(_native.PROJ_CLAMP, 0.0, 0.0, 1.0, 1.0, 0)
         if idx is not None and idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= n_cols):
             raise IndexError(f"projection entry '{key}' names a column outside [0, {n_cols})")
         if cls.kind != _native.PROJ_CLAMP:
@@ -138,7 +186,14 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
         self._a_vals = A.values().contiguous()
         self._c_vals = c.values().contiguous()
         self.nnz = int(self._a_vals.numel())
-        classes, n_classes, col_class = _build_class_table(ccol, self.n, self.projection_map, batching)
+        self._block_entries = []
+        classes, n_classes, col_class = _build_class_table(ccol, self.n, self.projection_map, batching, self.m,
+                                                           self._block_entries)
+        if self._block_entries:
+            ec = torch.cat([e.entries for e in self._block_entries])
+            self._blk_idx = ec
+            self._blk_a, self._blk_c = self._a_vals[ec], self._c_vals[ec]
+            self._blk_row = row[ec].to(torch.int64)
         self._classes = classes
         desc = _native.CscDesc(
             n_cols=self.n, nnz=self.nnz, n_rows=self.m, index_bits=32 if ccol.dtype == torch.int32 else 64,
@@ -196,6 +251,35 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
                                                    self._stream())
         _native.check(rc, "dualip_matching_partial")
 
+    @property
+    def has_block_entries(self) -> bool:
+        return bool(self._block_entries)
+
+    def add_block_entries(self, lam: torch.Tensor, gamma: float, partial: torch.Tensor, x_out: Optional[torch.Tensor] = None) -> None:
+        """Adds the columns of user-registered projections to the packed partial sums [sum_j a_rj x_rj (m) | c.x | ||x||^2]
+        that dualip_matching_partial produced for the natively projected columns: v = -(a*lambda + c)/gamma on their
+        entries (same rounding as the kernel and the reference, matching.py:130-142), the operator on zero-padded blocks
+        per length bucket (matching.py:145-150; a new operator object per call, like the reference), row sums
+        (matching.py:153) and the two scalars."""
+        s32 = torch.tensor(-1.0 / gamma, dtype=torch.float32, device=self.device)
+        lam_s = lam * s32
+        v = self._blk_a * lam_s[self._blk_row] + self._blk_c * s32
+        x = torch.empty_like(v)
+        base = 0
+        for ent in self._block_entries:
+            fn = project(ent.proj_type, **ent.proj_params)
+            for off, total, idx_in_col, cols_rep, L, K in ent.buckets:
+                block = torch.zeros((L, K), dtype=torch.float32, device=self.device)
+                block[idx_in_col, cols_rep] = v[base + off: base + off + total]
+                out = fn(block)
+                x[base + off: base + off + total] = out[idx_in_col, cols_rep]
+            base += ent.entries.numel()
+        partial[: self.m].index_add_(0, self._blk_row, self._blk_a * x)
+        partial[self.m] += torch.dot(self._blk_c, x)
+        partial[self.m + 1] += torch.dot(x, x)
+        if x_out is not None:
+            x_out[self._blk_idx] = x
+
     def _check_dual(self, dual_val: torch.Tensor) -> torch.Tensor:
         if dual_val.device != self.device:
             raise RuntimeError(f"dual_val is on {dual_val.device}, objective on {self.device}")
@@ -235,6 +319,9 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
         if isinstance(dual_val, torch.Tensor) and dual_val.device.type == "cpu":
             if save_primal or kwargs.get("diagnostics"):
                 raise ValueError("save_primal / diagnostics need a device-resident dual_val")
+            if self._block_entries:
+                r = self.calculate(dual_val.to(self.device), gamma=None, save_primal=False)
+                return _host_result(r.dual_gradient.cpu(), r.scalars64.cpu(), self.is_distributed)
             return self._calculate_host(dual_val)
         lam = self._check_dual(dual_val)
         with torch.cuda.device(self.device):
@@ -244,8 +331,19 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
             diag = None
             if kwargs.get("diagnostics"):
                 diag = torch.full((self.nnz,), 255, dtype=torch.uint8, device=self.device)
-            self.launch_calc(lam.data_ptr(), self.gamma, grad.data_ptr(), scal.data_ptr(),
-                             x.data_ptr() if x is not None else None, diag.data_ptr() if diag is not None else None)
+            if self._block_entries:
+                # natively projected columns in the fused kernel, the others through padded blocks, then the m-length tail
+                partial = torch.empty(self.m + 2, dtype=torch.float32, device=self.device)
+                self.launch_partial(lam.data_ptr(), self.gamma, partial.data_ptr(), x.data_ptr() if x is not None else None,
+                                    diag.data_ptr() if diag is not None else None)
+                self.add_block_entries(lam, self.gamma, partial, x)
+                rc = _native.lib().dualip_matching_epilogue(
+                    partial.data_ptr(), self.m, lam.data_ptr(), self.b_vec.data_ptr() if self.b_vec is not None else None,
+                    float(self.gamma), grad.data_ptr(), scal.data_ptr(), self._stream())
+                _native.check(rc, "dualip_matching_epilogue")
+            else:
+                self.launch_calc(lam.data_ptr(), self.gamma, grad.data_ptr(), scal.data_ptr(),
+                                 x.data_ptr() if x is not None else None, diag.data_ptr() if diag is not None else None)
             s32 = scal.to(torch.float32)
         if not self.is_distributed:
             res = ObjectiveResult(
@@ -330,14 +428,18 @@ class MatchingSolverDualObjectiveFunctionDistributed(BaseObjective):
             from dualip_b200.utils.peer_exchange import PeerExchange
 
             self._peer_tried = True
-            self._peer = PeerExchange.over_process_group(self.m, self.device)
+            # COLLECTIVE even when this rank cannot take part, so that every rank reaches the same decision
+            want = not self.local_objective.has_block_entries  # block entries add their sums with tensor ops
+            self._peer = PeerExchange.over_process_group(self.m, self.device, enabled=want)
         return self._peer
 
     def host_io_bytes(self) -> tuple:
         return 4 * self.m, 4 * self.m + 8 * len(_native.SCALAR_FIELDS)
 
-    def launch_partial_and_reduce(self, lam_ptr: int, gamma: float, partial: torch.Tensor) -> None:
+    def launch_partial_and_reduce(self, lam_ptr: int, gamma: float, partial: torch.Tensor, lam: Optional[torch.Tensor] = None) -> None:
         self.local_objective.launch_partial(lam_ptr, gamma, partial.data_ptr())
+        if self.local_objective.has_block_entries:
+            self.local_objective.add_block_entries(lam, gamma, partial)
         reduce_partials(partial)
 
     def launch_epilogue(self, partial_ptr: int, lam_ptr: int, gamma: float, grad_ptr: int, scal_ptr: int) -> None:
@@ -366,7 +468,7 @@ class MatchingSolverDualObjectiveFunctionDistributed(BaseObjective):
             partial = torch.empty(self.m + 2, dtype=torch.float32, device=self.device)
             grad = torch.empty(self.m, dtype=torch.float32, device=self.device)
             scal = torch.empty(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=self.device)
-            self.launch_partial_and_reduce(lam.data_ptr(), self.gamma, partial)
+            self.launch_partial_and_reduce(lam.data_ptr(), self.gamma, partial, lam)
             self.launch_epilogue(partial.data_ptr(), lam.data_ptr(), self.gamma, grad.data_ptr(), scal.data_ptr())
             if host_io:
                 self._h_grad.copy_(grad, non_blocking=True)

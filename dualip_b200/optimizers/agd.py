@@ -298,7 +298,11 @@ class FusedAscentLoop:
             self.x_ptr = self.lib.dualip_agd_x(self.handle)
             self.grad = torch.empty(self.m, dtype=torch.float32, device=self.device)
             self.scal = torch.zeros(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=self.device)
-            self.partial = torch.empty(self.m + 2, dtype=torch.float32, device=self.device) if self.sharded else None
+            local = f.local_objective if self.sharded else f
+            self.block_entries = bool(getattr(local, "has_block_entries", False))  # user-registered projections
+            need_partial = self.sharded or self.block_entries
+            self.partial = torch.empty(self.m + 2, dtype=torch.float32, device=self.device) if need_partial else None
+            self._xbuf = torch.empty(self.m, dtype=torch.float32, device=self.device) if self.block_entries else None
         # sharded, no per-iteration callback: the partial sums are exchanged through peer memory inside the update kernel
         # (the choice must not depend on the rank: every rank takes the same path)
         self.peer = f.peer_exchange() if (self.sharded and not solver._user_callback_active()) else None
@@ -335,6 +339,8 @@ class FusedAscentLoop:
 
                 f.local_objective.gamma = gamma_i
                 f.local_objective.launch_partial(self.x_ptr, gamma_i, self.partial.data_ptr())
+                if self.block_entries:
+                    f.local_objective.add_block_entries(self._x_tensor(stream), gamma_i, self.partial)
                 if ev is not None:
                     ev[1].record()
                 reduce_partials(self.partial)
@@ -351,6 +357,27 @@ class FusedAscentLoop:
                         self.handle, self.partial.data_ptr(), f.b_vec.data_ptr(), float(gamma_i), self.grad.data_ptr(),
                         self.scal.data_ptr(), float(self.beta[i - 1]), decay_now, factor, i - 1, stream),
                         "dualip_agd_step_sharded")
+            elif self.block_entries:
+                # natively projected columns in the fused kernel, user-registered projections through padded blocks, then
+                # the objective's tail and the update in one launch (or epilogue -> callback -> update)
+                if last_primal:
+                    self.primal = torch.empty(f.nnz, dtype=torch.float32, device=self.device)
+                f.launch_partial(self.x_ptr, gamma_i, self.partial.data_ptr(), self.primal.data_ptr() if last_primal else None)
+                f.add_block_entries(self._x_tensor(stream), gamma_i, self.partial, self.primal if last_primal else None)
+                if ev is not None:
+                    ev[1].record()
+                b_ptr = f.b_vec.data_ptr() if f.b_vec is not None else None
+                if callback or last_primal:
+                    _native.check(self.lib.dualip_matching_epilogue(self.partial.data_ptr(), self.m, self.x_ptr, b_ptr, float(gamma_i),
+                                                                    self.grad.data_ptr(), self.scal.data_ptr(), stream))
+                    if callback:
+                        solver.iteration_callback(i, solver._view_result(self.grad, self.scal, self.primal if last_primal else None))
+                    _native.check(self.lib.dualip_agd_step(self.handle, self.grad.data_ptr(), self.scal.data_ptr(),
+                                                           float(self.beta[i - 1]), decay_now, factor, i - 1, stream), "dualip_agd_step")
+                else:
+                    _native.check(self.lib.dualip_agd_step_sharded(
+                        self.handle, self.partial.data_ptr(), b_ptr, float(gamma_i), self.grad.data_ptr(), self.scal.data_ptr(),
+                        float(self.beta[i - 1]), decay_now, factor, i - 1, stream), "dualip_agd_step_sharded")
             else:
                 if last_primal:
                     self.primal = torch.empty(getattr(f, "primal_size", f.nnz), dtype=torch.float32, device=self.device)
@@ -366,6 +393,11 @@ class FusedAscentLoop:
             if decay_now:
                 solver.gamma = solver.gamma * factor
         self.steps_done = max(self.steps_done, i)
+
+    def _x_tensor(self, stream) -> torch.Tensor:
+        """The evaluation point as a tensor (a copy of the native state's x), for the tensor-op part of block entries."""
+        _native.check(self.lib.dualip_agd_get(self.handle, self._xbuf.data_ptr(), None, stream))
+        return self._xbuf
 
     def current_dual(self) -> torch.Tensor:
         y = torch.empty(self.m, dtype=torch.float32, device=self.device)

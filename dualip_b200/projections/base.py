@@ -25,15 +25,21 @@ class ProjectionEntry:
 
 
 class ProjectionOperator(ABC):
-    """Base class for projection operators (reference projections/base.py:15-36)."""
+    """Base class for projection operators (reference projections/base.py:15-36).
+
+    Built-in operators describe themselves to the fused kernel through `native_class()`.  A user-registered operator
+    written for the reference (it overrides `__init__` and `__call__` on a zero-padded [L x K] block and knows nothing
+    about `native_class`) keeps working: its columns are routed through padded blocks on the device, the reference's
+    apply_F_to_columns scheme (utils/sparse_utils.py:133-220), see objectives/matching.py."""
 
     @abstractmethod
     def __init__(self, **params):
         pass
 
-    @abstractmethod
-    def native_class(self) -> _native.ProjClass:
-        """Row of the C-ABI class table (include/dualip_b200.h: dualip_proj_class)."""
+    def native_class(self):
+        """Row of the C-ABI class table (include/dualip_b200.h: dualip_proj_class), or None for an operator the fused
+        kernel does not implement."""
+        return None
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         """Project the columns of a zero-padded [L x K] block; does not modify x."""
@@ -43,6 +49,9 @@ class ProjectionOperator(ABC):
             raise RuntimeError("dualip_b200 projections run on CUDA tensors only (no CPU fallback)")
         if x.dtype != torch.float32:
             raise TypeError("dualip_b200 projections are float32-only")
+        cls = self.native_class()
+        if cls is None:
+            raise NotImplementedError(f"{type(self).__name__} must override __call__ (it has no native class)")
         squeeze = x.ndim == 1
         if squeeze:
             x = x.unsqueeze(1)
@@ -50,7 +59,6 @@ class ProjectionOperator(ABC):
             raise ValueError("expected a 1-D vector or an [L x K] block")
         xc = x.contiguous()
         out = torch.empty_like(xc)
-        cls = self.native_class()
         with torch.cuda.device(x.device):
             rc = _native.lib().dualip_project_block(xc.data_ptr(), out.data_ptr(), xc.shape[0], xc.shape[1],
                                                     ctypes.byref(cls), torch.cuda.current_stream().cuda_stream)

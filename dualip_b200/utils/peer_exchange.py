@@ -55,14 +55,14 @@ class PeerExchange:
             _native.check(e.lib.dualip_peer_connect_ptrs(e.handle, ptrs), "dualip_peer_connect_ptrs")
 
     @classmethod
-    def over_process_group(cls, m: int, device: torch.device, group=None) -> Optional["PeerExchange"]:
+    def over_process_group(cls, m: int, device: torch.device, group=None, enabled: bool = True) -> Optional["PeerExchange"]:
         """Collective over `group`: allocates a window per rank and maps every peer's.  Returns None (on EVERY rank) when the
         ranks are not all on one host, the world is larger than the window's flag array, DUALIP_PEER_EXCHANGE=0, or any
         rank fails to map a peer window; the caller then keeps the NCCL all-reduce."""
         if not (dist.is_available() and dist.is_initialized()):
             return None
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        want = os.environ.get("DUALIP_PEER_EXCHANGE", "1") != "0" and 1 < world <= _native.PEER_MAX_WORLD
+        want = enabled and os.environ.get("DUALIP_PEER_EXCHANGE", "1") != "0" and 1 < world <= _native.PEER_MAX_WORLD
         if dist.get_backend(group) != "nccl":
             want = False
         device = torch.device(device)

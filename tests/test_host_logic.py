@@ -287,3 +287,29 @@ def test_reference_cache_layout_shard_direct_reader(tmp_path):
         if ref_gen is not None and hasattr(ref_gen, "_load_cached_numpy"):
             got = ref_gen._load_cached_numpy(ref_gen._get_cache_key(n, m, key["target_sparsity"], torch.float32, key["seed"]), str(tmp_path))
             assert got is not None and np.array_equal(got[0], d["ccol"]) and np.array_equal(got[3], c_pos)
+
+
+@pytest.mark.parametrize("batching", [True, False])
+def test_block_entry_buckets_follow_the_reference_rule(batching):
+    """_BlockEntry (padded-block route for user-registered projections) buckets columns like matching.py:87-114:
+    thresholds {1,2},{3,4},{5..8},..., empty columns dropped, one bucket without batching."""
+    from conftest import random_csc
+    from dualip_b200.objectives.matching import _BlockEntry
+
+    rng = np.random.default_rng(3)
+    n_rows = 40
+    ccol, row = random_csc(rng, 500, n_rows, 6.0, long_cols=[(3, 33), (8, 17)])
+    cols = np.arange(0, 500, 3)
+    ent = _BlockEntry("k", ProjectionEntry("user_op", {}, cols.tolist()), torch.from_numpy(cols), torch.from_numpy(ccol), n_rows, batching)
+    ref = O.compute_buckets(ccol, n_rows, cols, batching=batching)
+    ref = [b for b in ref if np.diff(ccol)[b].sum() > 0]
+    assert len(ent.buckets) == len(ref)
+    lens = np.diff(ccol)
+    seen = []
+    for (off, total, idx_in_col, cols_rep, L, K), rb in zip(ent.buckets, ref):
+        assert K == rb.size and L == lens[rb].max() and total == lens[rb].sum()
+        e = ent.entries[off: off + total].numpy()
+        assert np.array_equal(e, ccol[rb][cols_rep.numpy()] + idx_in_col.numpy())
+        seen.append(e)
+    expect = np.concatenate([np.arange(ccol[j], ccol[j + 1]) for j in cols])
+    assert np.array_equal(np.sort(np.concatenate(seen)), np.sort(expect))
