@@ -106,6 +106,70 @@ def duchi_proj(x: np.ndarray, z: float, inequality: bool, tol: float = 1e-6):
     return w, branch, rho_out
 
 
+def bisection_proj(x: np.ndarray, z: float, inequality: bool, tol: float = 1e-6, max_iter: int = 50) -> np.ndarray:
+    """projections/simplex.py:6-123 (`_proj_via_bisection_search`) on a zero-padded [L, K] block.
+
+    Differences from duchi_proj that are part of the reference and therefore kept: no pre-clamp (negative entries count in
+    the column sum, and a column is only "feasible" if all of its entries are >= -tol, :40); the shift subtracts the
+    maximum of x/z from the un-normalised x (:86-89) and the root is searched for a sum of 1, not z (:104) -- exact for
+    z = 1 only; the search interval [-1, 0] is halved for every active column at once, so all columns stop after the
+    same number of steps (:95-118)."""
+    x = np.asarray(x)
+    dt = x.dtype
+    L, K = x.shape
+    assert z > 0, "Simplex radius z must be positive."
+    zt = dt.type(z)
+    w = np.empty_like(x)
+    todo = np.ones(K, dtype=bool)
+    if inequality:  # :39-47
+        s = np.zeros(K, dtype=dt)
+        for i in range(L):
+            s = s + x[i]
+        feasible = (s <= dt.type(float(z) + tol)) & (x >= dt.type(-tol)).all(axis=0)
+        w[:, feasible] = x[:, feasible]
+        todo = ~feasible
+    if L > 1 and todo.any():  # :52-81, top-2 shortcut on x/z
+        idx = np.nonzero(todo)[0]
+        xn = x[:, idx] / zt
+        order = np.argsort(-xn, axis=0, kind="stable")
+        top0 = np.take_along_axis(xn, order[0:1], axis=0)[0]
+        top1 = np.take_along_axis(xn, order[1:2], axis=0)[0]
+        short = (top0 - top1) > dt.type(1.0)
+        if short.any():
+            cols = idx[short]
+            sol = np.zeros((L, cols.size), dtype=dt)
+            sol[order[0, short], np.arange(cols.size)] = zt
+            w[:, cols] = sol
+            todo[cols] = False
+    if not todo.any():
+        return w
+    idx = np.nonzero(todo)[0]  # :85-122
+    sub = x[:, idx]
+    shifted = sub - (sub / zt).max(axis=0)[None, :]
+    lo = np.full(idx.size, -1.0, dtype=dt)
+    hi = np.zeros(idx.size, dtype=dt)
+    active = np.ones(idx.size, dtype=bool)
+    prev = None
+    for _ in range(max_iter):
+        if not active.any():
+            break
+        mid = (lo + hi) / dt.type(2.0)
+        if prev is not None and np.abs(mid - prev).max() < tol:
+            break
+        ssum = np.zeros(idx.size, dtype=dt)
+        t = np.maximum(shifted - mid[None, :], dt.type(0.0))
+        for i in range(L):
+            ssum = ssum + t[i]
+        high = ssum > dt.type(1.0)
+        lo = np.where(high & active, mid, lo)
+        hi = np.where(~high & active, mid, hi)
+        active = active & ~((hi - lo) < tol)
+        prev = mid.copy()
+    nu = (lo + hi) / dt.type(2.0)
+    w[:, idx] = np.maximum(shifted - nu[None, :], dt.type(0.0)) * zt
+    return w
+
+
 # --------------------------------------------------------------------------------------
 # projection map handling  (reference projections/base.py, objectives/matching.py:70-114)
 # --------------------------------------------------------------------------------------
@@ -164,12 +228,16 @@ def _apply_entry(vals: np.ndarray, ccol: np.ndarray, entry: ProjEntry, n_rows: i
         elif pt == "cone":
             out = cone_proj(block, **pp)
         elif pt in ("simplex", "simplex_eq"):
-            if pp.get("method", "duchi") != "duchi":
-                raise NotImplementedError("oracle restates the Duchi method only")
-            out, br, rh = duchi_proj(block, float(pp.get("z", 1.0)), inequality=(pt == "simplex"))
-            nz = lengths > 0
-            branch[cols[nz]] = br[nz]
-            rho[cols[nz]] = rh[nz]
+            method = pp.get("method", "duchi")
+            if method == "bisection_search":
+                out = bisection_proj(block, float(pp.get("z", 1.0)), inequality=(pt == "simplex"))
+            elif method == "duchi":
+                out, br, rh = duchi_proj(block, float(pp.get("z", 1.0)), inequality=(pt == "simplex"))
+                nz = lengths > 0
+                branch[cols[nz]] = br[nz]
+                rho[cols[nz]] = rh[nz]
+            else:
+                raise ValueError(f"Unsupported projection method: {method}")
         else:
             raise ValueError(f"Unknown projection operator '{pt}'")
         vals[flat] = out[idx_in_col, cols_rep]

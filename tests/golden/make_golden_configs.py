@@ -135,6 +135,41 @@ def make_synthetic(rng):
     return out
 
 
+def make_bisection(rng):
+    """`method="bisection_search"` (projections/simplex.py:6-123): the operator on padded blocks, and through the reference
+    objective on a small matching problem (simplex, z = 1; batching on and off: the result depends on the padding)."""
+    import torch
+    from dualip.objectives.matching import MatchingInputArgs, MatchingSolverDualObjectiveFunction
+    from dualip.projections.base import create_projection_map, project
+    from make_golden import random_csc
+
+    out = {}
+    for L, K, scale in ((1, 40, 3.0), (2, 150, 2.0), (7, 200, 1.0), (16, 200, 0.5), (33, 80, 0.3)):
+        x = ((rng.standard_normal((L, K)) + 0.3) * scale).astype(np.float32)
+        lens = rng.integers(1, L + 1, size=K)
+        for j in range(K):
+            x[lens[j]:, j] = 0.0
+        out[f"L{L}_x"] = x
+        for name in ("simplex", "simplex_eq"):
+            for z in (1.0, 2.5):
+                out[f"L{L}_{name}_z{z}"] = project(name, z=z, method="bisection_search")(torch.from_numpy(x.copy())).numpy().copy()
+    n_cols, n_rows, gamma = 1500, 48, 5e-2
+    ccol, row = random_csc(rng, n_cols, n_rows, 7.0)
+    E = row.size
+    cval = (-np.minimum(rng.lognormal(-4.0, 0.75, E) * rng.lognormal(0, 0.7, E), 0.5) * 10.0).astype(np.float32)
+    aval = (rng.lognormal(0, 1, E) * (-cval)).astype(np.float32)
+    b = (rng.uniform(0.5, 1.0, n_rows) * 0.05 * n_cols / n_rows).astype(np.float32)
+    lam = rng.random(n_rows).astype(np.float32)
+    A = torch.sparse_csc_tensor(torch.from_numpy(ccol), torch.from_numpy(row), torch.from_numpy(aval), size=(n_rows, n_cols))
+    C = torch.sparse_csc_tensor(torch.from_numpy(ccol), torch.from_numpy(row), torch.from_numpy(cval), size=(n_rows, n_cols))
+    pm = create_projection_map("simplex", {"z": 1.0, "method": "bisection_search"}, n_cols)
+    out.update(ccol=ccol, row=row, a=aval, c=cval, b=b, lam=lam, gamma=np.float64(gamma), n_rows=np.int64(n_rows))
+    for batching, tag in ((True, "b1"), (False, "b0")):
+        obj = MatchingSolverDualObjectiveFunction(MatchingInputArgs(A, C, pm, torch.from_numpy(b)), gamma=gamma, batching=batching)
+        _calc_outputs(obj, torch.from_numpy(lam), tag, out)
+    return out
+
+
 def main():
     _import_reference()
     rng = np.random.default_rng(20261017)
@@ -143,6 +178,9 @@ def main():
     print("cfg1 nnz", d["row"].size, "box obj", d["box_obj_log"][[0, -1]], "simplex obj", d["simplex_obj_log"][[0, -1]])
     d = make_synthetic(rng)
     np.savez_compressed(os.path.join(HERE, "cfg2_synthetic.npz"), **d)
+    db = make_bisection(np.random.default_rng(20261018))
+    np.savez_compressed(os.path.join(HERE, "projection_bisection.npz"), **db)
+    print("bisection: nnz", db["row"].size, "scal", db["scal_b1"][:2], db["scal_b0"][:2])
     print("cfg2 nnz", d["row"].size, "plain", d["plain_obj_log"][[0, -1]], "warm", d["warm_obj_log"][[0, -1]],
           "jacobi", d["jacobi_obj_log"][[0, -1]])
 

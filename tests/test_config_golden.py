@@ -94,3 +94,20 @@ def test_reference_generator_ascent_warm_start_and_jacobi():
     assert np.allclose(a2, d["jacobi_a"], rtol=2e-6) and np.allclose(b2, d["jacobi_b"], rtol=2e-6)
     y3, obj_log, step_log, _ = _trace(d, d["jacobi_a"], d["jacobi_b"], cls, 40)
     _check_trace(y3, obj_log, step_log, d, "jacobi", tight=26)
+
+
+def test_bisection_method_matches_reference():
+    """`method="bisection_search"` (projections/simplex.py:6-123): the numpy restatement is bit-identical to the reference on
+    padded blocks (simplex / simplex_eq, z = 1 and 2.5) and through the objective with batching on and off."""
+    d = np.load(f"{GOLDEN}/projection_bisection.npz")
+    for L in (1, 2, 7, 16, 33):
+        x = d[f"L{L}_x"]
+        for name, ineq in (("simplex", True), ("simplex_eq", False)):
+            for z in (1.0, 2.5):
+                assert np.array_equal(O.bisection_proj(x, z, ineq), d[f"L{L}_{name}_z{z}"]), (L, name, z)
+    n, m = d["ccol"].size - 1, int(d["n_rows"])
+    pm = {"k": O.ProjEntry("simplex", {"z": 1.0, "method": "bisection_search"}, np.arange(n))}
+    for batching, tag in ((True, "b1"), (False, "b0")):
+        r = O.matching_calculate(d["ccol"], d["row"], d["a"], d["c"], m, pm, d["lam"], float(d["gamma"]), d["b"], batching=batching)
+        _check_calc(r.primal_var, r.dual_gradient, r.dual_objective, d, tag)
+    assert not np.array_equal(d["x_b1"], d["x_b0"])  # the padded length is part of the reference's result

@@ -95,3 +95,31 @@ def test_reference_generator_ascent_warm_start_and_jacobi(tmp_path):
     A3, _ = _csc(dict(ccol=d["ccol"], row=d["row"], a=d["jacobi_a"], c=d["c"], n_rows=d["n_rows"]))
     y, obj_log, step_log = _solve(A3, C, pm, torch.from_numpy(d["jacobi_b"]).to(DEV), gamma, 40)
     _check_trace(y, obj_log, step_log, d, "jacobi", tight=26)
+
+
+def test_bisection_method_on_the_device():
+    """`method="bisection_search"` is not in the fused kernel: the operator runs as tensor operations on padded device blocks
+    and the objective routes its columns through them.  The bisection decisions compare a float32 column sum with 1, and
+    the device sums in a different order than the reference's CPU loop, so single decisions may flip: values agree to the
+    bisection tolerance (1e-6 on nu, times z), not to the bit."""
+    from dualip_b200.projections import project
+
+    d = np.load(f"{GOLDEN}/projection_bisection.npz")
+    for L in (1, 2, 7, 16, 33):
+        x = torch.from_numpy(d[f"L{L}_x"]).to(DEV)
+        for name in ("simplex", "simplex_eq"):
+            for z in (1.0, 2.5):
+                out = project(name, z=z, method="bisection_search")(x).cpu().numpy()
+                assert np.abs(out - d[f"L{L}_{name}_z{z}"]).max() <= 4e-6 * z, (L, name, z)
+    n, m, gamma = d["ccol"].size - 1, int(d["n_rows"]), float(d["gamma"])
+    A, C = _csc(d)
+    pm = create_projection_map("simplex", {"z": 1.0, "method": "bisection_search"}, n)
+    for batching, tag in ((True, "b1"), (False, "b0")):
+        obj = MatchingSolverDualObjectiveFunction(MatchingInputArgs(A, C, pm, torch.from_numpy(d["b"]).to(DEV)), gamma=gamma, batching=batching)
+        assert obj.has_block_entries
+        r = obj.calculate(torch.from_numpy(d["lam"]).to(DEV), save_primal=True)
+        assert np.abs(r.primal_var.cpu().numpy() - d[f"x_{tag}"]).max() <= 4e-6
+        scal, got = d[f"scal_{tag}"], r.scalars64.cpu().numpy()
+        assert abs(got[0] - scal[0]) <= 1e-5 * abs(scal[0])
+        g, ref = r.dual_gradient.cpu().numpy(), d[f"grad_{tag}"]
+        assert np.abs(g - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
