@@ -20,7 +20,7 @@ from dualip_b200.run_solver import run_solver
 from dualip_b200.types import ComputeArgs, ObjectiveArgs, ObjectiveResult, SolverArgs, SolverResult
 from dualip_b200.utils.dist_utils import global_to_local_projection_map, shard_sizes, split_tensors_to_devices
 from dualip_b200.utils.sparse_utils import split_csc_by_cols
-from conftest import GOLDEN
+from conftest import GOLDEN, random_problem
 from oracle import dualip_oracle as O
 
 
@@ -313,3 +313,41 @@ def test_block_entry_buckets_follow_the_reference_rule(batching):
         seen.append(e)
     expect = np.concatenate([np.arange(ccol[j], ccol[j + 1]) for j in cols])
     assert np.array_equal(np.sort(np.concatenate(seen)), np.sort(expect))
+
+
+def test_block_entry_partial_sums_against_oracle_on_cpu():
+    """The tensor-op half of the padded-block route (add_block_entries: v, blocks per bucket, operator, row sums, c.x, ||x||^2)
+    checked on CPU tensors against the numpy oracle, with a user-style operator that equals box[0, 0.4]."""
+    from dualip_b200.objectives.matching import _BlockEntry
+    from dualip_b200.projections.base import ProjectionOperator, register
+
+    @register("cpu_test_capped_box")
+    class _Capped(ProjectionOperator):
+        def __init__(self, upper=0.4):
+            self.upper = upper
+
+        def __call__(self, x):
+            return torch.clamp(x, min=0.0, max=self.upper)
+
+    p = random_problem(9, 800, 30, 6.0, scale_c=10.0, lam_scale=0.5)
+    n, m, gamma = p["n_cols"], p["n_rows"], 3e-2
+    ccol, row = torch.from_numpy(p["ccol"]), torch.from_numpy(p["row"])
+    a, c = torch.from_numpy(p["a"]), torch.from_numpy(p["c"])
+    cols = torch.arange(1, n, 2)
+    entry = ProjectionEntry("cpu_test_capped_box", {"upper": 0.4}, cols.tolist())
+    obj = object.__new__(MatchingSolverDualObjectiveFunction)  # only the fields add_block_entries reads
+    obj.device, obj.m = torch.device("cpu"), m
+    obj._block_entries = [_BlockEntry("k", entry, cols, ccol, m, True)]
+    ec = obj._block_entries[0].entries
+    obj._blk_idx, obj._blk_a, obj._blk_c, obj._blk_row = ec, a[ec], c[ec], row[ec]
+    partial = torch.zeros(m + 2)
+    x_out = torch.zeros(row.numel())
+    obj.add_block_entries(torch.from_numpy(p["lam"]), gamma, partial, x_out)
+    # oracle: the same columns with box[0, 0.4]; the other columns contribute nothing (clamp to [0, 0] in the kernel)
+    pm = {"u": O.ProjEntry("box", {"lower": 0.0, "upper": 0.4}, cols.numpy()),
+          "z": O.ProjEntry("box", {"lower": 0.0, "upper": 0.0}, np.arange(0, n, 2))}
+    r = O.matching_calculate(p["ccol"], p["row"], p["a"], p["c"], m, pm, p["lam"], gamma, None)
+    assert np.array_equal(x_out.numpy(), r.primal_var)
+    assert np.allclose(partial[:m].numpy(), r.dual_gradient, rtol=1e-5, atol=1e-5)
+    assert abs(float(partial[m]) - r.primal_objective) <= 1e-5 * abs(r.primal_objective)
+    assert abs(0.5 * gamma * float(partial[m + 1]) - r.reg_penalty) <= 1e-5 * abs(r.reg_penalty)
