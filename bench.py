@@ -437,8 +437,11 @@ def run_reference(args):
         "impl": "reference", "metric": "dual-ascent iterations/sec", "value": it_s_full, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 / it_s_full, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic matching LP {n} entities x {m} duals, sparsity {args.sparsity}", "workload_id": args.workload,
-                   "entities": n, "duals": m},
+        "config": {"workload": f"synthetic matching LP {args.entities} entities x {args.duals} duals, sparsity {args.sparsity}, "
+                               f"{'simplex(z=1) even / box[0,1] odd' if args.mixed else 'simplex(z=1)'}, "
+                               f"{'Jacobi precond, ' if args.jacobi else ''}Nesterov AGD, gamma={GAMMA}",
+                   "workload_id": args.workload, "entities": n, "duals": m, "nnz": int(round(e_full)),
+                   "parallelism": "host threads (CPU arm)", "sample_entities": n_s},
         "cpu_baseline": {"value": it_s_full, "unit": "iterations/s", "cores": threads, "kind": "port",
                          "sample": f"first {n_s} of {n} entities ({e_s} nnz): {it_s_sample:.3f} it/s on the sample = "
                                    f"{e_s * it_s_sample / 1e6:.1f} M nnz/s, scaled by nnz to the full problem"},
