@@ -324,15 +324,26 @@ __device__ __forceinline__ void fast_clamp(const KArgs& k, const dualip_proj_cla
   for (int q = 0; q < D; ++q) x[q] = fminf(fmaxf(x[q], lo), hi);
 }
 
+// The reference's scan over the sorted column.  Zero entries cannot satisfy cond_i once the prefix sum has reached z
+// (q_i = (css_i - z)/i >= 0 = u_(i)), and they sit at the end of the sorted order, so the scan may stop at a position where
+// no lane of the warp that needs theta has a positive entry left.  `more` carries that per lane; lanes whose column sum is
+// within rounding distance of z (css_i >= z not certain: `near`) keep the warp scanning to the end, which reproduces the
+// reference there too.  The vote is taken at two positions (about 0.6 D and 0.8 D: at late iterates the longest support
+// in a warp is about D/2), not at every step, because it costs three instructions.
 template <int D, int I>
-__device__ __forceinline__ void scan_sorted(const float (&w)[D], float z, double& acc, float& t_sel, int& rho_sel) {
+__device__ __forceinline__ void scan_sorted(const float (&w)[D], float z, double& acc, float& t_sel, int& rho_sel, bool need,
+                                            bool near) {
   if constexpr (I < D) {
+    constexpr int kStop1 = (3 * D + 4) / 5, kStop2 = (4 * D + 4) / 5;
+    if constexpr (D >= 5 && (I == kStop1 || (I == kStop2 && kStop2 != kStop1))) {
+      if (!__any_sync(0xffffffffu, need && (near || w[I] > 0.f))) return;
+    }
     acc += (double)w[I];
     const float t = __fsub_rn((float)acc, z);
     const bool cond = w[I] > div_by_int<I + 1>(t);
     t_sel = cond ? t : t_sel;
     rho_sel = cond ? (I + 1) : rho_sel;
-    scan_sorted<D, I + 1>(w, z, acc, t_sel, rho_sel);
+    scan_sorted<D, I + 1>(w, z, acc, t_sel, rho_sel, need, near);
   }
 }
 
@@ -376,7 +387,10 @@ __device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_c
     double acc = 0.0;
     float t_sel = __fsub_rn(w[0], z);
     int rho_sel = 1;  // no cond true: torch's max over an all-zero mask gives index 0
-    scan_sorted<D, 0>(w, z, acc, t_sel, rho_sel);
+    // lanes that do not need theta never hold the warp in the scan; a lane whose sum is not clearly above z (within 1e-4 z,
+    // or below it: simplex_eq) scans everything
+    const bool near = !(S > __fmul_rn(z, 1.0001f));
+    scan_sorted<D, 0>(w, z, acc, t_sel, rho_sel, need_theta, near);
     if (need_theta) {
       theta = __fdiv_rn(t_sel, (float)rho_sel);                                                     // simplex.py:228-230
       rho = rho_sel;
