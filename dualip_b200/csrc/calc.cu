@@ -52,11 +52,6 @@ constexpr uint32_t kKeyLong = (255u << kDegBits) | 2046u;
 constexpr int kKeyBits = 19;
 constexpr int kMaxClasses = 255;
 constexpr size_t kSmemBudget = 227 * 1024;
-#ifdef DUALIP_TWO_SLOT
-constexpr int kWbarBytes = 256;  // two mbarriers per warp
-#else
-constexpr int kWbarBytes = 128;  // one mbarrier per warp
-#endif
 constexpr int kThreads = 512;         // one CTA of 16 warps per SM: up to 128 registers per thread for the register path
 
 struct SlabHdr {      // 8 bytes per slab (per 32*d nonzeros)
@@ -446,9 +441,9 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   //        [s_grad m_pad floats][per-warp stash (generic path) or per-warp staging buffers (register path)]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* wbar = reinterpret_cast<uint64_t*>(smem_raw + 16);
-  dualip_proj_class* s_cls = reinterpret_cast<dualip_proj_class*>(smem_raw + 16 + kWbarBytes);
+  dualip_proj_class* s_cls = reinterpret_cast<dualip_proj_class*>(smem_raw + 16 + 128);
   const int n_cls_bytes = ((k.n_classes * (int)sizeof(dualip_proj_class)) + 15) & ~15;
-  double* dscratch = reinterpret_cast<double*>(smem_raw + 16 + kWbarBytes + n_cls_bytes);
+  double* dscratch = reinterpret_cast<double*>(smem_raw + 16 + 128 + n_cls_bytes);
   float* fscratch = reinterpret_cast<float*>(dscratch + 32);
   float* s_lam = fscratch + 32;
   const int m = k.m;
@@ -481,7 +476,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     bulk_ok = ((reinterpret_cast<uintptr_t>(k.lambda) & 15u) == 0) && bulk_bytes >= 16;
     if (tid == 0) {
       mbar_init(bar, 1);
-      for (int w = 0; w < kWbarBytes / 8; ++w) mbar_init(wbar + w, 1);
+      for (int w = 0; w < THREADS / 32; ++w) mbar_init(wbar + w, 1);
       fence_mbar_init();
     }
     __syncthreads();
@@ -516,37 +511,6 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   using RowT = typename std::conditional<ROW16, unsigned short, uint32_t>::type;
   const RowT* row_all = reinterpret_cast<const RowT*>(k.row_t);
   int64_t sl = (int64_t)blockIdx.x * NW + warp;
-#ifdef DUALIP_TWO_SLOT
-  // slab headers are fetched three slabs ahead: the header of the slab after next is needed NOW (to start its copy)
-  uint2 hnext = make_uint2(0u, 0u), hnext2 = make_uint2(0u, 0u), hnext3 = make_uint2(0u, 0u);
-  if (sl < k.n_slabs) hnext = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl);
-  if (sl + total_warps < k.n_slabs) hnext2 = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl + total_warps);
-  if (sl + 2 * total_warps < k.n_slabs) hnext3 = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl + 2 * total_warps);
-  // TMA staging (register path): a warp owns two slots and two mbarriers; slab number i of its sequence uses slot i & 1.
-  // While it works on slab i, the copies of slabs i+1 and i+2 are in flight (i+2 is issued into slab i's slot as soon as
-  // slab i sits in registers).  Slabs longer than k.stage entries per column are read with plain loads.
-  const bool use_stage = FAST && (k.stage != 0);
-  const uint32_t slot_bytes = ((uint32_t)k.stage * 320u + 127u) & ~127u;
-  unsigned char* my_stage = s_stage + (size_t)warp * 2u * slot_bytes;
-  uint64_t* my_bar = wbar + 2 * warp;
-  // bit 0/1/2: slab i / i+1 / i+2 is staged; bits 4,5: phase of slot 0,1; bit 8: i & 1
-  uint32_t pipe = 0x100u;
-  auto stage_slab = [&](const uint2 h, uint32_t slot) {  // h: header of a slab with d <= k.stage
-    if (lane == 0) {
-      const size_t nb = (size_t)h.x * kSlabW;
-      stage_issue(my_stage + slot * slot_bytes, my_bar + slot, k.a_t + nb, k.c_t + nb,
-                  reinterpret_cast<const unsigned short*>(k.row_t) + nb, (int)(h.y & 0xffffu));
-    }
-  };
-  if (use_stage && sl < k.n_slabs && (int)(hnext.y & 0xffffu) <= k.stage) {
-    stage_slab(hnext, 0u);
-    pipe |= 2u;
-  }
-  if (use_stage && sl + total_warps < k.n_slabs && (int)(hnext2.y & 0xffffu) <= k.stage) {
-    stage_slab(hnext2, 1u);
-    pipe |= 4u;
-  }
-#else
   // slab headers are fetched two slabs ahead: the next slab's header is needed NOW (to start its staging copy)
   uint2 hnext = make_uint2(0u, 0u), hnext2 = make_uint2(0u, 0u);
   if (sl < k.n_slabs) hnext = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl);
@@ -568,7 +532,6 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     stage_slab(hnext);
     cur_staged = true;
   }
-#endif
   for (; sl < k.n_slabs; sl += total_warps) {
     unsigned long long* trace = nullptr;
     if (k.timeline != nullptr && warp == 0 && lane == 0 && blockIdx.x == 0) {  // debug: per-slab trace
@@ -581,13 +544,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     }
     const uint2 hraw = hnext;
     hnext = hnext2;
-#ifdef DUALIP_TWO_SLOT
-    hnext2 = hnext3;
-    if (sl + 3 * total_warps < k.n_slabs) hnext3 = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl + 3 * total_warps);
-    pipe = ((pipe & 6u) >> 1) | (pipe & 0x30u) | ((pipe ^ 0x100u) & 0x100u);
-#else
     if (sl + 2 * total_warps < k.n_slabs) hnext2 = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl + 2 * total_warps);
-#endif
     const int d = (int)(hraw.y & 0xffffu);
     const int cls = (int)((hraw.y >> 16) & 0xffu);
     const bool active = lane < (int)(hraw.y >> 24);
@@ -616,21 +573,6 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
         }
       }
     }
-#ifdef DUALIP_TWO_SLOT
-    const uint32_t par = (pipe >> 8) & 1u;
-    const bool staged = (pipe & 1u) != 0u;
-    unsigned char* cur_buf = my_stage + par * slot_bytes;
-    uint64_t* cur_bar = my_bar + par;
-    uint32_t stage_phase = (pipe >> (4u + par)) & 1u;
-    if (staged) pipe ^= 0x10u << par;
-    auto issue_next = [&]() {  // slab i+2 goes into the slot slab i has just left
-      if (use_stage && sl + 2 * total_warps < k.n_slabs && (int)(hnext2.y & 0xffffu) <= k.stage) {
-        __syncwarp();
-        stage_slab(hnext2, par);
-        pipe |= 4u;
-      }
-    };
-#else
     const bool have_next = sl + total_warps < k.n_slabs;
     const bool next_staged = use_stage && have_next && (int)(hnext.y & 0xffffu) <= k.stage;
     const bool staged = cur_staged;
@@ -641,9 +583,6 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
         stage_slab(hnext);
       }
     };
-    unsigned char* cur_buf = my_stage;
-    uint64_t* cur_bar = my_bar;
-#endif
     if (FAST && d <= kRegDeg) {
       // ---- register path: the whole column lives in registers, code specialised on d ----
       const unsigned char* s_lam_b = reinterpret_cast<const unsigned char*>(s_lam);
@@ -652,7 +591,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
 #define DUALIP_FAST_CASE(DD)                                                                              \
   case DD:                                                                                                \
     fast_slab<DD, SMODE, ACC>(k, pc, pa, pcv, pr16, lane, active, s_lam_b, s_grad_u32, s, sl, cx, xx,    \
-                              staged, cur_buf, cur_bar, stage_phase, issue_next, trace);                 \
+                              staged, my_stage, my_bar, stage_phase, issue_next, trace);                 \
     break;
         DUALIP_FAST_CASE(1)
         DUALIP_FAST_CASE(2)
@@ -1339,7 +1278,7 @@ static SlabKernel plan_kernel(const dualip_plan* p) {
 }
 
 static size_t smem_fixed_bytes(int n_classes) {
-  return 16 + kWbarBytes + (((size_t)n_classes * sizeof(dualip_proj_class) + 15) & ~(size_t)15) + 32 * sizeof(double) + 32 * sizeof(float);
+  return 16 + 128 + (((size_t)n_classes * sizeof(dualip_proj_class) + 15) & ~(size_t)15) + 32 * sizeof(double) + 32 * sizeof(float);
 }
 
 static int launch_eval(dualip_plan* p, const float* lambda, const float* b, double gamma, float* grad_out,
@@ -1807,18 +1746,7 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   const char* env_stage = getenv("DUALIP_STAGE");
   int stage_deg = env_stage ? atoi(env_stage) : (p->nnz >= kStageMinNnz ? kRegDeg : 0);
   stage_deg = std::max(0, std::min(stage_deg, kRegDeg));
-#ifdef DUALIP_TWO_SLOT
-  // two slots per warp: the largest staged column length whose 2 x 16 slots fit beside lambda and the accumulator
-  {
-    const size_t smem_cap = std::min<size_t>(kSmemBudget, prop.sharedMemPerBlockOptin) - 1024;
-    while (stage_deg > 0 &&
-           fixed + 8 * m_pad + (size_t)(p->threads / 32) * 2 * (((size_t)stage_deg * 320 + 127) & ~(size_t)127) + 128 > smem_cap)
-      --stage_deg;
-  }
-  const size_t stage_bytes = (size_t)(p->threads / 32) * 2 * (((size_t)stage_deg * 320 + 127) & ~(size_t)127) + 128;
-#else
   const size_t stage_bytes = (size_t)(p->threads / 32) * (((size_t)stage_deg * 320 + 127) & ~(size_t)127) + 128;
-#endif
   p->row_bits = (p->m <= 65536) ? 16 : 32;
   const size_t smem_max = std::min<size_t>(kSmemBudget, prop.sharedMemPerBlockOptin) - 1024;  // static smem + slack
   const bool want_stage = stage_deg > 0;
