@@ -54,3 +54,29 @@ def test_lp_oracle_ascent_trace_matches_reference_run(name):
     # gradients): the first iterations agree to fp32 accuracy, the full trace to a few per cent of its range
     assert np.allclose(got[:12], ref[:12], rtol=1e-4, atol=1e-4 * np.abs(ref[:12]).max())
     assert np.abs(got - ref).max() <= 5e-2 * np.abs(ref).max()
+
+
+def test_reference_known_answer_equality_constrained_lp():
+    """Reference tests/test_equality_constraints.py:19-66: minimise x1 + 2 x2 s.t. x1 + x2 = 4, 0 <= x1 <= 1 (x2 unprojected),
+    gamma 1e-5, 1000 AGD iterations with the default step sizes, free multiplier on the equality row -> objective 7.0 within
+    torch.isclose(atol=1e-5) (i.e. 1e-5 + 1e-5*7).  The reference itself, run in the build container, ends at
+    7.000050067901611 with lambda = -2.  Also project_on_nn_cone with an equality mask (:8-16)."""
+    from oracle import dualip_oracle as O
+
+    y = np.array([-1.0, -1.0, 2.0, -3.0, 4.0], dtype=np.float32)
+    mask = np.array([False, True, False, True, False])
+    assert np.array_equal(O.project_on_nn_cone(y, mask), np.array([0.0, -1.0, 2.0, -3.0, 4.0], dtype=np.float32))
+
+    A = np.array([[1.0, 1.0]], dtype=np.float32)
+    c = np.array([1.0, 2.0], dtype=np.float32)
+    b = np.array([4.0], dtype=np.float32)
+    lower = np.array([0.0, -np.inf], dtype=np.float32)  # box(upper=1) on x1 has lower = 0 (projections/box.py:6-13)
+    upper = np.array([1.0, np.inf], dtype=np.float32)
+
+    def calc(lam, gamma):
+        grad, dual_obj, _, _, _ = O.lp_calculate(A, c, b, lower, upper, lam, gamma)
+        return grad, np.float32(dual_obj)
+
+    y, obj_log, _, _ = O.agd_maximize(calc, np.zeros(1, np.float32), 1000, 1e-5, equality_mask=np.array([True]))
+    assert abs(obj_log[-1] - 7.0) <= 1e-5 + 1e-5 * 7.0
+    assert abs(obj_log[-1] - 7.000050067901611) < 1e-6 and abs(float(y[0]) + 2.0) < 1e-4 and obj_log[0] == -200000.0
