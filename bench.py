@@ -230,16 +230,20 @@ def run_native(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL announces its version on stdout when the first communicator comes up; stdout carries the JSON line only
         sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
+        try:
+            saved = os.dup(1)
+            os.dup2(2, 1)
+        except OSError:
+            saved = None
         try:
             dist.init_process_group("nccl", device_id=device)
             dist.barrier()
             torch.cuda.synchronize(device)
         finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+            if saved is not None:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
     if args.gpus != world:
         log(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
 
