@@ -16,6 +16,7 @@ CASES = [
     ("test_agd.py", "", 2),        # AcceleratedGradientDescent on Python objectives, incl. the four known-answer trace values
     ("test_import.py", "", 1),
     ("test_equality_constraints.py", "test_project_on_nn_cone", 1),
+    ("preprocessing/test_input_validation.py", "", None),  # vectorised checks, same errors as the reference's per-column loop
 ]
 
 
@@ -30,4 +31,6 @@ def test_reference_test_module_passes_against_this_package(module, select, expec
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=os.path.join(HERE, "dropin"), timeout=600)
     tail = res.stdout[-1500:] + res.stderr[-1500:]
     assert res.returncode == 0, tail
-    assert f"{expected} passed" in res.stdout, tail
+    assert " passed" in res.stdout and "failed" not in res.stdout, tail
+    if expected is not None:
+        assert f"{expected} passed" in res.stdout, tail
