@@ -62,9 +62,9 @@ class PeerExchange:
         if not (dist.is_available() and dist.is_initialized()):
             return None
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        want = enabled and os.environ.get("DUALIP_PEER_EXCHANGE", "1") != "0" and 1 < world <= _native.PEER_MAX_WORLD
-        if dist.get_backend(group) != "nccl":
-            want = False
+        if world < 2 or world > _native.PEER_MAX_WORLD or dist.get_backend(group) != "nccl":
+            return None  # the same on every rank: no need to agree on it
+        want = enabled and os.environ.get("DUALIP_PEER_EXCHANGE", "1") != "0"
         device = torch.device(device)
         with torch.cuda.device(device):
             host = zlib.crc32(socket.gethostname().encode())
