@@ -266,10 +266,20 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- warm start ("lambda_0 loaded from a saved C3 run"): an untimed run from zero produces the
+    #      saved dual; the measured run starts from it, so the timed iterations see a late iterate whatever --steps is
+    #      (from zero the first iterations are dominated by the cheap top-2 shortcut) ----
+    lam0 = torch.zeros(m, dtype=torch.float32, device=device)
+    if args.warm_start_iters > 0:
+        pre = AcceleratedGradientDescent(max_iter=args.warm_start_iters, gamma=GAMMA, initial_step_size=INITIAL_STEP,
+                                         max_step_size=MAX_STEP, iteration_callback=no_iteration_callback)
+        lam0 = pre.maximize(obj, lam0, rank=rank).dual_val.clone()
+        barrier()
+
     # ---- device-resident loop: W warm-up + K timed iterations ----
     solver = AcceleratedGradientDescent(max_iter=W + K, gamma=GAMMA, initial_step_size=INITIAL_STEP, max_step_size=MAX_STEP,
                                         iteration_callback=no_iteration_callback)
-    loop = FusedAscentLoop(solver, obj, torch.zeros(m, dtype=torch.float32, device=device), rank)
+    loop = FusedAscentLoop(solver, obj, lam0, rank)
     for i in range(1, W + 1):
         loop.step(i)
     sampler = ClockSampler(local_rank)
@@ -292,6 +302,14 @@ def run_native(args):
     result = loop.finish()
     lam_now = loop.current_dual()
     loop.close()
+    # every rank updates its own replica of the dual; they must never drift apart: compare bit patterns across ranks
+    replicas = None
+    if world > 1:
+        bits = lam_now.view(torch.int32).to(torch.int64)
+        hi, lo = bits.clone(), bits.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        replicas = {"ranks": world, "dual_bit_identical_on_all_ranks": bool((hi == lo).all().item())}
     launches_per_step = info["plan"]["launches_per_calc"] + 1  # objective kernel(s) + update (an all-reduce would be NCCL's)
     exchange = "none (single GPU)" if world == 1 else (
         "peer memory: partial sums read over NVLink inside the update kernel, no collective call" if loop.peer is not None
@@ -319,7 +337,7 @@ def run_native(args):
 
         host_solver = AcceleratedGradientDescent(max_iter=W + Ke, gamma=GAMMA, initial_step_size=INITIAL_STEP,
                                                  max_step_size=MAX_STEP, iteration_callback=mark)
-        lam_host = torch.zeros(m, dtype=torch.float32).pin_memory()
+        lam_host = lam0.cpu().pin_memory()
         barrier()
         host_solver.maximize(obj, lam_host, rank=0)  # every rank runs the host loop on its own copy of lambda
         torch.cuda.synchronize(device)
@@ -329,18 +347,30 @@ def run_native(args):
                "steps": Ke, "path": "AcceleratedGradientDescent.maximize with a pinned host dual vector: per iteration lambda "
                "host->device, fused kernel(s), grad+scalars device->host, host-side update; same iterations as `value`"}
 
-    # ---- CPU baseline (rank 0, N=1 only) ----
+    # ---- CPU baseline (rank 0, N=1 only): the unmodified reference (oracle/_ref) on a bounded sample, the C port beside it ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import c_oracle
+        from benchmark import reference_arm as R
+        from oracle import make_ref
 
-        threads = c_oracle.max_threads()
+        threads = R.host_threads()
         t_s, e_s, n_s = cpu_baseline_port(shard, b, args, args.cpu_sample_cols, threads)
-        it_s = 1.0 / (t_s * info["nnz_total"] / max(e_s, 1))
-        cpu = {"value": it_s, "unit": "iterations/s", "cores": threads, "kind": "port",
-               "sample": f"first {n_s} entities ({e_s} nnz) of the workload, best of 3 evaluations of the dual with the C/OpenMP "
-                         f"restatement; {t_s:.3f} s per evaluation = {e_s / t_s / 1e6:.1f} M nnz/s, scaled by nnz to the full problem",
-               "nnz_per_s": e_s / t_s}
+        port = {"value": 1.0 / (t_s * info["nnz_total"] / max(e_s, 1)), "unit": "iterations/s", "cores": threads, "kind": "port",
+                "sample": f"first {n_s} entities ({e_s} nnz), best of 3 evaluations of the dual with the C/OpenMP restatement: "
+                          f"{e_s / t_s / 1e6:.1f} M nnz/s, scaled by nnz", "nnz_per_s": e_s / t_s}
+        cpu = port
+        if make_ref.available():
+            del shard
+            torch.set_num_threads(threads)
+            n_r = min(args.ref_sample_cols, args.entities)
+            ref_args, e_r = R.build_reference_problem(args.entities, m, args.sparsity, SEED, n_r, args.mixed, args.jacobi, "cpu", device)
+            steps_r = 8
+            dt, _, _ = R.time_reference_maximize(ref_args, steps_r, 2, args.ref_batching, "cpu")
+            nnz_s = e_r * steps_r / dt
+            cpu = {"value": nnz_s / info["nnz_total"], "unit": "iterations/s", "cores": threads, "kind": "reference",
+                   "sample": f"UNMODIFIED reference (oracle/_ref) maximize() on torch CPU ({threads} threads), first {n_r} entities "
+                             f"({e_r} nnz), {steps_r} iterations after 2 warm-up, batching={args.ref_batching}: {nnz_s / 1e6:.1f} M nnz/s, "
+                             f"scaled by nnz to the full problem", "nnz_per_s": nnz_s, "port": port}
 
     if rank == 0:
         it_per_s = K / (ms_total * 1e-3)
@@ -355,7 +385,9 @@ def run_native(args):
                        "parallelism": f"entity-sharded x{world}" if world > 1 else "single GPU", "exchange": exchange,
                        "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush between iterations" % (b_alg / 1e9)
                        if b_alg > 2 * L2_BYTES else "inputs fit in L2: numbers are L2-resident, not a roofline claim",
-                       "index_dtype": "int64 inputs, uint16 row ids in the plan"},
+                       "index_dtype": "int64 inputs, uint16 row ids in the plan",
+                       "warm_start": (f"lambda after {args.warm_start_iters} untimed iterations from zero (BASELINE.md C4: saved-dual "
+                                      f"warm start); fresh optimizer state") if args.warm_start_iters > 0 else "none (lambda_0 = 0)"},
             "entities_x_constraints_per_s": args.entities * args.duals * it_per_s,
             "nnz_per_s": info["nnz_total"] * it_per_s,
             "gpu_launches": launches_per_step * K,
@@ -378,6 +410,8 @@ def run_native(args):
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if replicas is not None:
+            line["replicas"] = replicas
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -385,14 +419,78 @@ def run_native(args):
 
 
 def run_reference(args):
-    """CPU arm: the oracle port (C/OpenMP restatement of the reference's algorithm) on all host threads.
-
-    The reference itself is pure Python/PyTorch and is not present on the GPU box (it cannot travel), so this arm
-    times oracle/matching_oracle.c.  Each step is one dual-ascent iteration (evaluate + numpy update) on a bounded
-    column sample of the same workload; `value` is scaled by nnz to the full problem."""
+    """Reference arm: the UNMODIFIED reference (oracle/_ref = `pip install --target` of linkedin/DuaLip v5.0.1, see
+    oracle/make_ref.py) on the host cores of this box: its own MatchingSolverDualObjectiveFunction +
+    AcceleratedGradientDescent.maximize on torch CPU tensors, all hardware threads (set explicitly: torchrun exports
+    OMP_NUM_THREADS=1).  Each step is one dual-ascent iteration on a bounded entity sample of the same workload; `value`
+    is scaled by nnz to the full problem.  The C/OpenMP port of the oracle is timed beside it (`port`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from benchmark import reference_arm as R
+
+    threads = R.host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)  # before torch / libgomp start their pools
+    os.environ["MKL_NUM_THREADS"] = str(threads)
+    import numpy as np
+    import torch
+
+    torch.set_num_threads(threads)
+    from oracle import make_ref
+
+    n, m = args.entities, args.duals
+    K, W = args.steps, args.warmup
+    config = {"workload": f"synthetic matching LP {args.entities} entities x {args.duals} duals, sparsity {args.sparsity}, "
+                          f"{'simplex(z=1) even / box[0,1] odd' if args.mixed else 'simplex(z=1)'}, "
+                          f"{'Jacobi precond, ' if args.jacobi else ''}Nesterov AGD, gamma={GAMMA}",
+              "workload_id": args.workload, "entities": n, "duals": m, "parallelism": "host threads (CPU arm)"}
+    line = {"impl": "reference", "metric": "dual-ascent iterations/sec", "unit": "iterations/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config}
+
+    # ---- the C/OpenMP port of the oracle on a larger sample (kept as context: 10-20x faster than the reference) ----
+    port = None
+    try:
+        port = _time_port(args, threads, min(args.cpu_sample_cols, n))
+    except Exception as e:  # the port is context, never the headline
+        log(f"[bench] port timing failed: {e!r}")
+
+    if make_ref.available():
+        n_s = min(args.ref_sample_cols, n)
+        gen_device = "cuda" if torch.cuda.is_available() else "cpu"
+        input_args, e_s = R.build_reference_problem(n, m, args.sparsity, SEED, n_s, args.mixed, args.jacobi, "cpu", gen_device)
+        e_full = e_s * (n / n_s)
+        dt, t_obj, result = R.time_reference_maximize(input_args, K, W, args.ref_batching, "cpu")
+        it_s_sample = K / dt
+        it_s_full = it_s_sample * (e_s / e_full)
+        config.update({"nnz": int(round(e_full)), "sample_entities": n_s, "batching": args.ref_batching})
+        line.update({
+            "value": it_s_full, "ms_per_step": 1e3 / it_s_full,
+            "cpu_baseline": {"value": it_s_full, "unit": "iterations/s", "cores": threads, "kind": "reference",
+                             "torch_threads": torch.get_num_threads(),
+                             "sample": f"UNMODIFIED reference (oracle/_ref, {open(os.path.join(make_ref.OUT, 'HOW')).read().strip()}) "
+                                       f"maximize() on torch CPU, first {n_s} of {n} entities ({e_s} nnz), batching={args.ref_batching}: "
+                                       f"{it_s_sample:.3f} it/s on the sample = {e_s * it_s_sample / 1e6:.1f} M nnz/s, scaled by nnz to "
+                                       f"the full problem" + ("; note: the reference corrupts mixed projection maps "
+                                       "(utils/sparse_utils.py:177,220), its timing is unaffected" if args.mixed else ""),
+                             "nnz_per_s": e_s * it_s_sample, "objective_build_s": t_obj, "port": port},
+            "e2e": {"value": it_s_full, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        })
+    elif port is not None:
+        config.update({"nnz": port["nnz_full"], "sample_entities": port["sample_entities"]})
+        line.update({
+            "value": port["value"], "ms_per_step": 1e3 / port["value"],
+            "cpu_baseline": {"value": port["value"], "unit": "iterations/s", "cores": threads, "kind": "port",
+                             "sample": port["sample"] + " (oracle/_ref absent: the reference itself was not available)"},
+            "e2e": {"value": port["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        })
+    else:
+        line = {"impl": "reference", "unavailable": "neither oracle/_ref nor the C port could be run"}
+    print(json.dumps(line), flush=True)
+
+
+def _time_port(args, threads, n_s, iters=6, warm=2):
+    """oracle/matching_oracle.c (OpenMP) driving the numpy AGD restatement: iterations/s scaled to the full problem."""
     import numpy as np
     import torch
 
@@ -401,7 +499,6 @@ def run_reference(args):
     from oracle import dualip_oracle as O
 
     n, m = args.entities, args.duals
-    n_s = min(args.cpu_sample_cols, n)
     gen_device = "cuda" if torch.cuda.is_available() else "cpu"
     shard = generate_shard(n, m, args.sparsity, SEED, gen_device, 0, n_s)
     b = capacity_vector(shard.greedy_load * (n / n_s), m, args.sparsity, SEED, gen_device).cpu().numpy()
@@ -418,40 +515,21 @@ def run_reference(args):
         col_class = (np.arange(n_s) % 2).astype(np.uint8)
     else:
         classes, col_class = [c_oracle.make_class("simplex", {"z": 1.0})], None
-    threads = c_oracle.max_threads()
-    K, W = args.steps, args.warmup
-
-    def calc(lam, gamma):
-        r = c_oracle.calculate(ccol, row, a, c, m, classes, lam, gamma, b, col_class, want_x=False, want_diag=False, threads=threads)
-        return r["grad"], r["scal"][0]
-
     state = {"i": 0, "t0": None}
 
     def timed_calc(lam, gamma):
-        if state["i"] == W:
+        if state["i"] == warm:
             state["t0"] = time.perf_counter()
         state["i"] += 1
-        return calc(lam, gamma)
+        r = c_oracle.calculate(ccol, row, a, c, m, classes, lam, gamma, b, col_class, want_x=False, want_diag=False, threads=threads)
+        return r["grad"], r["scal"][0]
 
-    O.agd_maximize(timed_calc, np.zeros(m, dtype=np.float32), W + K, GAMMA, INITIAL_STEP, MAX_STEP)
-    dt = time.perf_counter() - state["t0"]
-    it_s_sample = K / dt
-    it_s_full = it_s_sample * (e_s / e_full)
-    line = {
-        "impl": "reference", "metric": "dual-ascent iterations/sec", "value": it_s_full, "unit": "iterations/s",
-        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 / it_s_full, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic matching LP {args.entities} entities x {args.duals} duals, sparsity {args.sparsity}, "
-                               f"{'simplex(z=1) even / box[0,1] odd' if args.mixed else 'simplex(z=1)'}, "
-                               f"{'Jacobi precond, ' if args.jacobi else ''}Nesterov AGD, gamma={GAMMA}",
-                   "workload_id": args.workload, "entities": n, "duals": m, "nnz": int(round(e_full)),
-                   "parallelism": "host threads (CPU arm)", "sample_entities": n_s},
-        "cpu_baseline": {"value": it_s_full, "unit": "iterations/s", "cores": threads, "kind": "port",
-                         "sample": f"first {n_s} of {n} entities ({e_s} nnz): {it_s_sample:.3f} it/s on the sample = "
-                                   f"{e_s * it_s_sample / 1e6:.1f} M nnz/s, scaled by nnz to the full problem"},
-        "e2e": {"value": it_s_full, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line), flush=True)
+    O.agd_maximize(timed_calc, np.zeros(m, dtype=np.float32), warm + iters, GAMMA, INITIAL_STEP, MAX_STEP)
+    it_s_sample = iters / (time.perf_counter() - state["t0"])
+    return {"value": it_s_sample * (e_s / e_full), "unit": "iterations/s", "cores": threads, "kind": "port",
+            "nnz_full": int(round(e_full)), "sample_entities": n_s,
+            "sample": f"C/OpenMP restatement (oracle/matching_oracle.c), first {n_s} entities ({e_s} nnz), {iters} iterations: "
+                      f"{e_s * it_s_sample / 1e6:.1f} M nnz/s, scaled by nnz"}
 
 
 def main():
@@ -468,6 +546,12 @@ def main():
     ap.add_argument("--ncu-traffic-bytes", type=float, default=None,
                     help="dram__bytes_read.sum + dram__bytes_write.sum per launch from an ncu --set full capture of this workload")
     ap.add_argument("--cpu-sample-cols", type=int, default=4_000_000)
+    ap.add_argument("--ref-sample-cols", type=int, default=1_000_000,
+                    help="--impl reference: entities of the workload the unmodified reference is timed on")
+    ap.add_argument("--ref-batching", action="store_true",
+                    help="--impl reference: batching=True (the reference benchmark's default is False, config.py:22)")
+    ap.add_argument("--warm-start-iters", type=int, default=200,
+                    help="untimed iterations from zero that produce the dual the measured run starts from (0: start at zero)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",

@@ -28,7 +28,10 @@ class CscDesc(C.Structure):
     _fields_ = [("n_cols", C.c_int64), ("nnz", C.c_int64), ("n_rows", C.c_int32), ("index_bits", C.c_int32),
                 ("ccol_dev", C.c_void_p), ("row_dev", C.c_void_p), ("a_dev", C.c_void_p), ("c_dev", C.c_void_p),
                 ("col_class_dev", C.c_void_p), ("classes", C.POINTER(ProjClass)), ("n_classes", C.c_int32),
-                ("device", C.c_int32)]
+                ("device", C.c_int32), ("pad_len", C.POINTER(C.c_int32))]
+
+
+PAD_BUCKETS = 32
 
 
 class LpDesc(C.Structure):

@@ -104,6 +104,7 @@ struct dualip_plan {
   dualip_proj_class classes_host[kMaxClasses];
   dualip_proj_class* classes_dev = nullptr;
   int n_classes = 0;
+  int* pad_dev = nullptr;      // n_classes x DUALIP_PAD_BUCKETS padded block lengths (simplex_eq), or null
   float* acc = nullptr;        // m floats, zero between calls
   int* acc_lo = nullptr;       // fixed-point mode: m ints each, zero between calls
   int* acc_hi = nullptr;
@@ -251,6 +252,7 @@ struct KArgs {
   int64_t n_slabs;
   const dualip_proj_class* classes;
   int n_classes;
+  const int* pad;            // n_classes x DUALIP_PAD_BUCKETS padded lengths of the reference's blocks, or null
   const float* lambda;
   const float* b;            // may be null
   float* acc;                // m floats (global accumulator across CTAs; fp32 mode)
@@ -311,6 +313,14 @@ __device__ __forceinline__ float make_v(float a, float lam_s, float s, float c) 
 // Largest double below x, for x >= 0 (so that {u > t} becomes {u >= x}).
 __device__ __forceinline__ double just_below(double x) {
   return x > 0.0 ? __longlong_as_double(__double_as_longlong(x) - 1LL) : -4.9406564584124654e-324;
+}
+
+// Padded length L of the reference's [L x K] block for a column of class `cls` with d entries (sparse_utils.py:197,207):
+// only simplex_eq depends on it.  Table index = ceil(log2(d)); 0 or absent = no padding.
+__device__ __forceinline__ int pad_len_of(const KArgs& k, int cls, int d) {
+  if (k.pad == nullptr) return d;
+  const int bkt = (d <= 1) ? 0 : 32 - __clz(d - 1);
+  return max(__ldg(k.pad + cls * DUALIP_PAD_BUCKETS + bkt), d);
 }
 
 }  // namespace dualip
@@ -590,8 +600,8 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       switch (d) {
 #define DUALIP_FAST_CASE(DD)                                                                              \
   case DD:                                                                                                \
-    fast_slab<DD, SMODE, ACC>(k, pc, pa, pcv, pr16, lane, active, s_lam_b, s_grad_u32, s, sl, cx, xx,    \
-                              staged, my_stage, my_bar, stage_phase, issue_next, trace);                 \
+    fast_slab<DD, SMODE, ACC>(k, pc, cls, pa, pcv, pr16, lane, active, s_lam_b, s_grad_u32, s, sl, cx,   \
+                              xx, staged, my_stage, my_bar, stage_phase, issue_next, trace);             \
     break;
         DUALIP_FAST_CASE(1)
         DUALIP_FAST_CASE(2)
@@ -681,9 +691,12 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       float* __restrict__ su = s_stash + (size_t)warp * (kStashDeg * kSlabW) + lane;
       float S = 0.f, m1 = -1.f, m2 = -1.f, m3 = -1.f;
       int i2 = 0;
+      const bool is_eq = pc.kind == DUALIP_PROJ_SIMPLEX_EQ;
+      double Sd = 0.0;  // simplex_eq: the column sum in double (css_d of the reference's scan)
       auto track = [&](float a, float c, uint32_t r, int kq) {
         const float u = fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);
         if (stash) su[kq * kSlabW] = u;
+        if (is_eq) Sd += (double)u;
         S = __fadd_rn(S, u);  // column sum in entry order
         const bool g1 = u > m1, g2 = u > m2;
         m3 = fmaxf(m3, fminf(m2, u));
@@ -721,7 +734,16 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       float x1 = 0.f, x2 = 0.f;     // results for the two largest entries when they are the only non-zeros
       bool need_theta = false;      // support of three or more: threshold search
       bool need_p2 = false;         // more than two non-zeros: second streaming pass
-      if (feasible) {
+      // simplex_eq with a clamped sum below z: in the reference's scan over the zero-padded column every padded position
+      // satisfies cond_i (0 - (css_d - z)/i > 0), so rho = L (the bucket's padded length) and theta = (css_d - z)/L < 0:
+      // every entry grows by -theta (simplex.py:160-161,207-233).  The shortcut needs u_(1) > z: excluded.
+      const float t_below = is_eq ? __fsub_rn((float)Sd, z) : 0.f;
+      if (is_eq && t_below < 0.f) {
+        branch = 2;
+        rho = pad_len_of(k, cls, d);
+        theta = __fdiv_rn(t_below, (float)rho);
+        need_p2 = true;
+      } else if (feasible) {
         branch = 0;
         if (m3p > 0.f) {
           need_p2 = true;
@@ -1111,7 +1133,12 @@ __global__ void __launch_bounds__(256) matching_long_kernel(const KArgs k, const
       }
       const bool feasible = (pc.kind == DUALIP_PROJ_SIMPLEX) && ((float)S <= pc.z_thr);
       const bool shortcut = !feasible && (__fsub_rn(m1, m2) > 1.0f);
-      if (feasible) {
+      const float t_below = __fsub_rn((float)S, pc.z);
+      if (pc.kind == DUALIP_PROJ_SIMPLEX_EQ && t_below < 0.f) {  // see the generic path of matching_slab_kernel
+        branch = 2;
+        rho = pad_len_of(k, lc.cls, lc.len);
+        theta = __fdiv_rn(t_below, (float)rho);
+      } else if (feasible) {
         branch = 0;
       } else if (shortcut) {
         branch = 1;
@@ -1297,6 +1324,7 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.n_slabs = p->n_slabs;
   k.classes = p->classes_dev;
   k.n_classes = p->n_classes;
+  k.pad = p->pad_dev;
   k.lambda = lambda;
   k.b = b;
   k.acc = p->acc;
@@ -1650,6 +1678,7 @@ void dualip_plan_destroy(dualip_plan* p) {
   cudaFree(p->long_c);
   cudaFree(p->long_row);
   cudaFree(p->classes_dev);
+  cudaFree(p->pad_dev);
   cudaFree(p->acc);
   cudaFree(p->acc_lo);
   cudaFree(p->timeline);
@@ -1803,6 +1832,15 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   DUALIP_TRY_FAIL(cudaMemset(p->acc_hi, 0, sizeof(int) * (m_pad + 4)));
   DUALIP_TRY_FAIL(cudaMalloc(&p->classes_dev, sizeof(dualip_proj_class) * p->n_classes));
   DUALIP_TRY_FAIL(cudaMemcpy(p->classes_dev, p->classes_host, sizeof(dualip_proj_class) * p->n_classes, cudaMemcpyHostToDevice));
+  if (d->pad_len != nullptr) {
+    bool any_eq = false;
+    for (int i = 0; i < p->n_classes; ++i) any_eq = any_eq || p->classes_host[i].kind == DUALIP_PROJ_SIMPLEX_EQ;
+    if (any_eq) {
+      const size_t bytes = sizeof(int) * (size_t)p->n_classes * DUALIP_PAD_BUCKETS;
+      DUALIP_TRY_FAIL(cudaMalloc(&p->pad_dev, bytes));
+      DUALIP_TRY_FAIL(cudaMemcpy(p->pad_dev, d->pad_len, bytes, cudaMemcpyHostToDevice));
+    }
+  }
   DUALIP_TRY_FAIL(cudaMalloc(&p->acc, sizeof(float) * (m_pad + 4)));
   DUALIP_TRY_FAIL(cudaMemset(p->acc, 0, sizeof(float) * (m_pad + 4)));
   DUALIP_TRY_FAIL(cudaMalloc(&p->acc_scal, sizeof(double) * 2));

@@ -350,7 +350,7 @@ __device__ __forceinline__ void scan_sorted(const float (&w)[D], float z, double
 // simplex / simplex_eq (simplex.py:143-236 per column at its true length).  On return x holds the projection;
 // branch: 0 feasible, 1 top-2 shortcut, 2 sorted scan ("Duchi"); rho: support size for branches 1 and 2.
 template <int D, int SMODE>
-__device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_class& pc, ColRegs<D>& R, bool active,
+__device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_class& pc, int cls, ColRegs<D>& R, bool active,
                                              const unsigned char* s_lam_b, float s, float (&u)[D], int& branch, int& rho) {
   const unsigned FULL = 0xffffffffu;
   make_v_cols<D, SMODE>(k, R, s_lam_b, s, u);
@@ -371,7 +371,19 @@ __device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_c
   branch = feasible ? 0 : (shortcut ? 1 : 2);
   rho = shortcut ? 1 : 0;
   float theta = 0.f;
-  const bool need_theta = active && branch == 2;
+  // simplex_eq with a clamped sum below z: every zero-padded position of the reference's block satisfies cond_i, so
+  // rho = L (the bucket's padded length) and theta = (css_d - z)/L < 0 (simplex.py:160-161,207-233).
+  // The shortcut needs u_(1) > z, which excludes it.  Uniform per slab: only simplex_eq slabs pay for the double sum.
+  bool below = false;
+  float t_below = 0.f;
+  if (pc.kind == DUALIP_PROJ_SIMPLEX_EQ) {
+    double sd = 0.0;
+#pragma unroll
+    for (int q = 0; q < D; ++q) sd += (double)u[q];
+    t_below = __fsub_rn((float)sd, z);
+    below = t_below < 0.f;
+  }
+  const bool need_theta = active && branch == 2 && !below;
 
   if (__any_sync(FULL, need_theta)) {
     // ---- the reference's sorted scan itself (simplex.py:207-231), on a sorted copy of the column in registers ----
@@ -396,6 +408,10 @@ __device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_c
       rho = rho_sel;
     }
   }
+  if (below) {
+    rho = pad_len_of(k, cls, D);
+    theta = __fdiv_rn(t_below, (float)rho);
+  }
   if (__any_sync(FULL, shortcut)) {
     // x = z at the (unique) maximum, 0 elsewhere (simplex.py:185-190); theta stays 0 so the subtraction below is exact
 #pragma unroll
@@ -410,7 +426,7 @@ __device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_c
 // `staged` the same bytes are waiting in (or on their way to) the warp's staging buffer.  issue_next() is called as
 // soon as the buffer has been read out, to start the copy of the warp's next slab.
 template <int D, int SMODE, int ACC, typename IssueNext>
-__device__ __forceinline__ void fast_slab(const KArgs& k, const dualip_proj_class& pc, const float* __restrict__ a_s,
+__device__ __forceinline__ void fast_slab(const KArgs& k, const dualip_proj_class& pc, int cls, const float* __restrict__ a_s,
                                           const float* __restrict__ c_s, const unsigned short* __restrict__ r_s, int lane,
                                           bool active, const unsigned char* s_lam_b, uint32_t s_grad_u32, float s,
                                           int64_t slab_index, double& cx, double& xx, bool staged,
@@ -437,7 +453,7 @@ __device__ __forceinline__ void fast_slab(const KArgs& k, const dualip_proj_clas
   if (pc.kind == DUALIP_PROJ_CLAMP)
     fast_clamp<D, SMODE>(k, pc, R, active, s_lam_b, s, x);
   else
-    fast_simplex<D, SMODE>(k, pc, R, active, s_lam_b, s, x, branch, rho);
+    fast_simplex<D, SMODE>(k, pc, cls, R, active, s_lam_b, s, x, branch, rho);
   if (trace) {
     float t = 0.f;
 #pragma unroll

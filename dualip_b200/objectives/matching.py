@@ -148,6 +148,42 @@ def _build_class_table(ccol: torch.Tensor, n_cols: int, projection_map, batching
     return arr, len(classes), col_class
 
 
+def _build_pad_table(ccol: torch.Tensor, n_cols: int, projection_map, batching: bool, n_rows: int, n_classes: int):
+    """Padded block lengths for `simplex_eq` entries, the only projection whose result depends on them:
+    the reference projects a column inside a zero-padded [L x K] block, L = longest column of the length bucket the column
+    falls in (matching.py:87-114: buckets (0,2], (2,4], (4,8], ..., (2^k, m]; batching=False: one bucket per entry;
+    utils/sparse_utils.py:197,207).  Returns a ctypes int32 array n_classes x 32 indexed by ceil(log2(d)), or None."""
+    entries = list(projection_map.items())
+    if not any(e.proj_type == "simplex_eq" and e.proj_params.get("method", "duchi") == "duchi" for _, e in entries):
+        return None
+    table = np.zeros((n_classes, _native.PAD_BUCKETS), dtype=np.int32)
+    lengths = ccol[1:] - ccol[:-1]
+    first = n_classes - len(entries)  # class 0 is the identity class when the map does not cover every column
+    for i, (_, entry) in enumerate(entries):
+        if entry.proj_type != "simplex_eq":
+            continue
+        ind = entry.indices
+        full = isinstance(ind, range) and ind.start == 0 and ind.step == 1 and ind.stop == n_cols
+        sel = lengths if full else lengths[_indices_to_device(ind, ccol.device)]
+        sel = sel[sel > 0]
+        if sel.numel() == 0:
+            continue
+        if batching:
+            bkt = torch.ceil(torch.log2(sel.to(torch.float64))).to(torch.int64).clamp_(min=1)  # lengths 1 and 2 share a bucket
+            lmax = torch.zeros(_native.PAD_BUCKETS, dtype=torch.int64, device=ccol.device)
+            lmax.scatter_reduce_(0, bkt, sel.to(torch.int64), reduce="amax", include_self=True)
+            row = lmax.cpu().numpy()
+            row[0] = row[1]
+            # the reference's last bucket is (2^k, m+1] with 2^k <= m: lengths above 2^k share it whatever their log2
+            k = int(np.floor(np.log2(max(n_rows, 1))))
+            if k + 1 < _native.PAD_BUCKETS:
+                row[k + 1:] = row[k + 1:].max()
+        else:
+            row = np.full(_native.PAD_BUCKETS, int(sel.max().item()), dtype=np.int64)
+        table[first + i] = row
+    return (ctypes.c_int32 * table.size)(*table.reshape(-1).tolist())
+
+
 class MatchingSolverDualObjectiveFunction(BaseObjective):
     """Dual gradient, objective and regularisation penalty of a matching LP on one GPU.
 
@@ -195,6 +231,7 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
             self._blk_a, self._blk_c = self._a_vals[ec], self._c_vals[ec]
             self._blk_row = row[ec].to(torch.int64)
         self._classes = classes
+        self._pad = _build_pad_table(ccol, self.n, self.projection_map, batching, self.m, n_classes)
         desc = _native.CscDesc(
             n_cols=self.n, nnz=self.nnz, n_rows=self.m, index_bits=32 if ccol.dtype == torch.int32 else 64,
             ccol_dev=ccol.data_ptr(), row_dev=row.data_ptr() if self.nnz else 0,
@@ -202,6 +239,7 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
             col_class_dev=col_class.data_ptr() if col_class is not None else None,
             classes=ctypes.cast(classes, ctypes.POINTER(_native.ProjClass)), n_classes=n_classes,
             device=self.device.index if self.device.index is not None else torch.cuda.current_device(),
+            pad_len=ctypes.cast(self._pad, ctypes.POINTER(ctypes.c_int32)) if self._pad is not None else None,
         )
         handle = ctypes.c_void_p()
         torch.cuda.synchronize(self.device)

@@ -51,10 +51,12 @@ def _bounds_from_projection_map(projection_map, n: int, device):
         else:
             raise ValueError(f"projection '{item.proj_type}' (entry {key!r}) is not an element-wise bound; the generic-LP "
                              "objective supports box and cone entries")
-        if lower is not None:
-            lo[idx] = torch.maximum(lo[idx], torch.tensor(float(lower), device=device))
-        if upper is not None:
-            hi[idx] = torch.minimum(hi[idx], torch.tensor(float(upper), device=device))
+        # entries are applied one after the other (miplib.py:80-90); a clamp after a clamp is the clamp whose bounds are
+        # the earlier bounds pushed through the later one: min(max(., l2), u2)
+        l2 = float("-inf") if lower is None else float(lower)
+        u2 = float("inf") if upper is None else float(upper)
+        lo[idx] = lo[idx].clamp_min(l2).clamp_max(u2)
+        hi[idx] = hi[idx].clamp_min(l2).clamp_max(u2)
     return lo, hi
 
 
@@ -68,11 +70,16 @@ class MIPLIB2017ObjectiveFunction(BaseObjective):
         self.device = args.c.device
         A = args.A.to(self.device)
         self.A = A
-        dense = A.to_dense() if A.layout != torch.strided else A
-        dense = dense.to(torch.float32)
-        self.m, self.n = int(dense.shape[0]), int(dense.shape[1])
-        csr = dense.to_sparse_csr()
-        csc = dense.to_sparse_csc()
+        self.m, self.n = int(A.shape[0]), int(A.shape[1])
+        # sparse inputs stay sparse (the reference keeps CSR + CSC copies, miplib.py:41-42); only strided inputs are dense
+        if A.layout == torch.strided:
+            src = A.to(torch.float32)
+        elif A.layout == torch.sparse_coo:
+            src = A.to(torch.float32).coalesce()
+        else:
+            src = A.to(torch.float32)
+        csr = src if src.layout == torch.sparse_csr else src.to_sparse_csr()
+        csc = src if src.layout == torch.sparse_csc else src.to_sparse_csc()
         self._csr = (csr.crow_indices().to(torch.int32).contiguous(), csr.col_indices().to(torch.int32).contiguous(),
                      csr.values().to(torch.float32).contiguous())
         self._csc = (csc.ccol_indices().to(torch.int32).contiguous(), csc.row_indices().to(torch.int32).contiguous(),
@@ -91,7 +98,7 @@ class MIPLIB2017ObjectiveFunction(BaseObjective):
         if use_jacobi_precondition:
             if args.A.layout != torch.strided:
                 raise NotImplementedError("Jacobi preconditioning is not implemented for sparse matrices")  # miplib.py:50-52
-            row_norms = torch.norm(dense, dim=1, keepdim=True)
+            row_norms = torch.norm(A.to(torch.float32), dim=1, keepdim=True)
             self.row_norms = torch.where(row_norms == 0, torch.ones_like(row_norms), row_norms).squeeze()
             self._row_scale = (1.0 / self.row_norms).to(torch.float32).contiguous()
         else:
@@ -176,12 +183,18 @@ class MIPLIB2017ObjectiveFunction(BaseObjective):
                                     tol: float = 1e-4):
         """PDLP stopping test without regularisation (reference miplib.py:156-230): relative duality gap, primal and
         dual feasibility.  Returns (gap_upperbound, gap_lower_bound, primal_feas, dual_feas, converged)."""
-        A = self.A.to_dense() if self.A.layout != torch.strided else self.A
-        A = A.to(torch.float32)
         dual_val = dual_val.to(self.device)
         if self.row_norms is not None:
             dual_val = 1 / self.row_norms * dual_val
-        r = self.c + A.t().mv(dual_val)
+        if self.A.layout == torch.strided:
+            A32 = self.A.to(torch.float32)
+            a_mv, at_mv = A32.mv, A32.t().mv
+        else:  # sparse products on the CSR / CSC copies built at construction; never densified
+            csr = torch.sparse_csr_tensor(self._csr[0], self._csr[1], self._csr[2], size=(self.m, self.n))
+            csct = torch.sparse_csr_tensor(self._csc[0], self._csc[1], self._csc[2], size=(self.n, self.m))  # A^T as CSR
+            a_mv = lambda v: (csr @ v.unsqueeze(1)).squeeze(1)  # noqa: E731
+            at_mv = lambda v: (csct @ v.unsqueeze(1)).squeeze(1)  # noqa: E731
+        r = self.c + at_mv(dual_val)
         if x is None:
             x = torch.where(r >= 0, self.lower, self.upper)
             if torch.isnan(x).any():
@@ -196,7 +209,7 @@ class MIPLIB2017ObjectiveFunction(BaseObjective):
             gap_lower_bound = torch.abs(p - optimal_primal_obj) / (1.0 + torch.abs(p) + abs(optimal_primal_obj))
         else:
             gap_lower_bound = torch.tensor(float("nan"))
-        resid = A.mv(x) - self.b_vec
+        resid = a_mv(x) - self.b_vec
         violation = torch.relu(resid) if self.equality_mask is None else torch.where(self.equality_mask, resid.abs(), torch.relu(resid))
         primal_feas = torch.linalg.vector_norm(violation) / (1.0 + torch.linalg.vector_norm(self.b_vec))
         x_bound_duals = self._clamp_x_bound_duals(-r, l_exists, u_exists)

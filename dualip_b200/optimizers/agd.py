@@ -80,7 +80,6 @@ class AcceleratedGradientDescent:
         self.gamma_decay_type = gamma_decay_type
         self.gamma_decay_params = gamma_decay_params
         self.save_primal = save_primal
-        self._user_callback = iteration_callback is not None
         self.iteration_callback = iteration_callback if iteration_callback is not None else self._default_iteration_callback
 
     def _compute_beta_seq(self, max_iter: int) -> torch.Tensor:
@@ -145,6 +144,12 @@ class AcceleratedGradientDescent:
             loop.close()
 
     @staticmethod
+    def _callback_result(grad, scal, primal) -> ObjectiveResult:
+        """What an iteration callback receives: fresh float32 tensors, like the reference hands out every iteration
+        (matching.py:171-187) -- a callback may keep them; the loop's own buffers are overwritten by the next step."""
+        return AcceleratedGradientDescent._view_result(grad.clone(), scal, primal, as_float32=True)
+
+    @staticmethod
     def _view_result(grad, scal, primal, as_float32: bool = False) -> ObjectiveResult:
         s = scal.to(torch.float32) if as_float32 else scal
         res = ObjectiveResult(
@@ -199,7 +204,9 @@ class AcceleratedGradientDescent:
                 kwargs = {"gamma": self.gamma} if self.gamma is not None else {}
                 if i == self.max_iter and self.save_primal:
                     kwargs["save_primal"] = self.save_primal
-                objective_result = f.calculate(dual_val=x, rank=rank, **kwargs)
+                # a copy: the objective or the callback may keep what they are given, and x is native memory that the
+                # optimizer state frees at the end of this call
+                objective_result = f.calculate(dual_val=x.clone(), rank=rank, **kwargs)
                 if rank == 0:
                     self.iteration_callback(i, objective_result)
                 dual_obj = float(objective_result.dual_objective)
@@ -347,7 +354,7 @@ class FusedAscentLoop:
                 if callback:
                     # the callback wants the result before the update: separate epilogue launch, then the plain step
                     f.launch_epilogue(self.partial.data_ptr(), self.x_ptr, gamma_i, self.grad.data_ptr(), self.scal.data_ptr())
-                    solver.iteration_callback(i, solver._view_result(self.grad, self.scal, None))
+                    solver.iteration_callback(i, solver._callback_result(self.grad, self.scal, None))
                     _native.check(self.lib.dualip_agd_step(self.handle, self.grad.data_ptr(), self.scal.data_ptr(),
                                                            float(self.beta[i - 1]), decay_now, factor, i - 1, stream),
                                   "dualip_agd_step")
@@ -371,7 +378,7 @@ class FusedAscentLoop:
                     _native.check(self.lib.dualip_matching_epilogue(self.partial.data_ptr(), self.m, self.x_ptr, b_ptr, float(gamma_i),
                                                                     self.grad.data_ptr(), self.scal.data_ptr(), stream))
                     if callback:
-                        solver.iteration_callback(i, solver._view_result(self.grad, self.scal, self.primal if last_primal else None))
+                        solver.iteration_callback(i, solver._callback_result(self.grad, self.scal, self.primal if last_primal else None))
                     _native.check(self.lib.dualip_agd_step(self.handle, self.grad.data_ptr(), self.scal.data_ptr(),
                                                            float(self.beta[i - 1]), decay_now, factor, i - 1, stream), "dualip_agd_step")
                 else:
@@ -386,7 +393,7 @@ class FusedAscentLoop:
                 if ev is not None:
                     ev[1].record()
                 if callback:
-                    solver.iteration_callback(i, solver._view_result(self.grad, self.scal, self.primal if last_primal else None))
+                    solver.iteration_callback(i, solver._callback_result(self.grad, self.scal, self.primal if last_primal else None))
                 _native.check(self.lib.dualip_agd_step(self.handle, self.grad.data_ptr(), self.scal.data_ptr(),
                                                        float(self.beta[i - 1]), decay_now, factor, i - 1, stream),
                               "dualip_agd_step")

@@ -10,7 +10,6 @@ from __future__ import annotations
 import ctypes
 import os
 import socket
-import zlib
 from typing import Optional, Sequence
 
 import torch
@@ -62,34 +61,33 @@ class PeerExchange:
         if not (dist.is_available() and dist.is_initialized()):
             return None
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        if world < 2 or world > _native.PEER_MAX_WORLD or dist.get_backend(group) != "nccl":
+        if world < 2 or world > _native.PEER_MAX_WORLD:
             return None  # the same on every rank: no need to agree on it
         want = enabled and os.environ.get("DUALIP_PEER_EXCHANGE", "1") != "0"
         device = torch.device(device)
+        # setup-time exchange of small Python objects: works over any backend (NCCL, or gloo when several ranks share a GPU)
         with torch.cuda.device(device):
-            host = zlib.crc32(socket.gethostname().encode())
-            mine = torch.tensor([1 if want else 0, host], dtype=torch.int64, device=device)
-            every = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(every, mine, group=group)
-            every = torch.stack(every).cpu()
-            if not bool((every[:, 0] == 1).all()) or not bool((every[:, 1] == every[0, 1]).all()):
+            every = [None] * world
+            dist.all_gather_object(every, (bool(want), socket.gethostname()), group=group)
+            if not all(w for w, _ in every) or len({h for _, h in every}) != 1:
                 return None
-            ex, ok = None, 1
+            ex, ok, handle = None, True, b""
             try:
                 ex = cls(m, rank, world, device)
-                h = torch.frombuffer(bytearray(ex.export_handle()), dtype=torch.uint8).to(device)
+                handle = ex.export_handle()
             except Exception:
-                ok, h = 0, torch.zeros(_native.PEER_HANDLE_BYTES, dtype=torch.uint8, device=device)
-            hs = [torch.empty_like(h) for _ in range(world)]
-            dist.all_gather(hs, h, group=group)
+                ok = False
+            handles = [None] * world
+            dist.all_gather_object(handles, (ok, handle), group=group)
+            ok = all(o for o, _ in handles)
             if ok:
                 try:
-                    ex.connect_ipc([bytes(t.cpu().numpy().tobytes()) for t in hs])
+                    ex.connect_ipc([h for _, h in handles])
                 except Exception:
-                    ok = 0
-            flag = torch.tensor([ok], dtype=torch.int32, device=device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-            if int(flag.item()) != 1:
+                    ok = False
+            oks = [None] * world
+            dist.all_gather_object(oks, ok, group=group)
+            if not all(oks):
                 if ex is not None:
                     ex.close()
                 return None

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DUALIP_B200_ABI_VERSION 1
+#define DUALIP_B200_ABI_VERSION 2
 
 /* error codes */
 #define DUALIP_OK 0
@@ -69,7 +69,14 @@ typedef struct dualip_csc_desc {
   const dualip_proj_class* classes; /* host array                                        */
   int32_t n_classes;       /* 1..255                                                    */
   int32_t device;          /* CUDA device ordinal                                       */
+  const int32_t* pad_len;  /* host array n_classes x DUALIP_PAD_BUCKETS, or NULL: the padded length L of the reference's
+                              [L x K] block that a column of class k with d entries is projected in
+                              (utils/sparse_utils.py:197,207), at pad_len[k*DUALIP_PAD_BUCKETS + ceil(log2(d))]; 0 = d.
+                              Only "simplex_eq" depends on it (simplex.py:160-161): a column whose
+                              clamped sum is below z gets (z - sum)/L added to every entry.  The reference derives L from
+                              its length buckets (objectives/matching.py:87-114). */
 } dualip_csc_desc;
+#define DUALIP_PAD_BUCKETS 32
 
 typedef struct dualip_plan dualip_plan;
 

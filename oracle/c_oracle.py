@@ -33,7 +33,7 @@ def lib():
             build()
         _lib = C.CDLL(LIB_PATH)
         _lib.oracle_matching_calculate.restype = C.c_int
-        _lib.oracle_matching_calculate.argtypes = [C.c_int64, C.c_int64, C.c_int32] + [C.c_void_p] * 8 + [C.c_double] + [C.c_void_p] * 4 + [C.c_int]
+        _lib.oracle_matching_calculate.argtypes = [C.c_int64, C.c_int64, C.c_int32] + [C.c_void_p] * 8 + [C.c_double] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
         _lib.oracle_max_threads.restype = C.c_int
     return _lib
 
@@ -55,8 +55,10 @@ def make_class(proj_type: str, params: dict, d1_unpadded: bool = False) -> Oracl
     raise ValueError(f"Unknown projection operator '{proj_type}'")
 
 
-def calculate(ccol, row, a, c, n_rows, classes, lam, gamma, b=None, col_class=None, want_x=True, want_diag=True, threads=0):
-    """Returns dict(grad, scal[7], x, diag).  classes: list[OracleClass]; col_class: uint8 per column or None."""
+def calculate(ccol, row, a, c, n_rows, classes, lam, gamma, b=None, col_class=None, want_x=True, want_diag=True, threads=0,
+              pad_len=None):
+    """Returns dict(grad, scal[7], x, diag).  classes: list[OracleClass]; col_class: uint8 per column or None;
+    pad_len: int32 [n_classes, 32] padded block lengths (dualip_oracle.pad_table) or None."""
     ccol = np.ascontiguousarray(ccol, dtype=np.int64)
     row = np.ascontiguousarray(row, dtype=np.int64)
     a = np.ascontiguousarray(a, dtype=np.float32)
@@ -70,12 +72,14 @@ def calculate(ccol, row, a, c, n_rows, classes, lam, gamma, b=None, col_class=No
     diag = np.empty(n, dtype=np.uint8) if want_diag else None
     bb = np.ascontiguousarray(b, dtype=np.float32) if b is not None else None
     cc = np.ascontiguousarray(col_class, dtype=np.uint8) if col_class is not None else None
+    pl = np.ascontiguousarray(pad_len, dtype=np.int32) if pad_len is not None else None
+    assert pl is None or pl.shape == (len(classes), 32)
 
     def p(arr):
         return arr.ctypes.data_as(C.c_void_p) if arr is not None else None
 
     rc = lib().oracle_matching_calculate(n, nnz, int(n_rows), p(ccol), p(row), p(a), p(c), p(cc), C.cast(cls_arr, C.c_void_p),
-                                         p(lam), p(bb), float(gamma), p(grad), p(scal), p(x), p(diag), int(threads))
+                                         p(lam), p(bb), float(gamma), p(grad), p(scal), p(x), p(diag), int(threads), p(pl))
     if rc != 0:
         raise RuntimeError("oracle_matching_calculate failed")
     return dict(grad=grad, scal=scal, x=x, diag=diag)

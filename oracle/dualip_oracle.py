@@ -205,6 +205,27 @@ def compute_buckets(ccol: np.ndarray, n_rows: int, indices: np.ndarray, batching
     return out
 
 
+def pad_table(ccol: np.ndarray, n_rows: int, entries: Sequence[ProjEntry], batching: bool = True) -> np.ndarray:
+    """Padded block length L per (entry, ceil(log2(column length))) from the reference's bucket rule
+    (objectives/matching.py:87-114 + utils/sparse_utils.py:197): int32 [len(entries), 32].  For checkers that work
+    per column (oracle/matching_oracle.c) instead of per padded block."""
+    lengths = np.diff(np.asarray(ccol, dtype=np.int64))
+    out = np.zeros((len(entries), 32), dtype=np.int32)
+    for e, entry in enumerate(entries):
+        for cols in compute_buckets(ccol, n_rows, np.asarray(entry.indices, dtype=np.int64), batching):
+            ln = lengths[cols]
+            ln = ln[ln > 0]
+            if ln.size == 0:
+                continue
+            L = int(ln.max())
+            for d in np.unique(ln):
+                bkt = 0
+                while (1 << bkt) < int(d):
+                    bkt += 1
+                out[e, bkt] = max(out[e, bkt], L)
+    return out
+
+
 def _apply_entry(vals: np.ndarray, ccol: np.ndarray, entry: ProjEntry, n_rows: int, batching: bool, branch, rho):
     """utils/sparse_utils.py:133-220 (`apply_F_to_columns`): padded [L x K] block per bucket."""
     dt = vals.dtype

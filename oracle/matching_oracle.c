@@ -3,7 +3,9 @@
  * as a fast checker at sizes the numpy oracle cannot reach, and by bench.py as the CPU baseline ("port").
  * The CUDA product never links or calls this file.
  *
- * Follows reference src/dualip/objectives/matching.py:116-188 per column at its TRUE length (no padding):
+ * Follows reference src/dualip/objectives/matching.py:116-188 per column at its true length, with the zero padding of
+ * the reference's [L x K] blocks restated literally where it changes the result (simplex_eq: the sorted scan runs
+ * over L positions, the last L - d of them zeros; L per (class, length bucket) is passed in by the caller):
  *   v = fl(fl(a * fl(s*lambda_r)) + fl(s*c)),  s = fl32(-1/gamma)          matching.py:133-142
  *   box/cone: x = min(max(v,lo),hi)                                          projections/box.py:16, cone.py:21-28
  *   simplex : u = max(v,0); feasible / top-2 shortcut / sorted scan          projections/simplex.py:143-236
@@ -34,8 +36,9 @@ static int cmp_desc(const void* pa, const void* pb) {
   return (a < b) - (a > b);
 }
 
-/* Projects one column in place: v[0..d) -> x[0..d).  Returns branch (0/1/2) and *rho. scratch holds d floats. */
-static int project_column(float* v, int64_t d, const oracle_class* pc, float* scratch, int* rho) {
+/* Projects one column in place: v[0..d) -> x[0..d).  Returns branch (0/1/2) and *rho. scratch holds d floats.
+ * d_pad >= d: length of the zero-padded column the reference's scan sees (sparse_utils.py:207-208). */
+static int project_column(float* v, int64_t d, int64_t d_pad, const oracle_class* pc, float* scratch, int* rho) {
   *rho = 0;
   if (pc->kind == 0) {
     for (int64_t k = 0; k < d; ++k) v[k] = fminf(fmaxf(v[k], pc->lo), pc->hi);
@@ -72,11 +75,12 @@ static int project_column(float* v, int64_t d, const oracle_class* pc, float* sc
   double acc = 0.0;
   int64_t r = 0;
   float css_r = 0.0f;
-  for (int64_t i = 0; i < d; ++i) {
-    acc += (double)scratch[i];
+  for (int64_t i = 0; i < d_pad; ++i) {
+    const float ui = i < d ? scratch[i] : 0.0f; /* padded zeros sort to the end */
+    acc += (double)ui;
     const float css = (float)acc;
     const float t = (css - z) / (float)(i + 1);
-    if (scratch[i] - t > 0.0f) {
+    if (ui - t > 0.0f) {
       r = i + 1;
       css_r = css;
     }
@@ -95,7 +99,8 @@ static int project_column(float* v, int64_t d, const oracle_class* pc, float* sc
 int oracle_matching_calculate(int64_t n_cols, int64_t nnz, int32_t m, const int64_t* ccol, const int64_t* row,
                               const float* a, const float* c, const uint8_t* col_class, const oracle_class* classes,
                               const float* lambda, const float* b, double gamma, float* grad_out, double* scal_out,
-                              float* x_out, uint8_t* diag_out, int n_threads) {
+                              float* x_out, uint8_t* diag_out, int n_threads, const int32_t* pad_len) {
+  /* pad_len: n_classes x 32 padded block lengths indexed by ceil(log2(d)), or NULL (no padding) */
   (void)nnz;
   const float s = (float)(-1.0 / gamma);
   float* sl = (float*)malloc(sizeof(float) * (size_t)m);
@@ -130,9 +135,16 @@ int oracle_matching_calculate(int64_t n_cols, int64_t nnz, int32_t m, const int6
         const float t = a[e0 + k] * sl[row[e0 + k]];
         v[k] = t + s * c[e0 + k];
       }
-      const oracle_class* pc = &classes[col_class ? col_class[j] : 0];
+      const int cls = col_class ? col_class[j] : 0;
+      const oracle_class* pc = &classes[cls];
+      int64_t d_pad = d;
+      if (pad_len && pc->kind == 2) {
+        int bkt = 0;
+        while (((int64_t)1 << bkt) < d) ++bkt;
+        if (pad_len[cls * 32 + bkt] > d_pad) d_pad = pad_len[cls * 32 + bkt];
+      }
       int rho = 0;
-      const int br = project_column(v, d, pc, scratch, &rho);
+      const int br = project_column(v, d, d_pad, pc, scratch, &rho);
       if (diag_out && br >= 0) diag_out[j] = (uint8_t)(br | ((rho > 63 ? 63 : rho) << 2));
       for (int64_t k = 0; k < d; ++k) {
         const float x = v[k];

@@ -16,9 +16,27 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def main():
     rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    one_gpu = os.environ.get("DUALIP_TEST_ONE_GPU") == "1"
+    if one_gpu:
+        # every rank on cuda:0 (a single-GPU box): NCCL refuses two ranks per device, so the process group is gloo; the
+        # per-iteration exchange still goes through CUDA-IPC windows and the in-kernel flags, the path under test
+        local_rank = 0
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    dist.init_process_group("nccl", device_id=dev)
+    if one_gpu:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def all_gather(t):
+        if one_gpu:  # gloo gathers host tensors
+            out = [torch.empty_like(t, device="cpu") for _ in range(world)]
+            dist.all_gather(out, t.cpu())
+            return out
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return out
+
     from conftest import random_problem
     from dualip_b200.objectives.matching import MatchingInputArgs, MatchingSolverDualObjectiveFunctionDistributed
     from dualip_b200.optimizers.agd import AcceleratedGradientDescent
@@ -54,8 +72,7 @@ def main():
     ref_first = c_oracle.calculate(p["ccol"], p["row"], p["a"], p["c"], m, [c_oracle.make_class("simplex", {"z": 1.0})],
                                    np.zeros(m, np.float32), gamma, p["b"])
     assert abs(out.dual_objective_log[0] - ref_first["scal"][0]) <= 1e-5 * abs(ref_first["scal"][0])
-    gathered = [torch.empty_like(lam) for _ in range(world)]
-    dist.all_gather(gathered, lam)
+    gathered = all_gather(lam)
     assert all(torch.equal(g, gathered[0]) for g in gathered), "replicated optimizer state diverged across ranks"
     # 3) the same shard through both exchange paths: partial sums read from peer memory inside the update kernel (no
     #    per-iteration callback) vs the NCCL all-reduce (DUALIP_PEER_EXCHANGE=0)
@@ -78,8 +95,7 @@ def main():
     assert np.allclose(runs["peer"].step_size_log, runs["nccl"].step_size_log, rtol=1e-3)
     assert torch.allclose(runs["peer"].dual_val, runs["nccl"].dual_val, rtol=1e-4, atol=1e-5)
     lam = runs["peer"].dual_val.clone()
-    gathered = [torch.empty_like(lam) for _ in range(world)]
-    dist.all_gather(gathered, lam)
+    gathered = all_gather(lam)
     assert all(torch.equal(g, gathered[0]) for g in gathered), "peer path: replicas must be bit-identical"
     dist.barrier()
     if rank == 0:

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_abi_version_and_error_string():
     lib = _native.lib()
-    assert lib.dualip_abi_version() == 1
+    assert lib.dualip_abi_version() == 2
     assert isinstance(lib.dualip_last_error(), bytes)
 
 

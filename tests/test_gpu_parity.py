@@ -74,6 +74,62 @@ def test_fixtures_generated_by_the_reference(name, index_dtype):
         assert np.array_equal(rho[sel], np.minimum(orc.rho[nonempty][sel], 63)), "support size differs"
 
 
+@pytest.mark.parametrize("batching", [True, False])
+@pytest.mark.parametrize("index_dtype", [torch.int64, torch.int32])
+def test_mixed_map_fixture_derived_from_the_reference(batching, index_dtype):
+    """configs[2]: simplex(z=1) on even entities, box[0,1] on odd ones, Jacobi-scaled C3-shaped data from the reference's
+    generator, at a late dual.  Expected values = the reference's own `calculate` per entry on that entry's column
+    sub-matrix, combined (tests/golden/make_golden_r2.py) -- the reference cannot evaluate a two-entry map itself
+    (utils/sparse_utils.py:177,220).  x must be bit-identical."""
+    d = np.load(f"{GOLDEN}/mixed_c3shape.npz")
+    n, m, tag = d["ccol"].size - 1, int(d["n_rows"]), "b1" if batching else "b0"
+    A, C = _csc(d, index_dtype=index_dtype)
+    pm = {}
+    pm.update(create_projection_map("simplex", {"z": 1.0}, n, indices=list(range(0, n, 2))))
+    pm.update(create_projection_map("box", {"lower": 0.0, "upper": 1.0}, n, indices=list(range(1, n, 2))))
+    obj = MatchingSolverDualObjectiveFunction(MatchingInputArgs(A, C, pm, torch.from_numpy(d["b"]).to(DEV)),
+                                              gamma=float(d["gamma"]), batching=batching)
+    r = obj.calculate(torch.from_numpy(d["lam"]).to(DEV), save_primal=True, diagnostics=True)
+    assert np.array_equal(r.primal_var.cpu().numpy(), d[f"x_{tag}"]), "primal x differs from the reference"
+    scal, got = d[f"scal_{tag}"], r.scalars64.cpu().numpy()
+    assert abs(got[0] - scal[0]) <= 1e-5 * abs(scal[0])
+    assert abs(got[2] - scal[1]) <= 1e-5 * abs(scal[1])
+    assert abs(got[1] - scal[2]) <= 1e-5 * abs(scal[2])
+    assert np.allclose(r.dual_gradient.cpu().numpy(), d[f"grad_{tag}"], rtol=1e-5, atol=1e-4)
+    br, _, nonempty = _diag_per_column(r.projection_diag.cpu().numpy(), d["ccol"])
+    even_nonempty = (np.arange(n) % 2 == 0)[nonempty]
+    assert np.mean(br[even_nonempty] == 2) > 0.05, "the fixture must exercise the sorted scan (late iterate)"
+
+
+@pytest.mark.parametrize("batching", [True, False])
+def test_simplex_eq_has_the_reference_padded_block_semantics(batching):
+    """`simplex_eq` through the objective depends on the padded length of the reference's length buckets
+    (simplex.py:160-161, sparse_utils.py:197-211): with and without batching the reference returns
+    different x for the same column.  Both must be reproduced bit for bit (fixture: tests/golden/make_golden_r2.py)."""
+    d, ptype, params = load_case("simplex_eq")
+    n = d["ccol"].size - 1
+    tag = "b1" if batching else "b0"
+    assert not np.array_equal(d["x_b1"], d["x_b0"])
+    A, C = _csc(d)
+    obj = MatchingSolverDualObjectiveFunction(
+        MatchingInputArgs(A, C, create_projection_map(ptype, params, n), torch.from_numpy(d["b"]).to(DEV)),
+        gamma=float(d["gamma"]), batching=batching)
+    r = obj.calculate(torch.from_numpy(d["lam"]).to(DEV), save_primal=True)
+    assert np.array_equal(r.primal_var.cpu().numpy(), d[f"x_{tag}"])
+    assert abs(r.scalars64.cpu().numpy()[0] - d[f"scal_{tag}"][0]) <= 1e-5 * abs(d[f"scal_{tag}"][0])
+    assert np.allclose(r.dual_gradient.cpu().numpy(), d[f"grad_{tag}"], rtol=1e-5, atol=1e-4)
+    # and on a map with an identity class in front (class ids shift by one), against the per-column C oracle
+    pm = create_projection_map(ptype, params, n, indices=list(range(n - 5)))
+    obj2 = MatchingSolverDualObjectiveFunction(MatchingInputArgs(A, C, pm, torch.from_numpy(d["b"]).to(DEV)),
+                                               gamma=float(d["gamma"]), batching=batching)
+    r2 = obj2.calculate(torch.from_numpy(d["lam"]).to(DEV), save_primal=True)
+    pad = O.pad_table(d["ccol"], int(d["n_rows"]), [O.ProjEntry(ptype, params, np.arange(n - 5))], batching)
+    rc = c_oracle.calculate(d["ccol"], d["row"], d["a"], d["c"], int(d["n_rows"]),
+                            [c_oracle.make_class("identity", {}), c_oracle.make_class(ptype, params)], d["lam"], float(d["gamma"]),
+                            d["b"], col_class=(np.arange(n) < n - 5).astype(np.uint8), pad_len=np.vstack([np.zeros(32, np.int32), pad[0]]))
+    assert np.array_equal(r2.primal_var.cpu().numpy(), rc["x"])
+
+
 def test_reference_known_answer_through_fused_maximizer():
     """Reference tests/objectives/test_dualip_matching_simplex.py:102-141 on the GPU path."""
     from test_oracle_golden import _scala_5x5
