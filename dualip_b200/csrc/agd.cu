@@ -302,7 +302,8 @@ __global__ void __launch_bounds__(1024) agd_step_peer_kernel(const AgdStepArgs A
     if (blockIdx.x == 0) st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.win[tid]) + P.rank, P.seq);
     const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(P.win[P.rank]) + tid;
     const unsigned long long t0 = global_timer_ns();
-    while (ld_relaxed_sys_u64(mine) < P.seq) {
+    // once a wait has timed out the run is invalid (the host raises): later steps must not wait the full time-out again
+    while (*reinterpret_cast<volatile int*>(P.status) == 0 && ld_relaxed_sys_u64(mine) < P.seq) {
       if (global_timer_ns() - t0 > P.timeout_ns) {
         *P.status = 1;
         break;
