@@ -10,7 +10,8 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libdualip_b200.so")
+# DUALIP_B200_LIB: an alternative build of the same library (kernel A/B experiments); never a different implementation
+LIB_PATH = os.environ.get("DUALIP_B200_LIB") or os.path.join(_HERE, "_lib", "libdualip_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 OK, EINVAL, ECUDA, ENOMEM, ERANGE = 0, -1, -2, -3, -4

@@ -12,6 +12,9 @@
 // its 32*d values in CHUNKS of four entries per column: entry k of column `lane` sits at
 //     (k & ~3)*32 + lane*4 + (k & 3)                      for k < (d & ~3)        (one 16-byte vector per lane and chunk)
 // and the d & 3 trailing entries form a 2-entry chunk (lane*2 + j) and/or a 1-entry chunk (lane); see slab_elem().
+// The three arrays of a slab are stored back to back -- [a: 32 d floats][c: 32 d floats][row: 32 d ids], 320 d bytes with
+// uint16 ids -- so that ONE bulk copy (TMA engine) moves a whole slab into shared memory; slabs follow each other in
+// (class, length) order, and a small group table {first slab, first row, d, class} replaces per-slab headers in the hot loop.
 // A warp owns a slab and a lane owns a column: one LDG.128 per lane fetches four entries of a (or c), one LDG.64
 // four uint16 row ids, every request is fully coalesced (512 contiguous bytes per warp instruction), all per-column
 // reductions are register arithmetic without shuffles, and lanes never diverge on column length or projection
@@ -52,7 +55,9 @@ constexpr uint32_t kKeyLong = (255u << kDegBits) | 2046u;
 constexpr int kKeyBits = 19;
 constexpr int kMaxClasses = 255;
 constexpr size_t kSmemBudget = 227 * 1024;
-constexpr int kThreads = 512;         // one CTA of 16 warps per SM: up to 128 registers per thread for the register path
+constexpr int kStageSlots = 2;        // slots of a warp's staging region = its mbarriers
+constexpr int kThreads = 512;
+constexpr int kBarBytes = (kThreads / 32) * kStageSlots * 8;  // slot mbarriers of all warps         // one CTA of 16 warps per SM: up to 128 registers per thread for the register path
 
 struct SlabHdr {      // 8 bytes per slab (per 32*d nonzeros)
   uint32_t off32;     // first row of the slab in units of 32 elements
@@ -69,6 +74,21 @@ __host__ __device__ __forceinline__ uint32_t slab_elem(int k, int d, int lane) {
   if (kr < two) return (uint32_t)(full * 32 + lane * 2 + kr);
   return (uint32_t)(full * 32 + two * 32 + lane);
 }
+
+// One (class, column length) group: n_slabs consecutive slabs of 32 columns of d entries each (the last one may hold
+// fewer columns).  Slab j of the group starts at row32 = off32_begin + j * d, i.e. at byte (off32_begin + j*d) * row_bytes.
+struct SlabGroup {       // 16 bytes
+  uint32_t slab_begin;   // index of the group's first slab
+  uint32_t off32_begin;  // its first row of 32 elements
+  uint16_t d;            // entries per column
+  uint8_t cls;           // projection class
+  uint8_t last_ncols;    // columns in the group's last slab (1..32)
+  uint32_t n_slabs;
+};
+constexpr int kMaxSmemGroups = 128;  // group tables up to this size are copied to shared memory
+
+// bytes of one row of 32 entries: a + c + row id
+__host__ __device__ constexpr int row32_bytes(int row_bits) { return 32 * (8 + row_bits / 8); }
 
 struct LongCol {
   int64_t src_start;  // position of the column's first entry in the caller's CSC value order
@@ -87,10 +107,10 @@ struct dualip_plan {
   int32_t m = 0;
   int row_bits = 32;
   // slabs (owned)
-  float* a_t = nullptr;
-  float* c_t = nullptr;
-  void* row_t = nullptr;
-  SlabHdr* hdr = nullptr;
+  unsigned char* data = nullptr;  // slabs back to back, row32_bytes(row_bits) bytes per row of 32 entries
+  SlabGroup* groups = nullptr;    // n_groups entries
+  int n_groups = 0;
+  SlabHdr* hdr = nullptr;         // per-slab headers (plan-time kernels, tests); not read by the hot kernel
   int64_t* orig_start = nullptr;  // per slab lane: first nnz position of the column in the caller's order, or -1
   int64_t n_slabs = 0;
   int64_t rows32 = 0;             // total slab rows (32 elements each)
@@ -124,7 +144,7 @@ struct dualip_plan {
   size_t smem_bytes = 0;
   size_t owned_bytes = 0;
   int flush_bulk = 1;
-  int prefetch = 0;
+  int stage_region = 0;        // staging bytes per warp
   unsigned long long* timeline = nullptr;  // debug only
   int stage = 0;               // longest column whose slab is TMA-staged (0: staging off / does not fit)
 };
@@ -164,7 +184,7 @@ __global__ void fill_slabs_kernel(const IdxT* __restrict__ ccol, const IdxT* __r
                                   const float* __restrict__ c, const uint32_t* __restrict__ perm, int64_t n_short,
                                   const int64_t* __restrict__ g_start, const int64_t* __restrict__ g_slab_base,
                                   const int64_t* __restrict__ g_off32, const uint32_t* __restrict__ g_key, int n_groups,
-                                  float* __restrict__ a_t, float* __restrict__ c_t, RowT* __restrict__ row_t,
+                                  unsigned char* __restrict__ data,
                                   SlabHdr* __restrict__ hdr, int64_t* __restrict__ orig_start, int32_t m,
                                   unsigned int* bad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,8 +206,12 @@ __global__ void fill_slabs_kernel(const IdxT* __restrict__ ccol, const IdxT* __r
   const int64_t off32 = g_off32[g] + (rel / kSlabW) * d;
   const uint32_t col = perm[i];
   const int64_t e0 = (int64_t)ccol[col];
+  unsigned char* slab_bytes = data + (size_t)off32 * (size_t)row32_bytes(8 * (int)sizeof(RowT));
+  float* a_t = reinterpret_cast<float*>(slab_bytes);
+  float* c_t = a_t + (size_t)d * kSlabW;
+  RowT* row_t = reinterpret_cast<RowT*>(c_t + (size_t)d * kSlabW);
   for (int k = 0; k < d; ++k) {
-    const int64_t dst = off32 * kSlabW + slab_elem(k, d, lane);
+    const uint32_t dst = slab_elem(k, d, lane);
     const IdxT r = row[e0 + k];
     if (r < 0 || r >= (IdxT)m) atomicOr(bad, 1u);
     a_t[dst] = a[e0 + k];
@@ -244,10 +268,9 @@ __global__ void long_copy_kernel(const LongCol* __restrict__ cols, int64_t n_lon
 // Hot kernel
 // ------------------------------------------------------------------------------------------
 struct KArgs {
-  const float* a_t;
-  const float* c_t;
-  const void* row_t;
-  const SlabHdr* hdr;
+  const unsigned char* data;   // slabs back to back
+  const SlabGroup* groups;
+  int n_groups;
   const int64_t* orig_start;
   int64_t n_slabs;
   const dualip_proj_class* classes;
@@ -274,7 +297,7 @@ struct KArgs {
   int do_epilogue;           // 1: calc (grad/scalars), 0: partial (packed sums)
   int stage;                 // slabs of up to this many entries per column are TMA-staged (per-warp buffer + mbarrier); 0: off
   unsigned long long* timeline;  // debug (DUALIP_TIMELINE=1): per CTA 5 x {clock64, globaltimer}, or null
-  int prefetch;              // L2 prefetch of each warp's next slab: 0 off, 1 bulk (TMA engine), 2 per-line
+  int stage_region;          // bytes of staging buffer per warp (multiple of 512), cut into 4 / 2 / 1 slots
   const float* long_a;
   const float* long_c;
   const uint32_t* long_row;
@@ -447,13 +470,15 @@ __device__ __forceinline__ void cta_epilogue(SumFn sum_load, ClearFn sum_clear, 
 template <bool ROW16, int SMODE, int ACC, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArgs k) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // carve: [mbarrier 16B][per-warp mbarriers 128B][classes][scratch 32 doubles + 32 floats][s_lam m_pad floats]
+  // carve: [mbarrier 16B][per-warp slot mbarriers 512B][classes][scratch 32 doubles + 32 floats][s_lam m_pad floats]
   //        [s_grad m_pad floats][per-warp stash (generic path) or per-warp staging buffers (register path)]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* wbar = reinterpret_cast<uint64_t*>(smem_raw + 16);
-  dualip_proj_class* s_cls = reinterpret_cast<dualip_proj_class*>(smem_raw + 16 + 128);
+  dualip_proj_class* s_cls = reinterpret_cast<dualip_proj_class*>(smem_raw + 16 + kBarBytes);
   const int n_cls_bytes = ((k.n_classes * (int)sizeof(dualip_proj_class)) + 15) & ~15;
-  double* dscratch = reinterpret_cast<double*>(smem_raw + 16 + 128 + n_cls_bytes);
+  SlabGroup* s_grp = reinterpret_cast<SlabGroup*>(smem_raw + 16 + kBarBytes + n_cls_bytes);
+  const int n_grp_bytes = (k.n_groups <= kMaxSmemGroups ? k.n_groups : 0) * (int)sizeof(SlabGroup);
+  double* dscratch = reinterpret_cast<double*>(smem_raw + 16 + kBarBytes + n_cls_bytes + n_grp_bytes);
   float* fscratch = reinterpret_cast<float*>(dscratch + 32);
   float* s_lam = fscratch + 32;
   const int m = k.m;
@@ -486,7 +511,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     bulk_ok = ((reinterpret_cast<uintptr_t>(k.lambda) & 15u) == 0) && bulk_bytes >= 16;
     if (tid == 0) {
       mbar_init(bar, 1);
-      for (int w = 0; w < THREADS / 32; ++w) mbar_init(wbar + w, 1);
+      for (int w = 0; w < (THREADS / 32) * kStageSlots; ++w) mbar_init(wbar + w, 1);
       fence_mbar_init();
     }
     __syncthreads();
@@ -497,6 +522,9 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   }
   for (int i = tid; i < k.n_classes * (int)(sizeof(dualip_proj_class) / 4); i += THREADS)
     reinterpret_cast<uint32_t*>(s_cls)[i] = reinterpret_cast<const uint32_t*>(k.classes)[i];
+  if (k.n_groups <= kMaxSmemGroups)
+    for (int i = tid; i < k.n_groups * (int)(sizeof(SlabGroup) / 4); i += THREADS)
+      reinterpret_cast<uint32_t*>(s_grp)[i] = reinterpret_cast<const uint32_t*>(k.groups)[i];
   if (SMODE <= 1)
     for (int i = tid; i < m; i += THREADS) s_grad[i] = 0.f;
   if (SMODE == 0) {
@@ -513,95 +541,86 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
 
   stamp(1);
   // ---- stream slabs: warp w of the grid takes slabs w, w + W, w + 2W, ... (neighbouring warps read neighbouring
-  //      slabs, and every warp sees the same mix of column lengths) ----
+  //      slabs, and every warp sees the same mix of column lengths).  Slabs are visited group by group: inside a
+  //      (class, length) group the slab addresses advance by a constant stride and the code is specialised on the length,
+  //      so the per-slab bookkeeping is a pointer increment ----
   double cx = 0.0, xx = 0.0;
-  const int64_t total_warps = (int64_t)gridDim.x * NW;
+  const int W = (int)gridDim.x * NW;
   const bool want_out = (k.x_out != nullptr) || (k.diag != nullptr);
   const float s = k.s;
   using RowT = typename std::conditional<ROW16, unsigned short, uint32_t>::type;
-  const RowT* row_all = reinterpret_cast<const RowT*>(k.row_t);
-  int64_t sl = (int64_t)blockIdx.x * NW + warp;
-  // slab headers are fetched two slabs ahead: the next slab's header is needed NOW (to start its staging copy)
-  uint2 hnext = make_uint2(0u, 0u), hnext2 = make_uint2(0u, 0u);
-  if (sl < k.n_slabs) hnext = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl);
-  if (sl + total_warps < k.n_slabs) hnext2 = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl + total_warps);
-  // TMA staging (register path): while a warp works on a slab, the engine copies its next slab into the warp's buffer
+  constexpr uint32_t RB = (uint32_t)row32_bytes(ROW16 ? 16 : 32);  // bytes per row of 32 entries
+  const int n_slabs = (int)k.n_slabs;
+  const int sl0 = (int)blockIdx.x * NW + warp;
+  const SlabGroup* __restrict__ grp = (k.n_groups <= kMaxSmemGroups) ? s_grp : k.groups;
+  // TMA staging (register path): every warp owns a region of shared memory and two mbarriers.  Slabs of up to half the
+  // region are staged two deep (slot = t mod 2, t = the warp's running slab count): while the warp works on slab t the
+  // engine copies slabs t+1 and t+2; longer slabs take the whole region, one at a time.  ONE bulk copy per slab.
   const bool use_stage = FAST && (k.stage != 0);
-  unsigned char* my_stage = s_stage + (size_t)warp * (((size_t)k.stage * 320 + 127) & ~(size_t)127);
-  uint64_t* my_bar = wbar + warp;
-  uint32_t stage_phase = 0;
-  bool cur_staged = false;
-  auto stage_slab = [&](const uint2 h) {  // h: header of a slab with d <= k.stage
-    if (lane == 0) {
-      const size_t nb = (size_t)h.x * kSlabW;
-      stage_issue(my_stage, my_bar, k.a_t + nb, k.c_t + nb, reinterpret_cast<const unsigned short*>(k.row_t) + nb,
-                  (int)(h.y & 0xffffu));
+  const uint32_t region = (uint32_t)k.stage_region;  // bytes per warp, multiple of 512
+  unsigned char* my_stage = s_stage + (size_t)warp * region;
+  uint64_t* my_bars = wbar + warp * kStageSlots;
+  uint32_t phases = 0;  // phase bit per slot barrier
+  // producer cursor: the next slab to hand to the engine (it runs ahead of the consumer, across group boundaries)
+  int p_sl = sl0, p_g = 0, p_t = 0, p_end = 0, p_big = -1;
+  uint32_t p_bytes = 0;
+  uint32_t p_off = 0, p_stride = 0;  // in rows of 32 entries (RB bytes each)
+  auto p_enter_group = [&]() {  // p_sl < n_slabs
+    while (p_sl >= (int)(grp[p_g].slab_begin + grp[p_g].n_slabs)) ++p_g;
+    const SlabGroup G = grp[p_g];
+    p_end = (int)(G.slab_begin + G.n_slabs);
+    p_bytes = (uint32_t)G.d * RB;
+    p_off = G.off32_begin + (uint32_t)(p_sl - (int)G.slab_begin) * G.d;
+    p_stride = (uint32_t)W * G.d;
+    if (G.d > kRegDeg) p_bytes = 0xffffffffu;  // generic path: never staged
+  };
+  // t_free: slabs < t_free (running count) have left their slots
+  auto top_up = [&](int t_free) {
+    while (p_sl < n_slabs) {
+      if (p_sl >= p_end) p_enter_group();
+      if (!use_stage || p_bytes > region) {  // not staged: the cursor just moves on (at most one slab ahead)
+        if (p_t > t_free) break;
+      } else if (p_bytes * 2u <= region) {   // two deep
+        if (p_big >= t_free || p_t > t_free + 1) break;
+        if (lane == 0) stage_issue(my_stage + (p_t & 1) * (region >> 1), my_bars + (p_t & 1), k.data + (size_t)p_off * RB, p_bytes);
+      } else {                               // whole region: only into an empty pipeline
+        if (p_t != t_free) break;
+        if (lane == 0) stage_issue(my_stage, my_bars, k.data + (size_t)p_off * RB, p_bytes);
+        p_big = p_t;
+      }
+      ++p_t;
+      p_sl += W;
+      p_off += p_stride;
     }
   };
-  if (use_stage && sl < k.n_slabs && (int)(hnext.y & 0xffffu) <= k.stage) {
-    stage_slab(hnext);
-    cur_staged = true;
-  }
-  for (; sl < k.n_slabs; sl += total_warps) {
-    unsigned long long* trace = nullptr;
-    if (k.timeline != nullptr && warp == 0 && lane == 0 && blockIdx.x == 0) {  // debug: per-slab trace
-      const int64_t it = (sl - ((int64_t)blockIdx.x * NW + warp)) / total_warps;
-      if (it < 1024) {
-        k.timeline[10 * 4096 + it] = (unsigned long long)clock64();
-        k.timeline[11 * 4096 + it] = (unsigned long long)hnext.y;
-        trace = k.timeline + 10 * 4096 + 1024 + 4 * it;  // [arrived, projected, -, -]
-      }
-    }
-    const uint2 hraw = hnext;
-    hnext = hnext2;
-    if (sl + 2 * total_warps < k.n_slabs) hnext2 = __ldg(reinterpret_cast<const uint2*>(k.hdr) + sl + 2 * total_warps);
-    const int d = (int)(hraw.y & 0xffffu);
-    const int cls = (int)((hraw.y >> 16) & 0xffu);
-    const bool active = lane < (int)(hraw.y >> 24);
-    const size_t base = (size_t)hraw.x * kSlabW;  // the slab's first element
-    const float* __restrict__ pa = k.a_t + base;
-    const float* __restrict__ pcv = k.c_t + base;
-    const RowT* __restrict__ pr = row_all + base;
+  int sl = sl0, g = 0, t = 0;
+  while (sl < n_slabs) {
+    while (sl >= (int)(grp[g].slab_begin + grp[g].n_slabs)) ++g;
+    const SlabGroup G = grp[g];
+    const int d = (int)G.d, cls = (int)G.cls;
+    const int g_end = (int)(G.slab_begin + G.n_slabs);
+    uint32_t boff = G.off32_begin + (uint32_t)(sl - (int)G.slab_begin) * G.d;  // in rows of 32 entries
     const dualip_proj_class pc = s_cls[cls];
-    if (k.prefetch && sl + total_warps < k.n_slabs) {
-      // pull this warp's NEXT slab into L2 while the current one is processed
-      const size_t nb = (size_t)hnext.x * kSlabW;
-      const uint32_t ne = (hnext.y & 0xffffu) * (uint32_t)kSlabW;
-      if (k.prefetch == 1) {  // three bulk requests to the TMA engine
-        if (lane == 0) {
-          prefetch_l2_bulk(k.a_t + nb, ne * 4u);
-          prefetch_l2_bulk(k.c_t + nb, ne * 4u);
-          prefetch_l2_bulk(row_all + nb, ne * (uint32_t)sizeof(RowT));
-        }
-      } else {  // one 128-byte line per lane and request
-        const uint32_t la = (ne * 4u + 127u) >> 7, lr = (ne * (uint32_t)sizeof(RowT) + 127u) >> 7;
-        for (uint32_t i = lane; i < 2 * la + lr; i += 32) {
-          const char* q = i < la ? reinterpret_cast<const char*>(k.a_t + nb) + ((size_t)i << 7)
-                                 : (i < 2 * la ? reinterpret_cast<const char*>(k.c_t + nb) + ((size_t)(i - la) << 7)
-                                               : reinterpret_cast<const char*>(row_all + nb) + ((size_t)(i - 2 * la) << 7));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-        }
-      }
-    }
-    const bool have_next = sl + total_warps < k.n_slabs;
-    const bool next_staged = use_stage && have_next && (int)(hnext.y & 0xffffu) <= k.stage;
-    const bool staged = cur_staged;
-    cur_staged = next_staged;
-    auto issue_next = [&]() {
-      if (next_staged) {
-        __syncwarp();
-        stage_slab(hnext);
-      }
-    };
     if (FAST && d <= kRegDeg) {
       // ---- register path: the whole column lives in registers, code specialised on d ----
+      const uint32_t stride = (uint32_t)W * G.d;
       const unsigned char* s_lam_b = reinterpret_cast<const unsigned char*>(s_lam);
-      const unsigned short* pr16 = reinterpret_cast<const unsigned short*>(pr);
+      StageCtx st{use_stage, region, my_stage, my_bars};
+      auto ensure_issued = [&](int tt) {
+        if (p_t <= tt) top_up(tt);
+      };
+      auto after_load = [&](int tt) {  // slab tt is in registers: its slot is free
+        __syncwarp();
+        top_up(tt + 1);
+      };
       switch (d) {
-#define DUALIP_FAST_CASE(DD)                                                                              \
-  case DD:                                                                                                \
-    fast_slab<DD, SMODE, ACC>(k, pc, cls, pa, pcv, pr16, lane, active, s_lam_b, s_grad_u32, s, sl, cx,   \
-                              xx, staged, my_stage, my_bar, stage_phase, issue_next, trace);             \
+#define DUALIP_FAST_CASE(DD)                                                                                        \
+  case DD:                                                                                                          \
+    for (; sl < g_end; sl += W, boff += stride, ++t) {                                                              \
+      const bool active = lane < ((sl == g_end - 1) ? (int)G.last_ncols : 32);                                      \
+      fast_slab<DD, SMODE, ACC>(k, pc, cls, k.data + (size_t)boff * RB, lane, active, s_lam_b, s_grad_u32, s, sl, t, cx, xx, st, \
+                                phases, ensure_issued, after_load);                                                 \
+    }                                                                                                               \
     break;
         DUALIP_FAST_CASE(1)
         DUALIP_FAST_CASE(2)
@@ -629,6 +648,15 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       }
       continue;
     }
+    // ---- generic path: one slab per turn of the outer loop ----
+    const bool active = lane < ((sl == g_end - 1) ? (int)G.last_ncols : 32);
+    const float* __restrict__ pa = reinterpret_cast<const float*>(k.data + (size_t)boff * RB);
+    const float* __restrict__ pcv = pa + (size_t)d * kSlabW;
+    const RowT* __restrict__ pr = reinterpret_cast<const RowT*>(pcv + (size_t)d * kSlabW);
+    auto issue_next = [&]() {
+      __syncwarp();
+      top_up(t + 1);
+    };
     issue_next();  // the generic path does not use the staging buffer
     auto ld1 = [&](int kq, float& av, float& cv, uint32_t& rv) {
       const uint32_t o = slab_elem(kq, d, lane);
@@ -940,7 +968,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
 
     if (want_out && active) {
       // ---- primal / diagnostics output (save_primal on the last iteration, tests): plain re-stream ----
-      const int64_t os = k.orig_start[sl * kSlabW + lane];
+      const int64_t os = k.orig_start[(int64_t)sl * kSlabW + lane];
       if (k.x_out) {
         for (int kq = 0; kq < d; ++kq) {
           float a, c;
@@ -961,6 +989,8 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       }
       if (k.diag && branch >= 0) k.diag[os] = (uint8_t)(branch | (min(rho, 63) << 2));
     }
+    sl += W;
+    ++t;
   }
 
   // ---- flush per-CTA partial sums ----
@@ -1223,7 +1253,7 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(const float* sum, int m,
 // kernel (warp w of CTA b takes slabs b*NW + w, + gridDim*NW, ...).  |a * x| <= |a| * xmax(class).
 // ------------------------------------------------------------------------------------------
 template <typename RowT>
-__global__ void cta_row_bound_kernel(const float* __restrict__ a_t, const RowT* __restrict__ row_t,
+__global__ void cta_row_bound_kernel(const unsigned char* __restrict__ data,
                                      const SlabHdr* __restrict__ hdr, int64_t n_slabs, const float* __restrict__ cls_xmax,
                                      int m, float* __restrict__ table, unsigned int* __restrict__ row_cnt) {
   extern __shared__ __align__(16) unsigned char bound_smem[];
@@ -1240,9 +1270,10 @@ __global__ void cta_row_bound_kernel(const float* __restrict__ a_t, const RowT* 
     const SlabHdr h = hdr[sl];
     if (lane >= (int)h.ncols) continue;
     const float xmax = cls_xmax[h.cls];
-    const size_t base = (size_t)h.off32 * kSlabW;
+    const float* a_t = reinterpret_cast<const float*>(data + (size_t)h.off32 * (size_t)row32_bytes(8 * (int)sizeof(RowT)));
+    const RowT* row_t = reinterpret_cast<const RowT*>(a_t + 2 * (size_t)h.d * kSlabW);
     for (int k = 0; k < (int)h.d; ++k) {
-      const size_t idx = base + slab_elem(k, (int)h.d, lane);
+      const uint32_t idx = slab_elem(k, (int)h.d, lane);
       const uint32_t r = (uint32_t)row_t[idx];
       atomicAdd(&s_bound[r], fabsf(a_t[idx]) * xmax);
       atomicAdd(&s_cnt[r], 1u);
@@ -1305,7 +1336,8 @@ static SlabKernel plan_kernel(const dualip_plan* p) {
 }
 
 static size_t smem_fixed_bytes(int n_classes) {
-  return 16 + 128 + (((size_t)n_classes * sizeof(dualip_proj_class) + 15) & ~(size_t)15) + 32 * sizeof(double) + 32 * sizeof(float);
+  return 16 + kBarBytes + (((size_t)n_classes * sizeof(dualip_proj_class) + 15) & ~(size_t)15) + kMaxSmemGroups * sizeof(SlabGroup) +
+         32 * sizeof(double) + 32 * sizeof(float);
 }
 
 static int launch_eval(dualip_plan* p, const float* lambda, const float* b, double gamma, float* grad_out,
@@ -1316,10 +1348,9 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
     return DUALIP_EINVAL;
   }
   KArgs k;
-  k.a_t = p->a_t;
-  k.c_t = p->c_t;
-  k.row_t = p->row_t;
-  k.hdr = p->hdr;
+  k.data = p->data;
+  k.groups = p->groups;
+  k.n_groups = p->n_groups;
   k.orig_start = p->orig_start;
   k.n_slabs = p->n_slabs;
   k.classes = p->classes_dev;
@@ -1344,7 +1375,7 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.s = (float)(-1.0 / gamma);
   k.flush_bulk = p->flush_bulk;
   k.do_epilogue = do_epilogue;
-  k.prefetch = p->prefetch;
+  k.stage_region = p->stage_region;
   k.timeline = p->timeline;
   k.stage = p->stage;
   k.long_a = p->long_a;
@@ -1477,17 +1508,12 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
     return DUALIP_ERANGE;
   }
   // slab storage
-  const size_t elems = (size_t)std::max<int64_t>(p->rows32, 1) * kSlabW;
-  const size_t row_bytes = (size_t)(p->row_bits / 8) * elems;
-  BS_TRY(cudaMalloc(&p->a_t, sizeof(float) * elems));
-  BS_TRY(cudaMalloc(&p->c_t, sizeof(float) * elems));
-  BS_TRY(cudaMalloc(&p->row_t, row_bytes));
+  const size_t data_bytes = (size_t)std::max<int64_t>(p->rows32, 1) * (size_t)row32_bytes(p->row_bits);
+  BS_TRY(cudaMalloc(&p->data, data_bytes + 512));  // + slack: vector loads of a partially filled last slab stay inside
   BS_TRY(cudaMalloc(&p->hdr, sizeof(SlabHdr) * std::max<int64_t>(p->n_slabs, 1)));
   BS_TRY(cudaMalloc(&p->orig_start, sizeof(int64_t) * std::max<int64_t>(p->n_slabs, 1) * kSlabW));
-  p->owned_bytes += 8 * elems + row_bytes + (sizeof(SlabHdr) + 8 * kSlabW) * (size_t)std::max<int64_t>(p->n_slabs, 1);
-  BS_TRY(cudaMemsetAsync(p->a_t, 0, sizeof(float) * elems, stream));
-  BS_TRY(cudaMemsetAsync(p->c_t, 0, sizeof(float) * elems, stream));
-  BS_TRY(cudaMemsetAsync(p->row_t, 0, row_bytes, stream));
+  p->owned_bytes += data_bytes + (sizeof(SlabHdr) + 8 * kSlabW) * (size_t)std::max<int64_t>(p->n_slabs, 1);
+  BS_TRY(cudaMemsetAsync(p->data, 0, data_bytes + 512, stream));
   BS_TRY(cudaMemsetAsync(p->orig_start, 0xff, sizeof(int64_t) * std::max<int64_t>(p->n_slabs, 1) * kSlabW, stream));
   if (n_short > 0) {
     const int G = (int)groups.size();
@@ -1511,12 +1537,26 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
     const unsigned nb = (unsigned)((n_short + tb - 1) / tb);
     if (p->row_bits == 16)
       fill_slabs_kernel<IdxT, unsigned short><<<nb, tb, 0, stream>>>(ccol, row, d->a_dev, d->c_dev, perm, n_short, g_start_d,
-                                                                      g_slab_d, g_off_d, g_key_d, G, p->a_t, p->c_t,
-                                                                      (unsigned short*)p->row_t, p->hdr, p->orig_start, p->m, bad);
+                                                                      g_slab_d, g_off_d, g_key_d, G, p->data, p->hdr,
+                                                                      p->orig_start, p->m, bad);
     else
       fill_slabs_kernel<IdxT, uint32_t><<<nb, tb, 0, stream>>>(ccol, row, d->a_dev, d->c_dev, perm, n_short, g_start_d, g_slab_d,
-                                                                g_off_d, g_key_d, G, p->a_t, p->c_t, (uint32_t*)p->row_t,
-                                                                p->hdr, p->orig_start, p->m, bad);
+                                                                g_off_d, g_key_d, G, p->data, p->hdr, p->orig_start, p->m,
+                                                                bad);
+    // group table of the hot kernel
+    std::vector<SlabGroup> gt(G);
+    for (int i = 0; i < G; ++i) {
+      const int64_t ns = (groups[i].count + kSlabW - 1) / kSlabW;
+      gt[i].slab_begin = (uint32_t)groups[i].slab_base;
+      gt[i].off32_begin = (uint32_t)groups[i].off32;
+      gt[i].d = (uint16_t)(groups[i].key & ((1u << kDegBits) - 1));
+      gt[i].cls = (uint8_t)(groups[i].key >> kDegBits);
+      gt[i].last_ncols = (uint8_t)(groups[i].count - (ns - 1) * kSlabW);
+      gt[i].n_slabs = (uint32_t)ns;
+    }
+    BS_TRY(cudaMalloc(&p->groups, sizeof(SlabGroup) * G));
+    BS_TRY(cudaMemcpyAsync(p->groups, gt.data(), sizeof(SlabGroup) * G, cudaMemcpyHostToDevice, stream));
+    p->n_groups = G;
     BS_TRY(cudaStreamSynchronize(stream));  // host vectors go out of scope
   }
   if (n_long > 0) {
@@ -1610,7 +1650,7 @@ static int choose_accumulator(dualip_plan* p, cudaStream_t stream) {
     const size_t bsm = 8 * (size_t)m;  // fits: mode 0 already keeps 8*m bytes of lambda + accumulator in shared memory
     CA_TRY(cudaFuncSetAttribute((const void*)cta_row_bound_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
     cta_row_bound_kernel<unsigned short><<<p->n_ctas, p->threads, bsm, stream>>>(
-        p->a_t, reinterpret_cast<const unsigned short*>(p->row_t), p->hdr, p->n_slabs, xmax_d, m, table, row_cnt);
+        p->data, p->hdr, p->n_slabs, xmax_d, m, table, row_cnt);
   }
   if (p->n_long > 0) {
     const int blocks = (int)std::min<int64_t>((p->n_long + 7) / 8, (int64_t)p->n_sms * 8);
@@ -1668,9 +1708,8 @@ const char* dualip_last_error(void) { return g_last_error.c_str(); }
 void dualip_plan_destroy(dualip_plan* p) {
   if (!p) return;
   DeviceGuard g(p->device);
-  cudaFree(p->a_t);
-  cudaFree(p->c_t);
-  cudaFree(p->row_t);
+  cudaFree(p->data);
+  cudaFree(p->groups);
   cudaFree(p->hdr);
   cudaFree(p->orig_start);
   cudaFree(p->longcols);
@@ -1747,8 +1786,6 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
     if (cudaMalloc(&p->timeline, sizeof(unsigned long long) * 12 * 4096) != cudaSuccess) p->timeline = nullptr;
     if (p->timeline) cudaMemset(p->timeline, 0, sizeof(unsigned long long) * 12 * 4096);
   }
-  const char* pf = getenv("DUALIP_PREFETCH");
-  p->prefetch = pf ? atoi(pf) : 0;
 
   auto fail = [&](int rc) {
     dualip_plan_destroy(p);
@@ -1770,21 +1807,25 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   const size_t fixed = smem_fixed_bytes(p->n_classes);
   const size_t m_pad = ((size_t)p->m + 3) & ~(size_t)3;
   const size_t stash_bytes = (size_t)(p->threads / 32) * kStashDeg * kSlabW * sizeof(float);
-  // TMA staging of the register-path slabs pays off on large shards only: measured on B200 (profiles/r1_stage_sweep.txt),
-  // staged vs plain vector loads is 0.67 vs 0.70 of the roofline at 1e8 nonzeros, 0.78 vs 0.72 at 2e8, 0.90 vs 0.76 at 1e9.
+  // TMA staging of the register-path slabs: every warp gets an equal share of the shared memory that lambda and the
+  // accumulator leave free, cut into 4 / 2 / 1 slots by column length (see the kernel).  DUALIP_STAGE=0 disables it.
   const char* env_stage = getenv("DUALIP_STAGE");
-  int stage_deg = env_stage ? atoi(env_stage) : (p->nnz >= kStageMinNnz ? kRegDeg : 0);
+  int stage_deg = env_stage ? atoi(env_stage) : kRegDeg;
   stage_deg = std::max(0, std::min(stage_deg, kRegDeg));
-  const size_t stage_bytes = (size_t)(p->threads / 32) * (((size_t)stage_deg * 320 + 127) & ~(size_t)127) + 128;
   p->row_bits = (p->m <= 65536) ? 16 : 32;
-  const size_t smem_max = std::min<size_t>(kSmemBudget, prop.sharedMemPerBlockOptin) - 1024;  // static smem + slack
-  const bool want_stage = stage_deg > 0;
+  const size_t smem_max = std::min<size_t>(kSmemBudget, prop.sharedMemPerBlockOptin) - 2560;  // static smem (1920 B) + slack
   const size_t need1 = fixed + 4 * m_pad + stash_bytes;
-  // mode 0 (register path): lambda + accumulator, plus the per-warp TMA staging buffers when they fit
-  if (p->row_bits == 16 && want_stage && fixed + 8 * m_pad + stage_bytes <= smem_max) {
+  const size_t n_warps = (size_t)(p->threads / 32);
+  size_t region = 0;
+  if (stage_deg > 0 && smem_max > fixed + 8 * m_pad + 128)
+    region = std::min<size_t>(((smem_max - fixed - 8 * m_pad - 128) / n_warps) & ~(size_t)511, ((size_t)2 * 320 * kRegDeg + 511) & ~(size_t)511);
+  if (const char* er = getenv("DUALIP_STAGE_REGION")) region = std::min(region, (size_t)atoi(er) & ~(size_t)511);
+  // mode 0 (register path): lambda + accumulator, plus the per-warp TMA staging regions when at least one slab fits
+  if (p->row_bits == 16 && region >= 320 && fixed + 8 * m_pad + 128 + n_warps * region <= smem_max) {
     p->smode = 0;
     p->stage = stage_deg;
-    p->smem_bytes = fixed + 8 * m_pad + stage_bytes;
+    p->stage_region = (int)region;
+    p->smem_bytes = fixed + 8 * m_pad + 128 + n_warps * region;
   } else if (p->row_bits == 16 && fixed + 8 * m_pad + 128 <= smem_max) {
     p->smode = 0;
     p->stage = 0;

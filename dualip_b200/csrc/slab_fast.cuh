@@ -261,16 +261,18 @@ __device__ __forceinline__ void load_cols_staged(ColRegs<D>& R, uint32_t buf, in
   }
 }
 
-// Staging of a warp's NEXT slab: one lane arms the warp's mbarrier with the slab's byte count and issues three bulk
-// async copies (TMA engine, SASS UBLKCP) global -> shared; they land while the warp works on the current slab.
-constexpr long long kStageMinNnz = 150000000LL;  // shards with fewer nonzeros use plain vector loads (see calc.cu)
-__device__ __forceinline__ void stage_issue(unsigned char* buf, uint64_t* bar, const float* a_s, const float* c_s,
-                                            const unsigned short* r_s, int d) {
-  fence_proxy_async_smem();  // the warp's reads of the buffer (generic proxy) precede the engine's writes
-  mbar_expect_tx(bar, (uint32_t)(320 * d));
-  bulk_g2s(buf, a_s, (uint32_t)(128 * d), bar);
-  bulk_g2s(buf + 128 * d, c_s, (uint32_t)(128 * d), bar);
-  bulk_g2s(buf + 256 * d, r_s, (uint32_t)(64 * d), bar);
+// Staging of one of a warp's upcoming slabs: one lane arms the slot's mbarrier with the slab's byte count and issues ONE
+// bulk async copy (TMA engine, SASS UBLKCP) global -> shared; it lands while the warp works on earlier slabs.
+struct StageCtx {
+  bool use_stage;
+  uint32_t region;        // bytes of this warp's staging region
+  unsigned char* base;    // its first byte
+  uint64_t* bars;         // its two slot barriers
+};
+__device__ __forceinline__ void stage_issue(unsigned char* buf, uint64_t* bar, const unsigned char* slab, uint32_t bytes) {
+  fence_proxy_async_smem();  // the warp's reads of the slot (generic proxy) precede the engine's writes
+  mbar_expect_tx(bar, bytes);
+  bulk_g2s(buf, slab, bytes, bar);
 }
 
 // Shared tail of both projections: scatter a*x into the CTA's gradient accumulator and form the c.x and ||x||^2
@@ -354,6 +356,57 @@ __device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_c
                                              const unsigned char* s_lam_b, float s, float (&u)[D], int& branch, int& rho) {
   const unsigned FULL = 0xffffffffu;
   make_v_cols<D, SMODE>(k, R, s_lam_b, s, u);
+  const float z = pc.z;
+#ifdef DUALIP_SORT_FIRST
+  // Late iterates: nearly every warp holds a column that needs the sorted scan, so the sort is not gated on the top-2
+  // test; the two largest values are then read off the sorted copy instead of being tracked entry by entry.
+  float S = 0.f;
+#pragma unroll
+  for (int q = 0; q < D; ++q) {
+    u[q] = fmaxf(u[q], 0.f);             // simplex.py:148
+    S = __fadd_rn(S, u[q]);              // column sum in entry order
+  }
+  const bool feasible = (pc.kind == DUALIP_PROJ_SIMPLEX) && (S <= pc.z_thr);                          // simplex.py:153-155
+  bool shortcut = false;
+  float m1 = 0.f;
+  float theta = 0.f;
+  bool below = false;
+  float t_below = 0.f;
+  branch = 0;
+  rho = 0;
+  if (__any_sync(FULL, active && !feasible)) {
+    float w[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) w[q] = u[q];
+    SortNet<D>::run(w);
+    m1 = w[0];
+    const float m2p = (D > 1) ? w[1] : 0.f;  // the reference's zero padding takes part in its top-2
+    const bool padded = (D > 1) || !(pc.flags & DUALIP_PROJ_FLAG_D1_UNPADDED);                        // simplex.py:166
+    const float un1 = (z == 1.0f) ? m1 : __fdiv_rn(m1, z), un2 = (z == 1.0f) ? m2p : __fdiv_rn(m2p, z);
+    shortcut = !feasible && padded && (__fsub_rn(un1, un2) > 1.0f);                                   // simplex.py:172-178
+    branch = feasible ? 0 : (shortcut ? 1 : 2);
+    rho = shortcut ? 1 : 0;
+    if (pc.kind == DUALIP_PROJ_SIMPLEX_EQ) {  // see below
+      double sd = 0.0;
+#pragma unroll
+      for (int q = 0; q < D; ++q) sd += (double)u[q];
+      t_below = __fsub_rn((float)sd, z);
+      below = t_below < 0.f;
+    }
+    const bool need_theta = active && branch == 2 && !below;
+    if (__any_sync(FULL, need_theta)) {
+      double acc = 0.0;
+      float t_sel = __fsub_rn(w[0], z);
+      int rho_sel = 1;
+      const bool near = !(S > __fmul_rn(z, 1.0001f));
+      scan_sorted<D, 0>(w, z, acc, t_sel, rho_sel, need_theta, near);
+      if (need_theta) {
+        theta = __fdiv_rn(t_sel, (float)rho_sel);                                                     // simplex.py:228-230
+        rho = rho_sel;
+      }
+    }
+  }
+#else
   float S = 0.f, m1 = -1.f, m2 = -1.f;
 #pragma unroll
   for (int q = 0; q < D; ++q) {
@@ -362,7 +415,6 @@ __device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_c
     m2 = fmaxf(m2, fminf(m1, u[q]));     // second largest (duplicates of the maximum count)
     m1 = fmaxf(m1, u[q]);
   }
-  const float z = pc.z;
   const bool feasible = (pc.kind == DUALIP_PROJ_SIMPLEX) && (S <= pc.z_thr);                          // simplex.py:153-155
   const bool padded = (D > 1) || !(pc.flags & DUALIP_PROJ_FLAG_D1_UNPADDED);                          // simplex.py:166
   const float m2p = fmaxf(m2, 0.f);  // the reference's zero padding takes part in its top-2
@@ -408,6 +460,7 @@ __device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_c
       rho = rho_sel;
     }
   }
+#endif
   if (below) {
     rho = pad_len_of(k, cls, D);
     theta = __fdiv_rn(t_below, (float)rho);
@@ -422,48 +475,40 @@ __device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_c
   for (int q = 0; q < D; ++q) u[q] = fmaxf(__fsub_rn(u[q], theta), 0.f);                             // simplex.py:233
 }
 
-// One slab of column length D, whole life cycle.  a_s/c_s/r_s: the slab's first element in global memory; when
-// `staged` the same bytes are waiting in (or on their way to) the warp's staging buffer.  issue_next() is called as
-// soon as the buffer has been read out, to start the copy of the warp's next slab.
-template <int D, int SMODE, int ACC, typename IssueNext>
-__device__ __forceinline__ void fast_slab(const KArgs& k, const dualip_proj_class& pc, int cls, const float* __restrict__ a_s,
-                                          const float* __restrict__ c_s, const unsigned short* __restrict__ r_s, int lane,
-                                          bool active, const unsigned char* s_lam_b, uint32_t s_grad_u32, float s,
-                                          int64_t slab_index, double& cx, double& xx, bool staged,
-                                          const unsigned char* stage_buf, uint64_t* stage_bar, uint32_t& stage_phase,
-                                          IssueNext issue_next, unsigned long long* trace) {
+// One slab of column length D, whole life cycle.  `slab`: the slab in global memory ([a][c][row ids] back to back); when the
+// slab is staged the same bytes are waiting in (or on their way to) one of the warp's slots.  ensure_issued(t) makes sure
+// the copy of slab t has been requested before the warp waits for it; after_load(t) is called as soon as the slot has been
+// read out, to request further slabs.
+template <int D, int SMODE, int ACC, typename Ensure, typename AfterLoad>
+__device__ __forceinline__ void fast_slab(const KArgs& k, const dualip_proj_class& pc, int cls, const unsigned char* slab,
+                                          int lane, bool active, const unsigned char* s_lam_b, uint32_t s_grad_u32, float s,
+                                          int slab_index, int t, double& cx, double& xx, const StageCtx& st, uint32_t& phases,
+                                          Ensure ensure_issued, AfterLoad after_load) {
+  constexpr uint32_t kBytes = 320u * D;  // uint16 row ids (the register path exists for them only)
+  const float* __restrict__ a_s = reinterpret_cast<const float*>(slab);
+  const float* __restrict__ c_s = a_s + 32 * D;
+  const unsigned short* __restrict__ r_s = reinterpret_cast<const unsigned short*>(c_s + 32 * D);
   ColRegs<D> R;
-  if (staged) {
-    mbar_wait(stage_bar, stage_phase);
-    stage_phase ^= 1u;
-    load_cols_staged<D>(R, smem_u32(stage_buf), lane);
+  if (st.use_stage && kBytes <= st.region) {
+    const bool two_deep = kBytes * 2u <= st.region;
+    const int slot = two_deep ? (t & 1) : 0;
+    ensure_issued(t);
+    mbar_wait(st.bars + slot, (phases >> slot) & 1u);
+    phases ^= 1u << slot;
+    load_cols_staged<D>(R, smem_u32(st.base) + (uint32_t)slot * (st.region >> 1), lane);
   } else {
     load_cols<D>(R, a_s, c_s, r_s, lane);
   }
-  issue_next();
+  after_load(t);
   float x[D];
   int branch = -1, rho = 0;
-  if (trace) {  // debug: time at which the loaded data has arrived
-    float t = 0.f;
-#pragma unroll
-    for (int q = 0; q < D; ++q) t += R.a[q] + R.c[q];
-    if (t == 123.456f) trace[3] = 1;
-    trace[0] = (unsigned long long)clock64();
-  }
   if (pc.kind == DUALIP_PROJ_CLAMP)
     fast_clamp<D, SMODE>(k, pc, R, active, s_lam_b, s, x);
   else
     fast_simplex<D, SMODE>(k, pc, cls, R, active, s_lam_b, s, x, branch, rho);
-  if (trace) {
-    float t = 0.f;
-#pragma unroll
-    for (int q = 0; q < D; ++q) t += x[q];
-    if (t == 123.456f) trace[3] = 1;
-    trace[1] = (unsigned long long)clock64();
-  }
   if ((k.x_out != nullptr) || (k.diag != nullptr)) {  // save_primal / diagnostics: straight from registers
     if (active) {
-      const int64_t os = k.orig_start[slab_index * 32 + lane];
+      const int64_t os = k.orig_start[(int64_t)slab_index * 32 + lane];
       if (k.x_out) {
 #pragma unroll
         for (int q = 0; q < D; ++q) k.x_out[os + q] = x[q];
