@@ -49,9 +49,14 @@ void set_error(const char* fmt, ...) {
 constexpr int kSlabW = 32;            // columns per slab = lanes per warp
 constexpr int kMaxThreadDeg = 1024;   // longest column handled one-lane-per-column
 constexpr int kStashDeg = 16;          // simplex columns up to this length keep u in the warp's shared-memory stash
-constexpr int kDegBits = 11;          // key = class << kDegBits | degree
-constexpr uint32_t kKeyEmpty = (255u << kDegBits) | 2047u;
-constexpr uint32_t kKeyLong = (255u << kDegBits) | 2046u;
+// Sort key of a column: length-major, key = length << 8 | class.  Groups of equal length and different class are
+// neighbours in the slab order, so a contiguous range of slabs holds the same mix of classes as the whole problem.
+constexpr int kClsBits = 8;
+__host__ __device__ constexpr uint32_t make_key(uint32_t cls, uint32_t d) { return (d << kClsBits) | cls; }
+__host__ __device__ constexpr int key_d(uint32_t key) { return (int)(key >> kClsBits); }
+__host__ __device__ constexpr int key_cls(uint32_t key) { return (int)(key & ((1u << kClsBits) - 1)); }
+constexpr uint32_t kKeyEmpty = make_key(255u, 2047u);
+constexpr uint32_t kKeyLong = make_key(255u, 2046u);
 constexpr int kKeyBits = 19;
 constexpr int kMaxClasses = 255;
 constexpr size_t kSmemBudget = 227 * 1024;
@@ -85,7 +90,15 @@ struct SlabGroup {       // 16 bytes
   uint8_t last_ncols;    // columns in the group's last slab (1..32)
   uint32_t n_slabs;
 };
-constexpr int kMaxSmemGroups = 128;  // group tables up to this size are copied to shared memory
+// The part of a group that falls into one CTA's slab range; built in shared memory at kernel start.
+struct Seg {             // 16 bytes
+  int a, b;              // slabs [a, b)
+  uint32_t off32_a;      // row of 32 elements where slab a starts
+  uint16_t d;
+  uint8_t cls;
+  uint8_t last_ncols;    // columns in slab b-1 (32 unless it is the group's last slab)
+};
+constexpr int kMaxSeg = 128;  // segments per batch (a CTA's range rarely touches more than a handful of groups)
 
 // bytes of one row of 32 entries: a + c + row id
 __host__ __device__ constexpr int row32_bytes(int row_bits) { return 32 * (8 + row_bits / 8); }
@@ -110,6 +123,8 @@ struct dualip_plan {
   unsigned char* data = nullptr;  // slabs back to back, row32_bytes(row_bits) bytes per row of 32 entries
   SlabGroup* groups = nullptr;    // n_groups entries
   int n_groups = 0;
+  std::vector<SlabGroup> groups_host;
+  int2* cta_range = nullptr;      // n_ctas + 1 entries {first slab, first group} of every CTA's contiguous slab range
   SlabHdr* hdr = nullptr;         // per-slab headers (plan-time kernels, tests); not read by the hot kernel
   int64_t* orig_start = nullptr;  // per slab lane: first nnz position of the column in the caller's order, or -1
   int64_t n_slabs = 0;
@@ -172,7 +187,7 @@ __global__ void column_keys_kernel(const IdxT* __restrict__ ccol, const uint8_t*
     else if (d > kMaxThreadDeg)
       key = kKeyLong;
     else
-      key = (cls << kDegBits) | (uint32_t)d;
+      key = make_key(cls, (uint32_t)d);
     keys[j] = key;
     vals[j] = (uint32_t)j;
   }
@@ -199,7 +214,7 @@ __global__ void fill_slabs_kernel(const IdxT* __restrict__ ccol, const IdxT* __r
   }
   const int g = lo;
   const uint32_t key = g_key[g];
-  const int d = (int)(key & ((1u << kDegBits) - 1));
+  const int d = key_d(key);
   const int64_t rel = i - g_start[g];
   const int64_t slab = g_slab_base[g] + rel / kSlabW;
   const int lane = (int)(rel % kSlabW);
@@ -225,7 +240,7 @@ __global__ void fill_slabs_kernel(const IdxT* __restrict__ ccol, const IdxT* __r
     SlabHdr h;
     h.off32 = (uint32_t)off32;
     h.d = (uint16_t)d;
-    h.cls = (uint8_t)(key >> kDegBits);
+    h.cls = (uint8_t)key_cls(key);
     h.ncols = (uint8_t)(left < kSlabW ? left : kSlabW);
     hdr[slab] = h;
   }
@@ -271,6 +286,7 @@ struct KArgs {
   const unsigned char* data;   // slabs back to back
   const SlabGroup* groups;
   int n_groups;
+  const int2* cta_range;       // gridDim.x + 1 entries {first slab, first group}
   const int64_t* orig_start;
   int64_t n_slabs;
   const dualip_proj_class* classes;
@@ -467,7 +483,9 @@ __device__ __forceinline__ void cta_epilogue(SumFn sum_load, ClearFn sum_clear, 
   }
 }
 
-template <bool ROW16, int SMODE, int ACC, int THREADS, int MINB>
+// OUT: the launch writes the primal (save_primal) and / or the per-column diagnostics; a separate instantiation keeps
+// those tests out of the hot loop of ordinary iterations.
+template <bool ROW16, int SMODE, int ACC, int THREADS, int MINB, bool OUT>
 __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArgs k) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // carve: [mbarrier 16B][per-warp slot mbarriers 512B][classes][scratch 32 doubles + 32 floats][s_lam m_pad floats]
@@ -476,9 +494,8 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   uint64_t* wbar = reinterpret_cast<uint64_t*>(smem_raw + 16);
   dualip_proj_class* s_cls = reinterpret_cast<dualip_proj_class*>(smem_raw + 16 + kBarBytes);
   const int n_cls_bytes = ((k.n_classes * (int)sizeof(dualip_proj_class)) + 15) & ~15;
-  SlabGroup* s_grp = reinterpret_cast<SlabGroup*>(smem_raw + 16 + kBarBytes + n_cls_bytes);
-  const int n_grp_bytes = (k.n_groups <= kMaxSmemGroups ? k.n_groups : 0) * (int)sizeof(SlabGroup);
-  double* dscratch = reinterpret_cast<double*>(smem_raw + 16 + kBarBytes + n_cls_bytes + n_grp_bytes);
+  Seg* s_seg = reinterpret_cast<Seg*>(smem_raw + 16 + kBarBytes + n_cls_bytes);
+  double* dscratch = reinterpret_cast<double*>(smem_raw + 16 + kBarBytes + n_cls_bytes + kMaxSeg * (int)sizeof(Seg));
   float* fscratch = reinterpret_cast<float*>(dscratch + 32);
   float* s_lam = fscratch + 32;
   const int m = k.m;
@@ -488,6 +505,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   unsigned char* s_stage = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(s_stash) + 127) & ~(uintptr_t)127);  // kStageBytes per warp (register path)
   __shared__ unsigned int s_ticket;
+  __shared__ int s_nseg;
 
   const unsigned FULL = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -522,9 +540,6 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   }
   for (int i = tid; i < k.n_classes * (int)(sizeof(dualip_proj_class) / 4); i += THREADS)
     reinterpret_cast<uint32_t*>(s_cls)[i] = reinterpret_cast<const uint32_t*>(k.classes)[i];
-  if (k.n_groups <= kMaxSmemGroups)
-    for (int i = tid; i < k.n_groups * (int)(sizeof(SlabGroup) / 4); i += THREADS)
-      reinterpret_cast<uint32_t*>(s_grp)[i] = reinterpret_cast<const uint32_t*>(k.groups)[i];
   if (SMODE <= 1)
     for (int i = tid; i < m; i += THREADS) s_grad[i] = 0.f;
   if (SMODE == 0) {
@@ -540,19 +555,19 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   __syncthreads();
 
   stamp(1);
-  // ---- stream slabs: warp w of the grid takes slabs w, w + W, w + 2W, ... (neighbouring warps read neighbouring
-  //      slabs, and every warp sees the same mix of column lengths).  Slabs are visited group by group: inside a
-  //      (class, length) group the slab addresses advance by a constant stride and the code is specialised on the length,
-  //      so the per-slab bookkeeping is a pointer increment ----
+  // ---- stream slabs.  Every CTA owns a contiguous range of the (length, class)-ordered slab sequence, cut at plan time so
+  //      that all ranges cost about the same: an SM then runs the code of one or two column lengths only (instruction
+  //      cache), and since groups of equal length and different class are neighbours, every range holds the problem's mix
+  //      of classes.  The range is split into segments (one per group it touches); warp w takes slabs a+w, a+w+16, ... of a
+  //      segment.  Inside a block of segments of equal length the warps start at different segments (rotation by warp
+  //      index): at any time some warps of the SM run compute-heavy simplex slabs and others bandwidth-heavy clamp slabs. ----
   double cx = 0.0, xx = 0.0;
-  const int W = (int)gridDim.x * NW;
-  const bool want_out = (k.x_out != nullptr) || (k.diag != nullptr);
   const float s = k.s;
   using RowT = typename std::conditional<ROW16, unsigned short, uint32_t>::type;
   constexpr uint32_t RB = (uint32_t)row32_bytes(ROW16 ? 16 : 32);  // bytes per row of 32 entries
-  const int n_slabs = (int)k.n_slabs;
-  const int sl0 = (int)blockIdx.x * NW + warp;
-  const SlabGroup* __restrict__ grp = (k.n_groups <= kMaxSmemGroups) ? s_grp : k.groups;
+  const int2 range0 = k.cta_range[blockIdx.x];
+  const int rb = range0.x, re = k.cta_range[blockIdx.x + 1].x;
+  int g_first = range0.y;
   // TMA staging (register path): every warp owns a region of shared memory and two mbarriers.  Slabs of up to half the
   // region are staged two deep (slot = t mod 2, t = the warp's running slab count): while the warp works on slab t the
   // engine copies slabs t+1 and t+2; longer slabs take the whole region, one at a time.  ONE bulk copy per slab.
@@ -561,95 +576,162 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   unsigned char* my_stage = s_stage + (size_t)warp * region;
   uint64_t* my_bars = wbar + warp * kStageSlots;
   uint32_t phases = 0;  // phase bit per slot barrier
-  // producer cursor: the next slab to hand to the engine (it runs ahead of the consumer, across group boundaries)
-  int p_sl = sl0, p_g = 0, p_t = 0, p_end = 0, p_big = -1;
-  uint32_t p_bytes = 0;
-  uint32_t p_off = 0, p_stride = 0;  // in rows of 32 entries (RB bytes each)
-  auto p_enter_group = [&]() {  // p_sl < n_slabs
-    while (p_sl >= (int)(grp[p_g].slab_begin + grp[p_g].n_slabs)) ++p_g;
-    const SlabGroup G = grp[p_g];
-    p_end = (int)(G.slab_begin + G.n_slabs);
-    p_bytes = (uint32_t)G.d * RB;
-    p_off = G.off32_begin + (uint32_t)(p_sl - (int)G.slab_begin) * G.d;
-    p_stride = (uint32_t)W * G.d;
-    if (G.d > kRegDeg) p_bytes = 0xffffffffu;  // generic path: never staged
-  };
-  // t_free: slabs < t_free (running count) have left their slots
-  auto top_up = [&](int t_free) {
-    while (p_sl < n_slabs) {
-      if (p_sl >= p_end) p_enter_group();
-      if (!use_stage || p_bytes > region) {  // not staged: the cursor just moves on (at most one slab ahead)
-        if (p_t > t_free) break;
-      } else if (p_bytes * 2u <= region) {   // two deep
-        if (p_big >= t_free || p_t > t_free + 1) break;
-        if (lane == 0) stage_issue(my_stage + (p_t & 1) * (region >> 1), my_bars + (p_t & 1), k.data + (size_t)p_off * RB, p_bytes);
-      } else {                               // whole region: only into an empty pipeline
-        if (p_t != t_free) break;
-        if (lane == 0) stage_issue(my_stage, my_bars, k.data + (size_t)p_off * RB, p_bytes);
-        p_big = p_t;
+  int t = 0;            // running count of this warp's slabs
+  for (bool more_batches = rb < re; more_batches;) {
+    // ---- this CTA's segments (one batch, unless its range touches more than kMaxSeg groups) ----
+    __syncthreads();
+    if (warp == 0) {
+      int count = 0;
+      for (int round = 0; round < kMaxSeg / 32; ++round) {
+        const int gi = g_first + count + lane;
+        bool valid = gi < k.n_groups;
+        SlabGroup G = {};
+        if (valid) G = k.groups[gi];
+        valid = valid && (int)G.slab_begin < re;
+        if (valid) {
+          const int g_end = (int)(G.slab_begin + G.n_slabs);
+          Seg sg;
+          sg.a = max(rb, (int)G.slab_begin);
+          sg.b = min(re, g_end);
+          sg.off32_a = G.off32_begin + (uint32_t)(sg.a - (int)G.slab_begin) * G.d;
+          sg.d = G.d;
+          sg.cls = G.cls;
+          sg.last_ncols = (sg.b == g_end) ? G.last_ncols : (uint8_t)32;
+          s_seg[count + lane] = sg;
+        }
+        const int nv = __popc(__ballot_sync(FULL, valid));
+        count += nv;
+        if (nv < 32) break;
       }
-      ++p_t;
-      p_sl += W;
-      p_off += p_stride;
+      if (lane == 0) s_nseg = count;
     }
-  };
-  int sl = sl0, g = 0, t = 0;
-  while (sl < n_slabs) {
-    while (sl >= (int)(grp[g].slab_begin + grp[g].n_slabs)) ++g;
-    const SlabGroup G = grp[g];
-    const int d = (int)G.d, cls = (int)G.cls;
-    const int g_end = (int)(G.slab_begin + G.n_slabs);
-    uint32_t boff = G.off32_begin + (uint32_t)(sl - (int)G.slab_begin) * G.d;  // in rows of 32 entries
-    const dualip_proj_class pc = s_cls[cls];
-    if (FAST && d <= kRegDeg) {
-      // ---- register path: the whole column lives in registers, code specialised on d ----
-      const uint32_t stride = (uint32_t)W * G.d;
-      const unsigned char* s_lam_b = reinterpret_cast<const unsigned char*>(s_lam);
-      StageCtx st{use_stage, region, my_stage, my_bars};
-      auto ensure_issued = [&](int tt) {
-        if (p_t <= tt) top_up(tt);
-      };
-      auto after_load = [&](int tt) {  // slab tt is in registers: its slot is free
-        __syncwarp();
-        top_up(tt + 1);
-      };
-      switch (d) {
-#define DUALIP_FAST_CASE(DD)                                                                                        \
-  case DD:                                                                                                          \
-    for (; sl < g_end; sl += W, boff += stride, ++t) {                                                              \
-      const bool active = lane < ((sl == g_end - 1) ? (int)G.last_ncols : 32);                                      \
-      fast_slab<DD, SMODE, ACC>(k, pc, cls, k.data + (size_t)boff * RB, lane, active, s_lam_b, s_grad_u32, s, sl, t, cx, xx, st, \
-                                phases, ensure_issued, after_load);                                                 \
-    }                                                                                                               \
+    __syncthreads();
+    const int n_seg = s_nseg;
+    g_first += n_seg;
+    more_batches = (n_seg == kMaxSeg);
+    // ---- segment walk: blocks of segments of equal length, entered at a warp-dependent position ----
+    struct Walk {
+      int bs, bn, i, rot;  // current block [bs, bs+bn), position inside it, rotation
+    };
+    auto block_len = [&](int bs) {
+      int n = 1;
+      while (bs + n < n_seg && s_seg[bs + n].d == s_seg[bs].d) ++n;
+      return n;
+    };
+    auto walk_next = [&](Walk& w) -> int {  // index of the next segment in which this warp has slabs, or -1
+      for (;;) {
+        ++w.i;
+        if (w.i >= w.bn) {
+          w.bs += w.bn;
+          if (w.bs >= n_seg) return -1;
+          w.bn = block_len(w.bs);
+          w.rot = warp % w.bn;
+          w.i = 0;
+        }
+        int idx = w.i + w.rot;
+        if (idx >= w.bn) idx -= w.bn;
+        idx += w.bs;
+        if (s_seg[idx].a + warp < s_seg[idx].b) return idx;
+      }
+    };
+    // producer cursor: the next slab to hand to the engine (it runs ahead of the consumer, across segments)
+    Walk pw{0, 0, 0, 0};
+    int p_sl = 0, p_t = t, p_end = 0, p_big = -1;
+    uint32_t p_bytes = 0, p_off = 0, p_stride = 0;  // offsets in rows of 32 entries (RB bytes each)
+    bool p_done = false;
+    auto p_next_seg = [&]() {
+      const int idx = walk_next(pw);
+      if (idx < 0) {
+        p_done = true;
+        return;
+      }
+      const Seg S = s_seg[idx];
+      p_sl = S.a + warp;
+      p_end = S.b;
+      p_bytes = (S.d > kRegDeg) ? 0xffffffffu : (uint32_t)S.d * RB;  // generic path: never staged
+      p_off = S.off32_a + (uint32_t)warp * S.d;
+      p_stride = (uint32_t)NW * S.d;
+    };
+    // t_free: slabs < t_free (running count) have left their slots
+    auto top_up = [&](int t_free) {
+      while (!p_done) {
+        if (p_sl >= p_end) {
+          p_next_seg();
+          continue;
+        }
+        if (!use_stage || p_bytes > region) {  // not staged: the cursor just moves on (at most one slab ahead)
+          if (p_t > t_free) break;
+        } else if (p_bytes * 2u <= region) {   // two deep
+          if (p_big >= t_free || p_t > t_free + 1) break;
+          if (lane == 0) stage_issue(my_stage + (p_t & 1) * (region >> 1), my_bars + (p_t & 1), k.data + (size_t)p_off * RB, p_bytes);
+        } else {                               // whole region: only into an empty pipeline
+          if (p_t != t_free) break;
+          if (lane == 0) stage_issue(my_stage, my_bars, k.data + (size_t)p_off * RB, p_bytes);
+          p_big = p_t;
+        }
+        ++p_t;
+        p_sl += NW;
+        p_off += p_stride;
+      }
+    };
+    Walk cw{0, 0, 0, 0};
+    for (int seg_idx = walk_next(cw); seg_idx >= 0; seg_idx = walk_next(cw)) {
+      const Seg S = s_seg[seg_idx];
+      const int d = (int)S.d, cls = (int)S.cls;
+      const int g_end = S.b;
+      int sl = S.a + warp;
+      uint32_t boff = S.off32_a + (uint32_t)warp * S.d;  // in rows of 32 entries
+      const uint32_t stride = (uint32_t)NW * S.d;
+      const dualip_proj_class pc = s_cls[cls];
+      if (FAST && d <= kRegDeg) {
+        // ---- register path: the whole column lives in registers, code specialised on d ----
+        const unsigned char* s_lam_b = reinterpret_cast<const unsigned char*>(s_lam);
+        StageCtx st{use_stage, region, my_stage, my_bars};
+        auto ensure_issued = [&](int tt) {
+          if (p_t <= tt) top_up(tt);
+        };
+        auto after_load = [&](int tt) {  // slab tt is in registers: its slot is free
+          __syncwarp();
+          top_up(tt + 1);
+        };
+        switch (d) {
+#define DUALIP_FAST_CASE(DD)                                                                                              \
+  case DD:                                                                                                                \
+    for (; sl < g_end; sl += NW, boff += stride, ++t) {                                                                   \
+      const bool active = lane < ((sl == g_end - 1) ? (int)S.last_ncols : 32);                                            \
+      fast_slab<DD, SMODE, ACC, OUT>(k, pc, cls, k.data + (size_t)boff * RB, lane, active, s_lam_b, s_grad_u32, s, sl, t, \
+                                     cx, xx, st, phases, ensure_issued, after_load);                                      \
+    }                                                                                                                     \
     break;
-        DUALIP_FAST_CASE(1)
-        DUALIP_FAST_CASE(2)
-        DUALIP_FAST_CASE(3)
-        DUALIP_FAST_CASE(4)
-        DUALIP_FAST_CASE(5)
-        DUALIP_FAST_CASE(6)
-        DUALIP_FAST_CASE(7)
-        DUALIP_FAST_CASE(8)
-        DUALIP_FAST_CASE(9)
-        DUALIP_FAST_CASE(10)
-        DUALIP_FAST_CASE(11)
-        DUALIP_FAST_CASE(12)
-        DUALIP_FAST_CASE(13)
-        DUALIP_FAST_CASE(14)
-        DUALIP_FAST_CASE(15)
-        DUALIP_FAST_CASE(16)
-        DUALIP_FAST_CASE(17)
-        DUALIP_FAST_CASE(18)
-        DUALIP_FAST_CASE(19)
-        DUALIP_FAST_CASE(20)
+          DUALIP_FAST_CASE(1)
+          DUALIP_FAST_CASE(2)
+          DUALIP_FAST_CASE(3)
+          DUALIP_FAST_CASE(4)
+          DUALIP_FAST_CASE(5)
+          DUALIP_FAST_CASE(6)
+          DUALIP_FAST_CASE(7)
+          DUALIP_FAST_CASE(8)
+          DUALIP_FAST_CASE(9)
+          DUALIP_FAST_CASE(10)
+          DUALIP_FAST_CASE(11)
+          DUALIP_FAST_CASE(12)
+          DUALIP_FAST_CASE(13)
+          DUALIP_FAST_CASE(14)
+          DUALIP_FAST_CASE(15)
+          DUALIP_FAST_CASE(16)
+          DUALIP_FAST_CASE(17)
+          DUALIP_FAST_CASE(18)
+          DUALIP_FAST_CASE(19)
+          DUALIP_FAST_CASE(20)
 #undef DUALIP_FAST_CASE
-        default:
-          break;
+          default:
+            break;
+        }
+        continue;
       }
-      continue;
-    }
-    // ---- generic path: one slab per turn of the outer loop ----
-    const bool active = lane < ((sl == g_end - 1) ? (int)G.last_ncols : 32);
+      // ---- generic path ----
+      for (; sl < g_end; sl += NW, boff += stride, ++t) {
+    const bool active = lane < ((sl == g_end - 1) ? (int)S.last_ncols : 32);
     const float* __restrict__ pa = reinterpret_cast<const float*>(k.data + (size_t)boff * RB);
     const float* __restrict__ pcv = pa + (size_t)d * kSlabW;
     const RowT* __restrict__ pr = reinterpret_cast<const RowT*>(pcv + (size_t)d * kSlabW);
@@ -966,7 +1048,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     cx += (double)cxs;
     xx += (double)xxs;
 
-    if (want_out && active) {
+    if (OUT && active) {
       // ---- primal / diagnostics output (save_primal on the last iteration, tests): plain re-stream ----
       const int64_t os = k.orig_start[(int64_t)sl * kSlabW + lane];
       if (k.x_out) {
@@ -989,9 +1071,9 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       }
       if (k.diag && branch >= 0) k.diag[os] = (uint8_t)(branch | (min(rho, 63) << 2));
     }
-    sl += W;
-    ++t;
-  }
+      }  // slabs of the segment (generic path)
+    }    // segments
+  }      // batches
 
   // ---- flush per-CTA partial sums ----
   __syncthreads();
@@ -1250,11 +1332,12 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(const float* sum, int m,
 
 // ------------------------------------------------------------------------------------------
 // Plan time: bound on every CTA's row sums, for the fixed-point accumulator.  Same slab -> CTA assignment as the hot
-// kernel (warp w of CTA b takes slabs b*NW + w, + gridDim*NW, ...).  |a * x| <= |a| * xmax(class).
+// kernel (CTA b owns the slabs of its range).  |a * x| <= |a| * xmax(class).
 // ------------------------------------------------------------------------------------------
 template <typename RowT>
 __global__ void cta_row_bound_kernel(const unsigned char* __restrict__ data,
-                                     const SlabHdr* __restrict__ hdr, int64_t n_slabs, const float* __restrict__ cls_xmax,
+                                     const SlabHdr* __restrict__ hdr, const int2* __restrict__ cta_range, int64_t n_slabs,
+                                     const float* __restrict__ cls_xmax,
                                      int m, float* __restrict__ table, unsigned int* __restrict__ row_cnt) {
   extern __shared__ __align__(16) unsigned char bound_smem[];
   float* s_bound = reinterpret_cast<float*>(bound_smem);              // m floats: this CTA's row bounds
@@ -1265,8 +1348,8 @@ __global__ void cta_row_bound_kernel(const unsigned char* __restrict__ data,
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
-  const int64_t total_warps = (int64_t)gridDim.x * NW;
-  for (int64_t sl = (int64_t)blockIdx.x * NW + warp; sl < n_slabs; sl += total_warps) {
+  (void)n_slabs;
+  for (int sl = cta_range[blockIdx.x].x + warp; sl < cta_range[blockIdx.x + 1].x; sl += NW) {
     const SlabHdr h = hdr[sl];
     if (lane >= (int)h.ncols) continue;
     const float xmax = cls_xmax[h.cls];
@@ -1325,18 +1408,21 @@ typedef void (*SlabKernel)(const KArgs);
 
 // Variants: the register path and fixed-point accumulation exist for uint16 rows with lambda and the accumulator in
 // shared memory (m up to ~24k); larger m streams through the generic path with fp32 accumulation.
-static SlabKernel plan_kernel(const dualip_plan* p) {
+template <bool OUT>
+static SlabKernel plan_kernel_out(const dualip_plan* p) {
   const bool row16 = p->row_bits == 16;
-  if (row16 && p->smode == 0) return p->fixed_point ? matching_slab_kernel<true, 0, 1, kThreads, 1> : matching_slab_kernel<true, 0, 0, kThreads, 1>;
-  if (row16 && p->smode == 1) return matching_slab_kernel<true, 1, 0, kThreads, 1>;
-  if (row16 && p->smode == 2) return matching_slab_kernel<true, 2, 0, kThreads, 1>;
-  if (!row16 && p->smode == 1) return matching_slab_kernel<false, 1, 0, kThreads, 1>;
-  if (!row16 && p->smode == 2) return matching_slab_kernel<false, 2, 0, kThreads, 1>;
+  if (row16 && p->smode == 0)
+    return p->fixed_point ? matching_slab_kernel<true, 0, 1, kThreads, 1, OUT> : matching_slab_kernel<true, 0, 0, kThreads, 1, OUT>;
+  if (row16 && p->smode == 1) return matching_slab_kernel<true, 1, 0, kThreads, 1, OUT>;
+  if (row16 && p->smode == 2) return matching_slab_kernel<true, 2, 0, kThreads, 1, OUT>;
+  if (!row16 && p->smode == 1) return matching_slab_kernel<false, 1, 0, kThreads, 1, OUT>;
+  if (!row16 && p->smode == 2) return matching_slab_kernel<false, 2, 0, kThreads, 1, OUT>;
   return nullptr;
 }
+static SlabKernel plan_kernel(const dualip_plan* p, bool out) { return out ? plan_kernel_out<true>(p) : plan_kernel_out<false>(p); }
 
 static size_t smem_fixed_bytes(int n_classes) {
-  return 16 + kBarBytes + (((size_t)n_classes * sizeof(dualip_proj_class) + 15) & ~(size_t)15) + kMaxSmemGroups * sizeof(SlabGroup) +
+  return 16 + kBarBytes + (((size_t)n_classes * sizeof(dualip_proj_class) + 15) & ~(size_t)15) + kMaxSeg * sizeof(Seg) +
          32 * sizeof(double) + 32 * sizeof(float);
 }
 
@@ -1351,6 +1437,7 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.data = p->data;
   k.groups = p->groups;
   k.n_groups = p->n_groups;
+  k.cta_range = p->cta_range;
   k.orig_start = p->orig_start;
   k.n_slabs = p->n_slabs;
   k.classes = p->classes_dev;
@@ -1388,7 +1475,7 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
     else
       matching_long_kernel<0><<<blocks, 256, 0, stream>>>(k, p->longcols, p->n_long);
   }
-  SlabKernel kern = plan_kernel(p);
+  SlabKernel kern = plan_kernel(p, x_out != nullptr || diag != nullptr);
   kern<<<p->n_ctas, p->threads, p->smem_bytes, stream>>>(k);
   DUALIP_CUDA_TRY(cudaGetLastError());
   return DUALIP_OK;
@@ -1490,9 +1577,9 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
         g.off32 = off32;
         const int64_t ns = (g.count + kSlabW - 1) / kSlabW;
         slab += ns;
-        off32 += ns * (int64_t)(g.key & ((1u << kDegBits) - 1));
+        off32 += ns * (int64_t)key_d(g.key);
         groups.push_back(g);
-        p->class_used[(g.key >> kDegBits) & 0xffu] = true;
+        p->class_used[key_cls(g.key)] = true;
         n_short = pos + g.count;
       }
       pos += uc[r];
@@ -1549,14 +1636,15 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
       const int64_t ns = (groups[i].count + kSlabW - 1) / kSlabW;
       gt[i].slab_begin = (uint32_t)groups[i].slab_base;
       gt[i].off32_begin = (uint32_t)groups[i].off32;
-      gt[i].d = (uint16_t)(groups[i].key & ((1u << kDegBits) - 1));
-      gt[i].cls = (uint8_t)(groups[i].key >> kDegBits);
+      gt[i].d = (uint16_t)key_d(groups[i].key);
+      gt[i].cls = (uint8_t)key_cls(groups[i].key);
       gt[i].last_ncols = (uint8_t)(groups[i].count - (ns - 1) * kSlabW);
       gt[i].n_slabs = (uint32_t)ns;
     }
     BS_TRY(cudaMalloc(&p->groups, sizeof(SlabGroup) * G));
     BS_TRY(cudaMemcpyAsync(p->groups, gt.data(), sizeof(SlabGroup) * G, cudaMemcpyHostToDevice, stream));
     p->n_groups = G;
+    p->groups_host = gt;
     BS_TRY(cudaStreamSynchronize(stream));  // host vectors go out of scope
   }
   if (n_long > 0) {
@@ -1593,6 +1681,70 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
     return DUALIP_EINVAL;
   }
   return rc;
+}
+
+// Cuts the slab sequence into n_ctas contiguous ranges of about equal cost.  Cost of a slab by projection kind and column
+// length d, fitted on B200 to per-CTA main-loop times of the C3 workload at a late iterate (100M- and 12.5M-entity shards
+// agree within 10 %; residual of the fit 2 % mean, 6 % max: profiles/r2), in units of 7.5 ns per CTA:
+//   simplex  4.0 + d (d <= 14, staged two deep)   1.27 d (15..16)   1.61 d (17..20, a and c are read twice)
+//   clamp    2.8 + 0.56 d (d <= 14)               0.76 d (15..20)
+//   generic path (longer columns, or a plan without the register path): simplex 6.7 d (iterative threshold search over
+//   re-streamed data), clamp 2.7 d.  DUALIP_COST_SCALE_SIMPLEX / _GENERIC rescale for experiments.
+static int build_cta_ranges(dualip_plan* p) {
+  const char* e1 = getenv("DUALIP_COST_SCALE_SIMPLEX");
+  const char* e2 = getenv("DUALIP_COST_SCALE_GENERIC");
+  const double ks = e1 ? atof(e1) : 1.0, kg = e2 ? atof(e2) : 1.0;
+  const bool fast = p->row_bits == 16 && p->smode == 0;
+  auto cost = [&](const SlabGroup& g) {
+    const bool simplex = p->classes_host[g.cls].kind != DUALIP_PROJ_CLAMP;
+    const double d = (double)g.d;
+    if (!fast || g.d > kRegDeg) return kg * (simplex ? 6.7 * d : 2.7 * d);
+    if (simplex) return ks * (g.d <= 14 ? 4.0 + d : (g.d <= 16 ? 1.27 * d : 1.61 * d));
+    return g.d <= 14 ? 2.8 + 0.56 * d : 0.76 * d;
+  };
+  double total = 0.0;
+  for (const SlabGroup& g : p->groups_host) total += cost(g) * (double)g.n_slabs;
+  std::vector<int2> r((size_t)p->n_ctas + 1);
+  const int G = (int)p->groups_host.size();
+  int gi = 0;            // current group
+  int64_t used = 0;      // slabs of group gi already handed out
+  double acc = 0.0;      // cost handed out so far
+  for (int c = 0; c < p->n_ctas; ++c) {
+    while (gi < G && used >= (int64_t)p->groups_host[gi].n_slabs) {
+      ++gi;
+      used = 0;
+    }
+    r[c].x = gi < G ? (int)(p->groups_host[gi].slab_begin + used) : (int)p->n_slabs;
+    r[c].y = gi < G ? gi : G;
+    const double target = total * (double)(c + 1) / (double)p->n_ctas;
+    while (gi < G && acc < target) {
+      const SlabGroup& g = p->groups_host[gi];
+      const double cs = cost(g);
+      const int64_t left = (int64_t)g.n_slabs - used;
+      int64_t take = (int64_t)ceil((target - acc) / cs);
+      if (take > left) take = left;
+      if (take < 0) take = 0;
+      used += take;
+      acc += cs * (double)take;
+      if (used >= (int64_t)g.n_slabs) {
+        ++gi;
+        used = 0;
+      } else {
+        break;
+      }
+    }
+  }
+  r[p->n_ctas].x = (int)p->n_slabs;
+  r[p->n_ctas].y = G;
+  // the last range ends at the last slab whatever the rounding did
+  cudaFree(p->cta_range);
+  p->cta_range = nullptr;
+  if (cudaMalloc(&p->cta_range, sizeof(int2) * r.size()) != cudaSuccess ||
+      cudaMemcpy(p->cta_range, r.data(), sizeof(int2) * r.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("allocating the CTA range table failed");
+    return DUALIP_ECUDA;
+  }
+  return DUALIP_OK;
 }
 
 // Chooses the accumulation mode of a plan.  Fixed point needs (a) a finite bound on x for every class, (b) the register /
@@ -1650,7 +1802,7 @@ static int choose_accumulator(dualip_plan* p, cudaStream_t stream) {
     const size_t bsm = 8 * (size_t)m;  // fits: mode 0 already keeps 8*m bytes of lambda + accumulator in shared memory
     CA_TRY(cudaFuncSetAttribute((const void*)cta_row_bound_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
     cta_row_bound_kernel<unsigned short><<<p->n_ctas, p->threads, bsm, stream>>>(
-        p->data, p->hdr, p->n_slabs, xmax_d, m, table, row_cnt);
+        p->data, p->hdr, p->cta_range, p->n_slabs, xmax_d, m, table, row_cnt);
   }
   if (p->n_long > 0) {
     const int blocks = (int)std::min<int64_t>((p->n_long + 7) / 8, (int64_t)p->n_sms * 8);
@@ -1710,6 +1862,7 @@ void dualip_plan_destroy(dualip_plan* p) {
   DeviceGuard g(p->device);
   cudaFree(p->data);
   cudaFree(p->groups);
+  cudaFree(p->cta_range);
   cudaFree(p->hdr);
   cudaFree(p->orig_start);
   cudaFree(p->longcols);
@@ -1863,6 +2016,10 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
     if (!(env_ctas && atoi(env_ctas) > 0) && want < p->n_ctas) p->n_ctas = (int)want;
   }
   {
+    int rc = build_cta_ranges(p);
+    if (rc != DUALIP_OK) return fail(rc);
+  }
+  {
     int rc = choose_accumulator(p, stream);
     if (rc != DUALIP_OK) return fail(rc);
   }
@@ -1893,13 +2050,13 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   DUALIP_TRY_FAIL(cudaMalloc(&p->scal_stage, sizeof(dualip_scalars)));
   p->owned_bytes += sizeof(float) * 3 * (m_pad + 4) + 64;
 
-  SlabKernel kern = plan_kernel(p);
-  if (!kern) {
-    set_error("no kernel variant");
-    return fail(DUALIP_EINVAL);
-  }
   // the attribute is per function, not per plan: always allow the device maximum so that plans of different m coexist
-  {
+  for (int out = 0; out < 2; ++out) {
+    SlabKernel kern = plan_kernel(p, out != 0);
+    if (!kern) {
+      set_error("no kernel variant");
+      return fail(DUALIP_EINVAL);
+    }
     cudaFuncAttributes fa;
     DUALIP_TRY_FAIL(cudaFuncGetAttributes(&fa, (const void*)kern));
     const int max_dyn = (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes;
@@ -1918,6 +2075,23 @@ int dualip_debug_timeline(dualip_plan* p, unsigned long long* out_host, int n_ct
   DUALIP_CUDA_TRY(cudaDeviceSynchronize());
   DUALIP_CUDA_TRY(cudaMemcpy(out_host, p->timeline, sizeof(unsigned long long) * (n_ctas < 0 ? 12 * 4096 : 10 * std::min(n_ctas, 4096)), cudaMemcpyDeviceToHost));
   return DUALIP_OK;
+}
+
+/* Debug only: group table (6 values per group: slab_begin, n_slabs, d, cls, off32_begin, last_ncols) and the CTA ranges
+ * (first slab of every CTA, n_ctas + 1 values).  Returns the number of groups. */
+int dualip_debug_layout(dualip_plan* p, int64_t* groups_out, int cap_groups, int64_t* ranges_out, int cap_ranges) {
+  if (!p) return DUALIP_EINVAL;
+  DeviceGuard g(p->device);
+  const int G = (int)p->groups_host.size();
+  for (int i = 0; i < G && i < cap_groups; ++i) {
+    const SlabGroup& sg = p->groups_host[i];
+    int64_t* o = groups_out + 6 * i;
+    o[0] = sg.slab_begin, o[1] = sg.n_slabs, o[2] = sg.d, o[3] = sg.cls, o[4] = sg.off32_begin, o[5] = sg.last_ncols;
+  }
+  std::vector<int2> r((size_t)p->n_ctas + 1);
+  if (p->cta_range) cudaMemcpy(r.data(), p->cta_range, sizeof(int2) * r.size(), cudaMemcpyDeviceToHost);
+  for (int i = 0; i <= p->n_ctas && i < cap_ranges; ++i) ranges_out[i] = r[i].x;
+  return G;
 }
 
 int dualip_plan_info(const dualip_plan* p, int64_t* out, int cap) {

@@ -479,7 +479,7 @@ __device__ __forceinline__ void fast_simplex(const KArgs& k, const dualip_proj_c
 // slab is staged the same bytes are waiting in (or on their way to) one of the warp's slots.  ensure_issued(t) makes sure
 // the copy of slab t has been requested before the warp waits for it; after_load(t) is called as soon as the slot has been
 // read out, to request further slabs.
-template <int D, int SMODE, int ACC, typename Ensure, typename AfterLoad>
+template <int D, int SMODE, int ACC, bool OUT, typename Ensure, typename AfterLoad>
 __device__ __forceinline__ void fast_slab(const KArgs& k, const dualip_proj_class& pc, int cls, const unsigned char* slab,
                                           int lane, bool active, const unsigned char* s_lam_b, uint32_t s_grad_u32, float s,
                                           int slab_index, int t, double& cx, double& xx, const StageCtx& st, uint32_t& phases,
@@ -506,7 +506,7 @@ __device__ __forceinline__ void fast_slab(const KArgs& k, const dualip_proj_clas
     fast_clamp<D, SMODE>(k, pc, R, active, s_lam_b, s, x);
   else
     fast_simplex<D, SMODE>(k, pc, cls, R, active, s_lam_b, s, x, branch, rho);
-  if ((k.x_out != nullptr) || (k.diag != nullptr)) {  // save_primal / diagnostics: straight from registers
+  if (OUT) {  // save_primal / diagnostics: straight from registers
     if (active) {
       const int64_t os = k.orig_start[(int64_t)slab_index * 32 + lane];
       if (k.x_out) {

@@ -43,3 +43,32 @@ info = obj.plan_info()
 print(json.dumps({"tag": tag, "n": n, "kind": kind, "ms_mean": round(ms, 4), "ms_min": round(ts[0], 4), "ms_med": round(ts[len(ts)//2], 4),
                   "frac": round(balg / ms / 1e6 / 6552.6, 4), "stage": info["staged_degree"], "obj": float(scal[0]),
                   "lib": os.path.basename(os.environ.get("DUALIP_B200_LIB", "default"))}), flush=True)
+if os.environ.get("DUALIP_TIMELINE"):
+    import ctypes
+    import numpy as np
+    from dualip_b200 import _native
+    nc = info["n_ctas"]
+    buf = (ctypes.c_uint64 * (10 * nc))()
+    fn = _native.lib().dualip_debug_timeline; fn.restype = ctypes.c_int; fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    assert fn(obj._plan, buf, nc) == 0
+    tl = np.frombuffer(buf, dtype=np.uint64).reshape(nc, 5, 2).astype(np.int64)
+    g = tl[:, :, 1]
+    g0 = g[:, 0].min()
+    rel = g - g0
+    names = ["start", "lambda staged", "main loop end", "flush end", "cta end"]
+    for i, nm in enumerate(names):
+        v = rel[:, i][g[:, i] > 0]
+        print(f"  {nm:14s} ns after first CTA start: min {v.min():8d} mean {int(v.mean()):8d} max {v.max():8d} (n={v.size})")
+    order = np.argsort(rel[:, 2])
+    print("  slowest CTAs (main loop end):", [(int(c), int(rel[c, 2])) for c in order[-6:]], "fastest:", [(int(c), int(rel[c, 2])) for c in order[:4]])
+if os.environ.get("DUMP_LAYOUT") and os.environ.get("DUALIP_TIMELINE"):
+    lib = _native.lib()
+    fn2 = lib.dualip_debug_layout; fn2.restype = ctypes.c_int
+    fn2.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    gbuf = (ctypes.c_int64 * (6 * 4096))(); rbuf = (ctypes.c_int64 * (nc + 1))()
+    G = fn2(obj._plan, gbuf, 4096, rbuf, nc + 1)
+    groups = np.frombuffer(gbuf, dtype=np.int64)[: 6 * G].reshape(G, 6).tolist()
+    ranges = list(rbuf)
+    kinds = {}
+    json.dump({"n": n, "groups": groups, "ranges": ranges, "main_ns": (rel[:, 2] - rel[:, 1]).tolist()},
+              open(os.environ["DUMP_LAYOUT"], "w"))
