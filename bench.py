@@ -310,9 +310,10 @@ def run_native(args):
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         replicas = {"ranks": world, "dual_bit_identical_on_all_ranks": bool((hi == lo).all().item())}
-    launches_per_step = info["plan"]["launches_per_calc"] + 1  # objective kernel(s) + update (an all-reduce would be NCCL's)
+    # evaluation and accelerated step share ONE launch (the kernel's last CTA steps); the two-launch paths add the update kernel
+    launches_per_step = info["plan"]["launches_per_calc"] + (0 if loop.one_launch and (world == 1 or loop.peer is not None) else 1)
     exchange = "none (single GPU)" if world == 1 else (
-        "peer memory: partial sums read over NVLink inside the update kernel, no collective call" if loop.peer is not None
+        "peer memory: the shard kernel's last CTA publishes its sums, reads the peers' over NVLink and steps; no collective call, one launch per iteration" if loop.peer is not None
         else "one NCCL all_reduce of m+2 floats per iteration")
 
     # ---- dominant kernel, for the roofline: CUDA events around every launch of the timed region ----

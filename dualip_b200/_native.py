@@ -87,6 +87,11 @@ SIGNATURES = {
     "dualip_peer_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "dualip_agd_step_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_float,
                                        C.c_int32, C.c_double, C.c_int32, C.c_void_p]),
+    "dualip_peer_status_nowait": (C.c_int, [C.c_void_p]),
+    "dualip_matching_ascent_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_float, C.c_int32, C.c_double, C.c_int32, C.c_void_p]),
+    "dualip_matching_ascent_step_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+                                                   C.c_void_p, C.c_float, C.c_int32, C.c_double, C.c_int32, C.c_void_p]),
     "dualip_agd_host_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                          C.c_int32]),
     "dualip_agd_host_destroy": (None, [C.c_void_p]),

@@ -10,282 +10,15 @@
 #include <new>
 
 #include "common.cuh"
+#include "agd_step.cuh"
 
 using namespace dualip;
 
-struct dualip_agd {
-  int device = 0;
-  int m = 0;
-  int H = 15;
-  float* x = nullptr;
-  float* y = nullptr;
-  float* gh = nullptr;      // H x m ring of gradients
-  float* yh = nullptr;      // H x m ring of y iterates (the reference stores y, not x: agd.py:170-172)
-  float* ratios = nullptr;  // H-1 ring: ratio of pair (j, j+1) at slot j % (H-1)
-  long long* pushes = nullptr;  // number of history pushes so far
-  double* dstate = nullptr;     // [0] max_step_size (mutable: gamma decay), [1] initial_step_size
-  uint8_t* eqmask = nullptr;
-  double* log_obj = nullptr;
-  double* log_step = nullptr;
-  int log_cap = 0;
-};
-
 namespace dualip {
-
-// One CTA.  FROM_PARTIAL: `grad` points at the all-reduced packed sums [sum_j a_rj x_rj (m) | c.x | ||x||^2] of the sharded
-// path; the kernel then also does the m-length tail of the objective (grad = sum - b, lambda.grad, slacks, dual objective:
-// matching.py:280-299), writes grad_out / scal_out, and saves the separate epilogue launch.  Both loops are unrolled by
-// four with every load of a round issued before the first use: a single CTA has no other warps to hide L2 latency.
-struct AgdStepArgs {
-  float* x;
-  float* y;
-  float* gh;
-  float* yh;
-  float* ratios;
-  long long* pushes;
-  double* dstate;
-  const uint8_t* eqmask;
-  const float* grad;  // FROM_PARTIAL: packed sums, m+2 floats
-  const dualip_scalars* scal;
-  int m, H;
-  float beta;
-  int decay_now;
-  double decay_factor;
-  double* log_obj;
-  double* log_step;
-  int iter_index;
-  const float* b;
-  double gamma;
-  float* grad_out;
-  dualip_scalars* scal_out;
-};
-
-template <bool FROM_PARTIAL>
-__device__ __forceinline__ void agd_step_body(const AgdStepArgs& A) {
-  float* __restrict__ x = A.x;
-  float* __restrict__ y = A.y;
-  float* __restrict__ gh = A.gh;
-  float* __restrict__ yh = A.yh;
-  float* __restrict__ ratios = A.ratios;
-  long long* __restrict__ pushes = A.pushes;
-  double* __restrict__ dstate = A.dstate;
-  const uint8_t* __restrict__ eqmask = A.eqmask;
-  const float* grad = A.grad;
-  const dualip_scalars* __restrict__ scal = A.scal;
-  const int m = A.m, H = A.H;
-  const float beta = A.beta;
-  const int decay_now = A.decay_now, iter_index = A.iter_index;
-  const double decay_factor = A.decay_factor, gamma = A.gamma;
-  double* log_obj = A.log_obj;
-  double* log_step = A.log_step;
-  const float* __restrict__ b = A.b;
-  float* grad_out = A.grad_out;
-  dualip_scalars* __restrict__ scal_out = A.scal_out;
-  __shared__ double s_red[5][32];
-  __shared__ float s_mx[32];
-  __shared__ double s_step;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
-  const long long t = *pushes;  // index of the entry pushed now
-  const int slot = (int)(t % H);
-  const int prev = (int)((t + H - 1) % H);
-  const bool have_prev = t > 0;
-  // 1) gradient (sharded path: the objective's tail), push (grad, y), measure the newest pair
-  //    agd_utils.py:11-27, :30-41 ; matching.py:280-299
-  double dg2 = 0.0, dy2 = 0.0, lg = 0.0, sp = 0.0, g2 = 0.0;
-  float mx = -INFINITY;
-  for (int base = tid; base < m; base += 4 * nt) {
-    float g4[4], y4[4], gp4[4], yp4[4], b4[4], x4[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = base + u * nt;
-      g4[u] = y4[u] = gp4[u] = yp4[u] = b4[u] = x4[u] = 0.f;
-      if (i < m) {
-        g4[u] = grad[i];
-        y4[u] = y[i];
-        if (have_prev) {
-          gp4[u] = gh[(size_t)prev * m + i];
-          yp4[u] = yh[(size_t)prev * m + i];
-        }
-        if (FROM_PARTIAL) {
-          b4[u] = b ? b[i] : 0.f;
-          x4[u] = x[i];
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = base + u * nt;
-      if (i < m) {
-        float g = g4[u];
-        if (FROM_PARTIAL) {
-          g = b ? __fsub_rn(g, b4[u]) : g;
-          grad_out[i] = g;
-          lg = fma((double)x4[u], (double)g, lg);
-          sp += (double)fmaxf(g, 0.f);
-          g2 = fma((double)g, (double)g, g2);
-          mx = fmaxf(mx, g);
-        }
-        gh[(size_t)slot * m + i] = g;
-        yh[(size_t)slot * m + i] = y4[u];
-        if (have_prev) {
-          const float dg = __fsub_rn(gp4[u], g);
-          const float dy = __fsub_rn(yp4[u], y4[u]);
-          dg2 = fma((double)dg, (double)dg, dg2);
-          dy2 = fma((double)dy, (double)dy, dy2);
-        }
-      }
-    }
-  }
-  dg2 = warp_sum(dg2);
-  dy2 = warp_sum(dy2);
-  if (FROM_PARTIAL) {
-    lg = warp_sum(lg);
-    sp = warp_sum(sp);
-    g2 = warp_sum(g2);
-    mx = warp_max(mx);
-  }
-  if (lane == 0) {
-    s_red[0][warp] = dg2;
-    s_red[1][warp] = dy2;
-    if (FROM_PARTIAL) {
-      s_red[2][warp] = lg;
-      s_red[3][warp] = sp;
-      s_red[4][warp] = g2;
-      s_mx[warp] = mx;
-    }
-  }
-  __syncthreads();
-  if (warp == 0) {
-    dg2 = warp_sum(lane < nw ? s_red[0][lane] : 0.0);
-    dy2 = warp_sum(lane < nw ? s_red[1][lane] : 0.0);
-    if (FROM_PARTIAL) {
-      lg = warp_sum(lane < nw ? s_red[2][lane] : 0.0);
-      sp = warp_sum(lane < nw ? s_red[3][lane] : 0.0);
-      g2 = warp_sum(lane < nw ? s_red[4][lane] : 0.0);
-      mx = warp_max(lane < nw ? s_mx[lane] : -INFINITY);
-    }
-  }
-  if (tid == 0) {
-    double dual_obj = scal ? scal->dual_objective : 0.0;
-    if (FROM_PARTIAL) {
-      const double cxv = (double)grad[m], xxv = (double)grad[m + 1];
-      dualip_scalars r;
-      r.primal_objective = cxv;
-      r.reg_penalty = 0.5 * gamma * xxv;
-      r.dual_val_times_grad = lg;
-      r.dual_objective = cxv + r.reg_penalty + lg;
-      r.max_pos_slack = (double)fmaxf(mx, 0.f);
-      r.sum_pos_slack = sp;
-      r.x_sq_norm = xxv;
-      r.grad_sq_norm = g2;
-      *scal_out = r;
-      dual_obj = r.dual_objective;
-    }
-    if (have_prev) ratios[(t - 1) % (H - 1)] = __fdiv_rn((float)sqrt(dg2), (float)sqrt(dy2));
-    // 2) step size                                                      agd_utils.py:44-62
-    const long long n_pairs = t < (long long)(H - 1) ? t : (long long)(H - 1);
-    const double max_step = dstate[0], init_step = dstate[1];
-    double step = init_step;
-    if (n_pairs >= H - 1) {
-      // Python max() over the list in chronological order: the first element wins unless a later one is greater
-      const long long j0 = t - (H - 1);
-      float lmax = ratios[j0 % (H - 1)];
-      for (long long j = j0 + 1; j < t; ++j) {
-        const float v = ratios[j % (H - 1)];
-        if (v > lmax) lmax = v;
-      }
-      if (!(isnan(lmax) || isinf(lmax))) {
-        const double cand = (lmax != 0.f) ? 1.0 / (double)lmax : max_step;
-        step = cand < max_step ? cand : max_step;
-      }
-    }
-    s_step = step;
-    if (log_obj) log_obj[iter_index] = dual_obj;
-    if (log_step) log_step[iter_index] = step;
-    if (decay_now) dstate[0] = step * decay_factor;  // agd.py:107
-    *pushes = t + 1;
-  }
-  __syncthreads();
-  // 3) ascent step, projection on the dual cone, momentum              agd.py:181-185, :13-21
-  const float step32 = (float)s_step;
-  const float omb = __fsub_rn(1.0f, beta);
-  const float* gsrc = FROM_PARTIAL ? grad_out : grad;
-  for (int base = tid; base < m; base += 4 * nt) {
-    float g4[4], y4[4], x4[4];
-    uint8_t e4[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = base + u * nt;
-      g4[u] = y4[u] = x4[u] = 0.f;
-      e4[u] = 0;
-      if (i < m) {
-        g4[u] = gsrc[i];
-        y4[u] = y[i];
-        x4[u] = x[i];
-        e4[u] = eqmask ? eqmask[i] : (uint8_t)0;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = base + u * nt;
-      if (i < m) {
-        float yn = __fadd_rn(x4[u], __fmul_rn(g4[u], step32));
-        if (!e4[u]) yn = fmaxf(yn, 0.f);
-        x[i] = __fadd_rn(__fmul_rn(yn, omb), __fmul_rn(y4[u], beta));
-        y[i] = yn;
-      }
-    }
-  }
-}
 
 template <bool FROM_PARTIAL>
 __global__ void __launch_bounds__(1024) agd_step_kernel(const AgdStepArgs A) {
   agd_step_body<FROM_PARTIAL>(A);
-}
-
-// ---- peer-memory exchange: arrival flags and slots in every rank's window (include/dualip_b200.h) ----
-constexpr int kPeerFlagBytes = 256;  // DUALIP_PEER_MAX_WORLD x 8-byte arrival flags, padded
-
-struct PeerArgs {
-  unsigned char* win[DUALIP_PEER_MAX_WORLD];  // window base of every rank, as mapped in this process
-  int rank, world;
-  unsigned long long seq;  // number of this step (1, 2, ...): the flag value, and seq & 1 the slot
-  size_t slot_bytes;
-  unsigned long long timeout_ns;
-  unsigned int* ticket;  // local word, 0 between steps: which CTA of the step kernel finishes last
-  float* sum;   // local m+2 floats (padded to a multiple of 4): the reduced packed sums
-  int* status;  // local word: set to 1 when a wait timed out
-};
-
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float* p) {
-  float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
 }
 
 // ceil((m+2) / 4096) CTAs of 1024 threads.  CTA 0 tells every peer that this rank's partial sums (written by the preceding
@@ -306,6 +39,7 @@ __global__ void __launch_bounds__(1024) agd_step_peer_kernel(const AgdStepArgs A
     while (*reinterpret_cast<volatile int*>(P.status) == 0 && ld_relaxed_sys_u64(mine) < P.seq) {
       if (global_timer_ns() - t0 > P.timeout_ns) {
         *P.status = 1;
+        *reinterpret_cast<volatile int*>(P.status_host) = 1;
         break;
       }
     }
@@ -466,36 +200,6 @@ int dualip_agd_get(dualip_agd* a, float* x_out_dev, float* y_out_dev, void* stre
   return DUALIP_OK;
 }
 
-static AgdStepArgs step_args(dualip_agd* a, const float* grad, const dualip_scalars* scal, float beta, int decay_now,
-                             double decay_factor, int iter_index, const float* b, double gamma, float* grad_out,
-                             dualip_scalars* scal_out) {
-  const bool log = iter_index >= 0 && iter_index < a->log_cap;
-  AgdStepArgs A;
-  A.x = a->x;
-  A.y = a->y;
-  A.gh = a->gh;
-  A.yh = a->yh;
-  A.ratios = a->ratios;
-  A.pushes = a->pushes;
-  A.dstate = a->dstate;
-  A.eqmask = a->eqmask;
-  A.grad = grad;
-  A.scal = scal;
-  A.m = a->m;
-  A.H = a->H;
-  A.beta = beta;
-  A.decay_now = decay_now;
-  A.decay_factor = decay_factor;
-  A.log_obj = log ? a->log_obj : nullptr;
-  A.log_step = log ? a->log_step : nullptr;
-  A.iter_index = log ? iter_index : 0;
-  A.b = b;
-  A.gamma = gamma;
-  A.grad_out = grad_out;
-  A.scal_out = scal_out;
-  return A;
-}
-
 int dualip_agd_step(dualip_agd* a, const float* grad_dev, const dualip_scalars* scalars_dev, float beta,
                     int32_t decay_now, double decay_factor, int32_t iter_index, void* stream) {
   if (!a || !grad_dev) {
@@ -522,19 +226,6 @@ int dualip_agd_step_sharded(dualip_agd* a, const float* partial_sum_dev, const f
 }
 
 // ---- exchange windows ----
-struct dualip_peer {
-  int device = 0, m = 0, rank = 0, world = 1;
-  size_t slot_bytes = 0, window_bytes = 0;
-  unsigned char* window = nullptr;                    // own window (cudaMalloc: exportable through CUDA IPC)
-  unsigned char* win[DUALIP_PEER_MAX_WORLD] = {};     // all windows as mapped here
-  bool opened[DUALIP_PEER_MAX_WORLD] = {};            // mapped with cudaIpcOpenMemHandle
-  bool connected = false;
-  float* sum = nullptr;
-  int* status = nullptr;  // [0] status, [1] ticket of the step kernel
-  unsigned long long seq = 0;  // steps taken
-  unsigned long long timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;  // DUALIP_PEER_TIMEOUT_MS overrides
-};
-
 void dualip_peer_destroy(dualip_peer* p) {
   if (!p) return;
   DeviceGuard g(p->device);
@@ -542,7 +233,9 @@ void dualip_peer_destroy(dualip_peer* p) {
     if (p->opened[r]) cudaIpcCloseMemHandle(p->win[r]);
   cudaFree(p->window);
   cudaFree(p->sum);
+  cudaFree(p->ticket);
   cudaFree(p->status);
+  if (p->status_host) cudaFreeHost(p->status_host);
   delete p;
 }
 
@@ -572,8 +265,17 @@ int dualip_peer_create(dualip_peer** out, int32_t m, int32_t rank, int32_t world
   cudaError_t e = cudaMalloc(&p->window, p->window_bytes);
   if (e == cudaSuccess) e = cudaMemset(p->window, 0, p->window_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&p->sum, sizeof(float) * (m + 8));
-  if (e == cudaSuccess) e = cudaMalloc(&p->status, 2 * sizeof(int));
-  if (e == cudaSuccess) e = cudaMemset(p->status, 0, 2 * sizeof(int));
+  // the status word lives in mapped host memory: the kernel sets it over PCIe only when a wait times out, and the host can
+  // look at it at any time without synchronising the stream
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&p->status_host), sizeof(int), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *p->status_host = 0;
+    e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&p->status_host_dev), p->status_host, 0);
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&p->status, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(p->status, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&p->ticket, sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(p->ticket, 0, sizeof(unsigned int));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     set_error("allocating the exchange window failed: %s", cudaGetErrorString(e));
@@ -648,12 +350,12 @@ int dualip_peer_status(dualip_peer* p, int32_t* status_out, void* stream) {
     return DUALIP_EINVAL;
   }
   DeviceGuard g(p->device);
-  int v = 0;
-  DUALIP_CUDA_TRY(cudaMemcpyAsync(&v, p->status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   DUALIP_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-  *status_out = v;
+  *status_out = *reinterpret_cast<volatile int*>(p->status_host);
   return DUALIP_OK;
 }
+
+int dualip_peer_status_nowait(dualip_peer* p) { return p ? *reinterpret_cast<volatile int*>(p->status_host) : 0; }
 
 int dualip_agd_step_peer(dualip_agd* a, dualip_peer* p, const float* b_dev, double gamma, float* grad_out_dev,
                          dualip_scalars* scalars_out_dev, float beta, int32_t decay_now, double decay_factor,
@@ -666,16 +368,7 @@ int dualip_agd_step_peer(dualip_agd* a, dualip_peer* p, const float* b_dev, doub
     set_error("exchange window is not connected or does not match the optimizer state");
     return DUALIP_EINVAL;
   }
-  PeerArgs P;
-  for (int r = 0; r < DUALIP_PEER_MAX_WORLD; ++r) P.win[r] = r < p->world ? p->win[r] : nullptr;
-  P.rank = p->rank;
-  P.world = p->world;
-  P.seq = ++p->seq;
-  P.slot_bytes = p->slot_bytes;
-  P.timeout_ns = p->timeout_ns;
-  P.sum = p->sum;
-  P.status = p->status;
-  P.ticket = reinterpret_cast<unsigned int*>(p->status + 1);
+  const PeerArgs P = peer_args(p, true);
   const int n_ctas = (a->m + 2 + 4095) / 4096;
   agd_step_peer_kernel<<<n_ctas, 1024, 0, (cudaStream_t)stream>>>(
       step_args(a, p->sum, nullptr, beta, decay_now, decay_factor, iter_index, b_dev, gamma, grad_out_dev, scalars_out_dev), P);

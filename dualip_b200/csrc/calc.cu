@@ -33,6 +33,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "agd_step.cuh"
 
 namespace dualip {
 
@@ -317,6 +318,12 @@ struct KArgs {
   const float* long_a;
   const float* long_c;
   const uint32_t* long_row;
+  // fused tail: the CTA that finishes last also takes the accelerated step on the optimizer state (one launch per
+  // iteration).  0: none; 1: after the objective's tail (single device); 2: sharded -- this rank's packed sums go into
+  // its exchange slot, the peers' sums are fetched over NVLink, then the tail and the step (dualip_agd_step_peer's work).
+  int fuse;
+  AgdStepArgs agd;
+  PeerArgs peer;
 };
 
 template <bool ROW16>
@@ -1166,6 +1173,10 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   };
   if (k.do_epilogue) {
     cta_epilogue(sum_load, sum_clear, cxv, xxv, k.lambda, k.b, m, k.gamma, k.grad_out, k.scalars_out, dscratch, fscratch);
+    if (k.fuse == 1) {
+      __syncthreads();  // grad_out / scalars_out written above are read by other threads of this CTA
+      agd_step_body<false>(k.agd);
+    }
   } else {
     for (int base = tid; base < m; base += 4 * THREADS) {
       float raw[4];
@@ -1181,6 +1192,10 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     if (tid == 0) {
       k.partial_out[m] = (float)cxv;
       k.partial_out[m + 1] = (float)xxv;
+    }
+    if (k.fuse == 2) {
+      peer_exchange_cta(k.peer, m + 2);
+      agd_step_body<true>(k.agd);
     }
   }
   if (tid == 0) {
@@ -1426,9 +1441,15 @@ static size_t smem_fixed_bytes(int n_classes) {
          32 * sizeof(double) + 32 * sizeof(float);
 }
 
+struct FuseSpec {
+  int mode = 0;
+  AgdStepArgs agd = {};
+  PeerArgs peer = {};
+};
+
 static int launch_eval(dualip_plan* p, const float* lambda, const float* b, double gamma, float* grad_out,
                        dualip_scalars* scalars_out, float* partial_out, float* x_out, uint8_t* diag, int do_epilogue,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const FuseSpec* fuse = nullptr) {
   if (!(gamma > 0.0) && !(gamma < 0.0)) {
     set_error("gamma must be non-zero");
     return DUALIP_EINVAL;
@@ -1468,6 +1489,14 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.long_a = p->long_a;
   k.long_c = p->long_c;
   k.long_row = p->long_row;
+  k.fuse = fuse ? fuse->mode : 0;
+  if (fuse) {
+    k.agd = fuse->agd;
+    k.peer = fuse->peer;
+  } else {
+    memset(&k.agd, 0, sizeof(k.agd));
+    memset(&k.peer, 0, sizeof(k.peer));
+  }
   if (p->n_long > 0) {
     const int blocks = (int)std::min<int64_t>((p->n_long + 7) / 8, (int64_t)p->n_sms * 8);
     if (p->fixed_point)
@@ -1966,7 +1995,7 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   int stage_deg = env_stage ? atoi(env_stage) : kRegDeg;
   stage_deg = std::max(0, std::min(stage_deg, kRegDeg));
   p->row_bits = (p->m <= 65536) ? 16 : 32;
-  const size_t smem_max = std::min<size_t>(kSmemBudget, prop.sharedMemPerBlockOptin) - 2560;  // static smem (1920 B) + slack
+  const size_t smem_max = std::min<size_t>(kSmemBudget, prop.sharedMemPerBlockOptin) - 4096;  // static shared memory (block reductions) + slack
   const size_t need1 = fixed + 4 * m_pad + stash_bytes;
   const size_t n_warps = (size_t)(p->threads / 32);
   size_t region = 0;
@@ -2129,6 +2158,44 @@ int dualip_matching_partial(dualip_plan* p, const float* lambda_dev, double gamm
   DeviceGuard g(p->device);
   return launch_eval(p, lambda_dev, nullptr, gamma, nullptr, nullptr, partial_out_dev, x_out_dev, diag_out_dev, 0,
                      (cudaStream_t)stream);
+}
+
+int dualip_matching_ascent_step(dualip_plan* p, dualip_agd* a, const float* b_dev, double gamma, float* grad_out_dev,
+                                dualip_scalars* scalars_out_dev, float* x_out_dev, float beta, int32_t decay_now,
+                                double decay_factor, int32_t iter_index, void* stream) {
+  if (!p || !a || !grad_out_dev || !scalars_out_dev) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  if (a->m != p->m || a->device != p->device) {
+    set_error("optimizer state does not match the plan (m or device)");
+    return DUALIP_EINVAL;
+  }
+  DeviceGuard g(p->device);
+  FuseSpec f;
+  f.mode = 1;
+  f.agd = step_args(a, grad_out_dev, scalars_out_dev, beta, decay_now, decay_factor, iter_index, nullptr, 0.0, nullptr, nullptr);
+  return launch_eval(p, a->x, b_dev, gamma, grad_out_dev, scalars_out_dev, nullptr, x_out_dev, nullptr, 1, (cudaStream_t)stream, &f);
+}
+
+int dualip_matching_ascent_step_peer(dualip_plan* p, dualip_agd* a, dualip_peer* peer, const float* b_dev, double gamma,
+                                     float* grad_out_dev, dualip_scalars* scalars_out_dev, float beta, int32_t decay_now,
+                                     double decay_factor, int32_t iter_index, void* stream) {
+  if (!p || !a || !peer || !grad_out_dev || !scalars_out_dev) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  if (a->m != p->m || a->device != p->device || !peer->connected || peer->m != a->m || peer->device != a->device) {
+    set_error("optimizer state / exchange window do not match the plan, or the window is not connected");
+    return DUALIP_EINVAL;
+  }
+  DeviceGuard g(p->device);
+  FuseSpec f;
+  f.mode = 2;
+  f.peer = peer_args(peer, true);
+  float* slot = reinterpret_cast<float*>(peer->window + kPeerFlagBytes + (size_t)(f.peer.seq & 1ull) * peer->slot_bytes);
+  f.agd = step_args(a, peer->sum, nullptr, beta, decay_now, decay_factor, iter_index, b_dev, gamma, grad_out_dev, scalars_out_dev);
+  return launch_eval(p, a->x, nullptr, gamma, nullptr, nullptr, slot, nullptr, nullptr, 0, (cudaStream_t)stream, &f);
 }
 
 int dualip_matching_epilogue(const float* partial_sum_dev, int32_t m, const float* lambda_dev, const float* b_dev,

@@ -289,6 +289,23 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
                                                    self._stream())
         _native.check(rc, "dualip_matching_partial")
 
+    def launch_ascent_step(self, agd_handle, gamma: float, grad_ptr: int, scal_ptr: int, beta: float, decay_now: int,
+                           decay_factor: float, iter_index: int, x_ptr: Optional[int] = None) -> None:
+        """Evaluation at the optimizer's evaluation point + the accelerated step in ONE launch (dualip_matching_ascent_step)."""
+        b_ptr = self.b_vec.data_ptr() if self.b_vec is not None else None
+        rc = _native.lib().dualip_matching_ascent_step(self._plan, agd_handle, b_ptr, float(gamma), grad_ptr, scal_ptr, x_ptr,
+                                                       float(beta), int(decay_now), float(decay_factor), int(iter_index),
+                                                       self._stream())
+        _native.check(rc, "dualip_matching_ascent_step")
+
+    def launch_ascent_step_peer(self, agd_handle, peer_handle, b_ptr: int, gamma: float, grad_ptr: int, scal_ptr: int, beta: float,
+                                decay_now: int, decay_factor: float, iter_index: int) -> None:
+        """Sharded twin: shard kernel, exchange through peer memory, tail and step in ONE launch."""
+        rc = _native.lib().dualip_matching_ascent_step_peer(self._plan, agd_handle, peer_handle, b_ptr, float(gamma), grad_ptr,
+                                                            scal_ptr, float(beta), int(decay_now), float(decay_factor),
+                                                            int(iter_index), self._stream())
+        _native.check(rc, "dualip_matching_ascent_step_peer")
+
     @property
     def has_block_entries(self) -> bool:
         return bool(self._block_entries)
@@ -462,6 +479,9 @@ class MatchingSolverDualObjectiveFunctionDistributed(BaseObjective):
         """The NVLink exchange windows of this objective (dualip_b200.utils.peer_exchange), set up on first use.
         COLLECTIVE: every rank must call it at the same point.  None when the ranks cannot map each other's memory (not
         one host, not NCCL, DUALIP_PEER_EXCHANGE=0); the fused loop then uses the NCCL all-reduce."""
+        if getattr(self, "_peer_failed", False):
+            raise RuntimeError("the exchange windows of this objective timed out in an earlier run; build a new objective "
+                               "(or set DUALIP_PEER_EXCHANGE=0 for the NCCL path)")
         if not self._peer_tried:
             from dualip_b200.utils.peer_exchange import PeerExchange
 

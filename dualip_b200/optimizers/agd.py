@@ -313,6 +313,14 @@ class FusedAscentLoop:
         # sharded, no per-iteration callback: the partial sums are exchanged through peer memory inside the update kernel
         # (the choice must not depend on the rank: every rank takes the same path)
         self.peer = f.peer_exchange() if (self.sharded and not solver._user_callback_active()) else None
+        if self.peer is not None and dist.is_available() and dist.is_initialized():
+            # the windows may be reused from an earlier maximize(): nobody starts polling flags before every rank is here
+            dist.barrier()
+        # matching objectives whose columns are all projected natively: evaluation and step in one launch
+        from dualip_b200.objectives.matching import MatchingSolverDualObjectiveFunction
+
+        self.one_launch = (not self.block_entries and os.environ.get("DUALIP_ONE_LAUNCH", "1") != "0"
+                           and isinstance(local, MatchingSolverDualObjectiveFunction))
         self.primal = None
         self.kernel_events = None  # optional list of (start, end) CUDA events per step, for measurement
         self.kernel_events_base = 1
@@ -333,14 +341,25 @@ class FusedAscentLoop:
                 decay_now, factor = 1, float(solver.gamma_decay_params["decay_factor"])
             callback = self.rank == 0 and solver._user_callback_active()
             if self.sharded and self.peer is not None:
-                # shard kernel -> update kernel that reads every peer's partial sums over NVLink: no collective call
                 f.local_objective.gamma = gamma_i
-                f.local_objective.launch_partial(self.x_ptr, gamma_i, self.peer.next_slot())
-                if ev is not None:
-                    ev[1].record()
-                _native.check(self.lib.dualip_agd_step_peer(
-                    self.handle, self.peer.handle, f.b_vec.data_ptr(), float(gamma_i), self.grad.data_ptr(),
-                    self.scal.data_ptr(), float(self.beta[i - 1]), decay_now, factor, i - 1, stream), "dualip_agd_step_peer")
+                if self.one_launch:
+                    # ONE launch: shard kernel whose last CTA publishes the partial sums, reads every peer's over NVLink,
+                    # runs the objective's tail and takes the step -- no collective call, no second kernel
+                    f.local_objective.launch_ascent_step_peer(self.handle, self.peer.handle, f.b_vec.data_ptr(), gamma_i,
+                                                              self.grad.data_ptr(), self.scal.data_ptr(), self.beta[i - 1],
+                                                              decay_now, factor, i - 1)
+                    if ev is not None:
+                        ev[1].record()
+                else:
+                    # shard kernel -> update kernel that reads every peer's partial sums over NVLink
+                    f.local_objective.launch_partial(self.x_ptr, gamma_i, self.peer.next_slot())
+                    if ev is not None:
+                        ev[1].record()
+                    _native.check(self.lib.dualip_agd_step_peer(
+                        self.handle, self.peer.handle, f.b_vec.data_ptr(), float(gamma_i), self.grad.data_ptr(),
+                        self.scal.data_ptr(), float(self.beta[i - 1]), decay_now, factor, i - 1, stream), "dualip_agd_step_peer")
+                if (i & 31) == 0 and self.peer.status_nowait():
+                    self._peer_timed_out()
             elif self.sharded:
                 from dualip_b200.objectives.matching import reduce_partials
 
@@ -385,6 +404,17 @@ class FusedAscentLoop:
                     _native.check(self.lib.dualip_agd_step_sharded(
                         self.handle, self.partial.data_ptr(), b_ptr, float(gamma_i), self.grad.data_ptr(), self.scal.data_ptr(),
                         float(self.beta[i - 1]), decay_now, factor, i - 1, stream), "dualip_agd_step_sharded")
+            elif self.one_launch:
+                # evaluation at the optimizer's evaluation point and the accelerated step in ONE launch; a callback sees the
+                # result the kernel wrote before it stepped
+                if last_primal:
+                    self.primal = torch.empty(f.nnz, dtype=torch.float32, device=self.device)
+                f.launch_ascent_step(self.handle, gamma_i, self.grad.data_ptr(), self.scal.data_ptr(), self.beta[i - 1],
+                                     decay_now, factor, i - 1, self.primal.data_ptr() if last_primal else None)
+                if ev is not None:
+                    ev[1].record()
+                if callback:
+                    solver.iteration_callback(i, solver._callback_result(self.grad, self.scal, self.primal if last_primal else None))
             else:
                 if last_primal:
                     self.primal = torch.empty(getattr(f, "primal_size", f.nnz), dtype=torch.float32, device=self.device)
@@ -400,6 +430,13 @@ class FusedAscentLoop:
             if decay_now:
                 solver.gamma = solver.gamma * factor
         self.steps_done = max(self.steps_done, i)
+
+    def _peer_timed_out(self):
+        """A rank did not arrive within the time-out: this run is invalid and the windows are unusable from now on."""
+        self.f._peer_failed = True
+        self.f._peer = None
+        raise RuntimeError("peer exchange: a rank did not arrive within the time-out (ranks out of step?); results of this run "
+                           "are invalid.  DUALIP_PEER_EXCHANGE=0 selects the NCCL path")
 
     def _x_tensor(self, stream) -> torch.Tensor:
         """The evaluation point as a tensor (a copy of the native state's x), for the tensor-op part of block entries."""
@@ -427,8 +464,7 @@ class FusedAscentLoop:
                 if dist.is_available() and dist.is_initialized() and self.peer.world == dist.get_world_size():
                     dist.barrier()  # nobody frees or reuses a window a peer may still be reading
                 if timed_out:
-                    raise RuntimeError("peer exchange: a rank did not arrive within the time-out (ranks out of step?); "
-                                       "results of this run are invalid.  DUALIP_PEER_EXCHANGE=0 selects the NCCL path")
+                    self._peer_timed_out()
         dual_obj_log = [float(v) for v in obj_log[:n]]
         step_size_log = [float(v) for v in step_log[:n]]
         if self.decay and step_size_log:

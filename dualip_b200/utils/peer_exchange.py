@@ -105,6 +105,10 @@ class PeerExchange:
                                                       torch.cuda.current_stream(self.device).cuda_stream), "dualip_peer_status")
         return int(out.value)
 
+    def status_nowait(self) -> int:
+        """The time-out flag as the host sees it right now (mapped host memory; no synchronisation)."""
+        return int(self.lib.dualip_peer_status_nowait(self.handle))
+
     def close(self) -> None:
         if self.handle:
             self.lib.dualip_peer_destroy(self.handle)

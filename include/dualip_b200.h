@@ -228,6 +228,25 @@ int dualip_agd_step_peer(dualip_agd* agd, dualip_peer* peer, const float* b_dev,
                          dualip_scalars* scalars_out_dev, float beta, int32_t decay_now, double decay_factor,
                          int32_t iter_index, void* stream);
 
+/* 0 = fine, 1 = a wait timed out; reads a flag in mapped host memory, does not synchronise (poll it every few steps). */
+int dualip_peer_status_nowait(dualip_peer* peer);
+
+/* ---- one launch per iteration: evaluation at the optimizer's own evaluation point + the accelerated step ----
+ * dualip_matching_ascent_step = dualip_matching_calc(lambda = dualip_agd_x(agd)) followed by dualip_agd_step, in ONE kernel
+ * launch: the CTA of the fused kernel that finishes last runs the objective's m-length tail (grad_out_dev, scalars_out_dev
+ * are written as by dualip_matching_calc) and then takes the step on the device-resident state.  Replaces one turn of the
+ * loop of AcceleratedGradientDescent.maximize (reference optimizers/agd.py:150-206).  x_out_dev as for dualip_matching_calc. */
+int dualip_matching_ascent_step(dualip_plan* plan, dualip_agd* agd, const float* b_dev, double gamma, float* grad_out_dev,
+                                dualip_scalars* scalars_out_dev, float* x_out_dev, float beta, int32_t decay_now,
+                                double decay_factor, int32_t iter_index, void* stream);
+/* Sharded twin: dualip_matching_partial into this rank's exchange slot + dualip_agd_step_peer, in ONE launch.  The last CTA
+ * publishes the shard's packed sums, waits for the peers' arrival flags, adds all slots in rank order (peer-memory loads
+ * over NVLink), runs the tail and the step.  No collective call, no second launch (reference: three dist.reduce + barrier
+ * + two broadcasts per iteration, objectives/matching.py:272-277, optimizers/agd.py:204-206). */
+int dualip_matching_ascent_step_peer(dualip_plan* plan, dualip_agd* agd, dualip_peer* peer, const float* b_dev, double gamma,
+                                     float* grad_out_dev, dualip_scalars* scalars_out_dev, float beta, int32_t decay_now,
+                                     double decay_factor, int32_t iter_index, void* stream);
+
 /* ---- host-resident twin of the Maximizer state: for callers that keep the dual iterate in host memory and hand it to
  * dualip_matching_calc_host every iteration (the host-buffer path).  Same update as dualip_agd_step (agd.py:163-187,
  * agd_utils.py:4-89) in one call instead of ~25 tensor operations; needs no GPU.  x (the evaluation point) lives in

@@ -123,3 +123,39 @@ def test_bisection_method_on_the_device():
         assert abs(got[0] - scal[0]) <= 1e-5 * abs(scal[0])
         g, ref = r.dual_gradient.cpu().numpy(), d[f"grad_{tag}"]
         assert np.abs(g - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_one_launch_iteration_equals_two_launches(monkeypatch):
+    """dualip_matching_ascent_step (evaluation + accelerated step in one kernel launch, the default of the fused loop) against
+    dualip_matching_calc followed by dualip_agd_step: same logs and iterate, with step gamma decay and save_primal."""
+    import os
+
+    from conftest import random_problem
+    from dualip_b200.objectives.matching import MatchingInputArgs, MatchingSolverDualObjectiveFunction
+    from dualip_b200.optimizers.agd import AcceleratedGradientDescent, no_iteration_callback
+    from dualip_b200.projections import create_projection_map
+
+    p = random_problem(5, 20011, 300, 9.0, scale_c=10.0, lam_scale=0.5, long_cols=((3, 40), (77, 150)))
+    n, m = p["n_cols"], p["n_rows"]
+    ccol, row = torch.from_numpy(p["ccol"]), torch.from_numpy(p["row"])
+    A = torch.sparse_csc_tensor(ccol, row, torch.from_numpy(p["a"]), size=(m, n)).to("cuda:0")
+    C = torch.sparse_csc_tensor(ccol, row, torch.from_numpy(p["c"]), size=(m, n)).to("cuda:0")
+    pm = {}
+    pm.update(create_projection_map("simplex", {"z": 1.0}, n, indices=list(range(0, n, 2))))
+    pm.update(create_projection_map("box", {"lower": 0.0, "upper": 1.0}, n, indices=list(range(1, n, 2))))
+    out = {}
+    seen = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DUALIP_ONE_LAUNCH", mode)
+        obj = MatchingSolverDualObjectiveFunction(MatchingInputArgs(A, C, pm, torch.from_numpy(p["b"]).to("cuda:0")), gamma=2e-2)
+        seen[mode] = []
+        solver = AcceleratedGradientDescent(max_iter=45, gamma=2e-2, initial_step_size=1e-3, max_step_size=0.1, save_primal=True,
+                                            gamma_decay_type="step", gamma_decay_params={"decay_steps": 10, "decay_factor": 0.5},
+                                            iteration_callback=lambda i, r, mode=mode: seen[mode].append(float(r.dual_objective)))
+        out[mode] = solver.maximize(obj, torch.zeros(m, device="cuda:0"))
+    a, b = out["1"], out["0"]
+    assert np.allclose(a.dual_objective_log, b.dual_objective_log, rtol=1e-6) and np.allclose(a.step_size_log, b.step_size_log, rtol=1e-5)
+    assert torch.allclose(a.dual_val, b.dual_val, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(a.objective_result.primal_var, b.objective_result.primal_var, rtol=1e-4, atol=1e-6)
+    # the callback saw every iteration's result, as written by the kernel before it stepped
+    assert np.allclose(seen["1"], a.dual_objective_log, rtol=1e-6) and len(seen["1"]) == 45

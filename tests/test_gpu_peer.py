@@ -90,6 +90,35 @@ def test_peer_step_matches_summed_partials(world, n_rows, monkeypatch):
         assert np.array_equal(peer_logs[k][0], peer_logs[0][0]) and np.array_equal(peer_logs[k][1], peer_logs[0][1])
         assert torch.equal(peer_duals[k], peer_duals[0])
 
+    # (a') the same exchange fused into the shard kernel: ONE launch per rank and iteration (dualip_matching_ascent_step_peer)
+    fused = [_Rank(o, m, 1e-3, 0.1) for o in shards()]
+    ex2 = [PeerExchange(m, k, world, torch.device(DEV)) for k in range(world)]
+    PeerExchange.connect_local(ex2)
+    torch.cuda.synchronize()
+    for i in range(iters):
+        decay = 1 if (i + 1) % 9 == 0 else 0
+        g_i = gamma * 0.5 ** (i // 9)
+        for k, r in enumerate(fused):
+            with torch.cuda.stream(r.stream):
+                r.obj.launch_ascent_step_peer(r.agd, ex2[k].handle, b.data_ptr(), g_i, r.grad.data_ptr(), r.scal.data_ptr(),
+                                              beta[i], decay, 0.5, i)
+    torch.cuda.synchronize()
+    assert [e.status() for e in ex2] == [0] * world and [e.status_nowait() for e in ex2] == [0] * world
+    fused_logs = [r.logs(iters) for r in fused]
+    fused_duals = [r.dual() for r in fused]
+    for k in range(1, world):
+        assert np.array_equal(fused_logs[k][0], fused_logs[0][0]) and np.array_equal(fused_logs[k][1], fused_logs[0][1])
+        assert torch.equal(fused_duals[k], fused_duals[0])
+    # against the two-launch path: the same sums in the same order; only the block reductions of the step run with a different
+    # thread count (double precision partial sums in another order)
+    # (a last-bit difference in a Lipschitz ratio changes a step by one ulp; the ascent carries it along)
+    assert np.allclose(fused_logs[0][0], peer_logs[0][0], rtol=1e-6) and np.allclose(fused_logs[0][1], peer_logs[0][1], rtol=1e-5)
+    assert torch.allclose(fused_duals[0], peer_duals[0], rtol=1e-4, atol=1e-6)
+    for r in fused:
+        lib.dualip_agd_destroy(r.agd)
+    for e in ex2:
+        e.close()
+
     # (b) what a collective would do: partial sums added in rank order on the host side, then dualip_agd_step_sharded
     ref = _Rank(None, m, 1e-3, 0.1)
     objs = shards()
