@@ -56,6 +56,7 @@ SIGNATURES = {
     "dualip_last_error": (C.c_char_p, []),
     "dualip_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(CscDesc)]),
     "dualip_plan_destroy": (None, [C.c_void_p]),
+    "dualip_plan_rebalance": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dualip_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
     "dualip_matching_calc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),

@@ -126,6 +126,9 @@ struct dualip_plan {
   int n_groups = 0;
   std::vector<SlabGroup> groups_host;
   int2* cta_range = nullptr;      // n_ctas + 1 entries {first slab, first group} of every CTA's contiguous slab range
+  std::vector<int2> ranges_host;
+  unsigned int* cta_ns = nullptr; // per CTA: duration of its main loop in the last launch (ns), input of dualip_plan_rebalance
+  int rebalances = 0;
   SlabHdr* hdr = nullptr;         // per-slab headers (plan-time kernels, tests); not read by the hot kernel
   int64_t* orig_start = nullptr;  // per slab lane: first nnz position of the column in the caller's order, or -1
   int64_t n_slabs = 0;
@@ -288,6 +291,7 @@ struct KArgs {
   const SlabGroup* groups;
   int n_groups;
   const int2* cta_range;       // gridDim.x + 1 entries {first slab, first group}
+  unsigned int* cta_ns;        // per CTA: main-loop duration of this launch, ns
   const int64_t* orig_start;
   int64_t n_slabs;
   const dualip_proj_class* classes;
@@ -562,6 +566,8 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   __syncthreads();
 
   stamp(1);
+  unsigned long long t_loop0 = 0;
+  if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_loop0));
   // ---- stream slabs.  Every CTA owns a contiguous range of the (length, class)-ordered slab sequence, cut at plan time so
   //      that all ranges cost about the same: an SM then runs the code of one or two column lengths only (instruction
   //      cache), and since groups of equal length and different class are neighbours, every range holds the problem's mix
@@ -804,8 +810,13 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       // shortcut and resolves the sorted scan in closed form when the support has at most two entries.  Lanes with a
       // larger support run a Michelot threshold search on the stash; lanes with more than two non-zeros take pass 2.
       const float z = pc.z;
-      const bool stash = d <= kStashDeg;
-      float* __restrict__ su = s_stash + (size_t)warp * (kStashDeg * kSlabW) + lane;
+      // The stash holds u of the whole slab (d x 32 floats).  Kernels with the register path reach this code only for
+      // columns longer than it handles; those sit at the END of a CTA's range (the slab order is length-major), so no staged
+      // copy is in flight any more and the warp's staging region serves as the stash: the threshold search and pass 2 then
+      // read shared memory instead of re-streaming the column from L2.
+      const int stash_cap = FAST ? (use_stage ? (int)(region / (kSlabW * sizeof(float))) : 0) : kStashDeg;
+      const bool stash = d <= stash_cap;
+      float* __restrict__ su = (FAST ? reinterpret_cast<float*>(my_stage) : s_stash + (size_t)warp * (kStashDeg * kSlabW)) + lane;
       float S = 0.f, m1 = -1.f, m2 = -1.f, m3 = -1.f;
       int i2 = 0;
       const bool is_eq = pc.kind == DUALIP_PROJ_SIMPLEX_EQ;
@@ -1084,6 +1095,11 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
 
   // ---- flush per-CTA partial sums ----
   __syncthreads();
+  if (tid == 0 && k.cta_ns != nullptr) {  // how long this CTA's range took: feedback for dualip_plan_rebalance
+    unsigned long long t_loop1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_loop1));
+    k.cta_ns[blockIdx.x] = (unsigned int)min(t_loop1 - t_loop0, 0xffffffffull);
+  }
   stamp(2);
   cx = block_sum(cx, dscratch);
   xx = block_sum(xx, dscratch);
@@ -1459,6 +1475,7 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.groups = p->groups;
   k.n_groups = p->n_groups;
   k.cta_range = p->cta_range;
+  k.cta_ns = p->cta_ns;
   k.orig_start = p->orig_start;
   k.n_slabs = p->n_slabs;
   k.classes = p->classes_dev;
@@ -1712,51 +1729,55 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
   return rc;
 }
 
-// Cuts the slab sequence into n_ctas contiguous ranges of about equal cost.  Cost of a slab by projection kind and column
-// length d, fitted on B200 to per-CTA main-loop times of the C3 workload at a late iterate (100M- and 12.5M-entity shards
-// agree within 10 %; residual of the fit 2 % mean, 6 % max: profiles/r2), in units of 7.5 ns per CTA:
+// Cost of a slab by projection kind and column length d, fitted on B200 to per-CTA main-loop times of the C3 workload at a
+// late iterate (100M- and 12.5M-entity shards agree within 10 %; residual of the fit 2 % mean, 6 % max: profiles/r2), in
+// units of 7.5 ns per CTA:
 //   simplex  4.0 + d (d <= 14, staged two deep)   1.27 d (15..16)   1.61 d (17..20, a and c are read twice)
 //   clamp    2.8 + 0.56 d (d <= 14)               0.76 d (15..20)
-//   generic path (longer columns, or a plan without the register path): simplex 6.7 d (iterative threshold search over
-//   re-streamed data), clamp 2.7 d.  DUALIP_COST_SCALE_SIMPLEX / _GENERIC rescale for experiments.
-static int build_cta_ranges(dualip_plan* p) {
-  const char* e1 = getenv("DUALIP_COST_SCALE_SIMPLEX");
-  const char* e2 = getenv("DUALIP_COST_SCALE_GENERIC");
-  const double ks = e1 ? atof(e1) : 1.0, kg = e2 ? atof(e2) : 1.0;
+//   generic path (longer columns, or a plan without the register path): simplex 6.7 d (iterative threshold search), clamp 2.7 d.
+// The table only seeds the partition: dualip_plan_rebalance corrects it with measured per-CTA times.
+static double slab_cost(const dualip_plan* p, const SlabGroup& g) {
   const bool fast = p->row_bits == 16 && p->smode == 0;
-  auto cost = [&](const SlabGroup& g) {
-    const bool simplex = p->classes_host[g.cls].kind != DUALIP_PROJ_CLAMP;
-    const double d = (double)g.d;
-    if (!fast || g.d > kRegDeg) return kg * (simplex ? 6.7 * d : 2.7 * d);
-    if (simplex) return ks * (g.d <= 14 ? 4.0 + d : (g.d <= 16 ? 1.27 * d : 1.61 * d));
-    return g.d <= 14 ? 2.8 + 0.56 * d : 0.76 * d;
-  };
+  const bool simplex = p->classes_host[g.cls].kind != DUALIP_PROJ_CLAMP;
+  const double d = (double)g.d;
+  if (!fast || g.d > kRegDeg) return simplex ? 6.7 * d : 2.7 * d;
+  if (simplex) return g.d <= 14 ? 4.0 + d : (g.d <= 16 ? 1.27 * d : 1.61 * d);
+  return g.d <= 14 ? 2.8 + 0.56 * d : 0.76 * d;
+}
+
+// A run of consecutive slabs of one group with one cost per slab.
+struct CostPiece {
+  int group;
+  int64_t slab_begin, n_slabs;
+  double cost;
+};
+
+// Cuts the slab sequence (given as cost pieces in slab order) into n_ctas contiguous ranges of about equal cost.
+static std::vector<int2> cut_ranges(const dualip_plan* p, const std::vector<CostPiece>& pieces) {
   double total = 0.0;
-  for (const SlabGroup& g : p->groups_host) total += cost(g) * (double)g.n_slabs;
+  for (const CostPiece& c : pieces) total += c.cost * (double)c.n_slabs;
   std::vector<int2> r((size_t)p->n_ctas + 1);
-  const int G = (int)p->groups_host.size();
-  int gi = 0;            // current group
-  int64_t used = 0;      // slabs of group gi already handed out
-  double acc = 0.0;      // cost handed out so far
+  const int P = (int)pieces.size(), G = (int)p->groups_host.size();
+  int pi = 0;
+  int64_t used = 0;
+  double acc = 0.0;
   for (int c = 0; c < p->n_ctas; ++c) {
-    while (gi < G && used >= (int64_t)p->groups_host[gi].n_slabs) {
-      ++gi;
+    while (pi < P && used >= pieces[pi].n_slabs) {
+      ++pi;
       used = 0;
     }
-    r[c].x = gi < G ? (int)(p->groups_host[gi].slab_begin + used) : (int)p->n_slabs;
-    r[c].y = gi < G ? gi : G;
+    r[c].x = pi < P ? (int)(pieces[pi].slab_begin + used) : (int)p->n_slabs;
+    r[c].y = pi < P ? pieces[pi].group : G;
     const double target = total * (double)(c + 1) / (double)p->n_ctas;
-    while (gi < G && acc < target) {
-      const SlabGroup& g = p->groups_host[gi];
-      const double cs = cost(g);
-      const int64_t left = (int64_t)g.n_slabs - used;
-      int64_t take = (int64_t)ceil((target - acc) / cs);
-      if (take > left) take = left;
-      if (take < 0) take = 0;
+    while (pi < P && acc < target) {
+      const CostPiece& pc = pieces[pi];
+      const int64_t left = pc.n_slabs - used;
+      int64_t take = pc.cost > 0.0 ? (int64_t)ceil((target - acc) / pc.cost) : left;
+      take = std::max<int64_t>(0, std::min(take, left));
       used += take;
-      acc += cs * (double)take;
-      if (used >= (int64_t)g.n_slabs) {
-        ++gi;
+      acc += pc.cost * (double)take;
+      if (used >= pc.n_slabs) {
+        ++pi;
         used = 0;
       } else {
         break;
@@ -1765,22 +1786,45 @@ static int build_cta_ranges(dualip_plan* p) {
   }
   r[p->n_ctas].x = (int)p->n_slabs;
   r[p->n_ctas].y = G;
-  // the last range ends at the last slab whatever the rounding did
-  cudaFree(p->cta_range);
-  p->cta_range = nullptr;
-  if (cudaMalloc(&p->cta_range, sizeof(int2) * r.size()) != cudaSuccess ||
-      cudaMemcpy(p->cta_range, r.data(), sizeof(int2) * r.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+  return r;
+}
+
+static int upload_ranges(dualip_plan* p, const std::vector<int2>& r, cudaStream_t stream) {
+  if (!p->cta_range && cudaMalloc(&p->cta_range, sizeof(int2) * r.size()) != cudaSuccess) {
     set_error("allocating the CTA range table failed");
     return DUALIP_ECUDA;
   }
+  p->ranges_host = r;  // the copy below reads this vector: it lives as long as the plan, and a later upload synchronises first
+  if (cudaMemcpyAsync(p->cta_range, p->ranges_host.data(), sizeof(int2) * r.size(), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+      cudaStreamSynchronize(stream) != cudaSuccess) {
+    set_error("uploading the CTA range table failed");
+    return DUALIP_ECUDA;
+  }
   return DUALIP_OK;
+}
+
+static int build_cta_ranges(dualip_plan* p) {
+  std::vector<CostPiece> pieces;
+  for (int g = 0; g < (int)p->groups_host.size(); ++g) {
+    const SlabGroup& sg = p->groups_host[g];
+    pieces.push_back({g, (int64_t)sg.slab_begin, (int64_t)sg.n_slabs, slab_cost(p, sg)});
+  }
+  if (!p->cta_ns) {
+    if (cudaMalloc(&p->cta_ns, sizeof(unsigned int) * (size_t)std::max(p->n_ctas, 1)) != cudaSuccess) {
+      set_error("allocating the per-CTA timers failed");
+      return DUALIP_ECUDA;
+    }
+    cudaMemset(p->cta_ns, 0, sizeof(unsigned int) * (size_t)std::max(p->n_ctas, 1));
+  }
+  return upload_ranges(p, cut_ranges(p, pieces), 0);
 }
 
 // Chooses the accumulation mode of a plan.  Fixed point needs (a) a finite bound on x for every class, (b) the register /
 // shared-memory configuration it is built for (uint16 rows, lambda + accumulator in shared memory), and (c) enough
 // resolution: with quantum q = 2^-F the rounding error of a row sum of N terms is ~ q*sqrt(N/12); it must stay below a
 // few fp32 ulps of the row's largest possible sum, otherwise (heavy-tailed row bounds) the plan keeps fp32 atomics.
-static int choose_accumulator(dualip_plan* p, cudaStream_t stream) {
+// keep_bits < 0: plan construction.  keep_bits >= 0: re-check after the CTA ranges moved; F stays at keep_bits if it still fits.
+static int choose_accumulator(dualip_plan* p, cudaStream_t stream, int keep_bits = -1) {
   p->fixed_point = 0;
   const char* env = getenv("DUALIP_ACCUM");
   if (env && strcmp(env, "f32") == 0) return DUALIP_OK;
@@ -1856,8 +1900,11 @@ static int choose_accumulator(dualip_plan* p, cudaStream_t stream) {
   if (!(bmax < INFINITY) || !(total_max < INFINITY)) return DUALIP_OK;
   // the float table itself carries rounding error: 1.001 covers it.  B * 2^F <= 2^30 leaves 2^30 of headroom for the
   // +-1/2 per term of the integer rounding (up to 2^31 terms).
+  // One more bit is left free at plan time so that dualip_plan_rebalance can move the CTA ranges without changing F (the
+  // sums stay bit-identical across rebalances); a rebalance lowers F only if a range's bound grew past that.
   int F = 20;
-  if (bmax > 0.0) F = (int)floor(log2(1073741824.0 / (bmax * 1.001)));
+  if (bmax > 0.0) F = (int)floor(log2(1073741824.0 / (bmax * 1.001))) - (keep_bits < 0 ? 1 : 0);
+  if (keep_bits >= 0 && F > keep_bits) F = keep_bits;
   F = std::max(-64, std::min(64, F));
   const double q = ldexp(1.0, -F);
   if (total_max * 1.001 * ldexp(1.0, F) >= 7.0e13) return DUALIP_OK;  // grid-wide high parts must fit 32 bits (2^46 = 7.04e13)
@@ -2121,6 +2168,68 @@ int dualip_debug_layout(dualip_plan* p, int64_t* groups_out, int cap_groups, int
   if (p->cta_range) cudaMemcpy(r.data(), p->cta_range, sizeof(int2) * r.size(), cudaMemcpyDeviceToHost);
   for (int i = 0; i <= p->n_ctas && i < cap_ranges; ++i) ranges_out[i] = r[i].x;
   return G;
+}
+
+int dualip_plan_rebalance(dualip_plan* p, void* stream_v) {
+  if (!p) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  if (p->n_ctas < 2 || p->n_slabs == 0 || !p->cta_ns || p->ranges_host.empty()) return DUALIP_OK;
+  DeviceGuard g(p->device);
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  std::vector<unsigned int> ns((size_t)p->n_ctas);
+  DUALIP_CUDA_TRY(cudaStreamSynchronize(stream));
+  DUALIP_CUDA_TRY(cudaMemcpy(ns.data(), p->cta_ns, sizeof(unsigned int) * ns.size(), cudaMemcpyDeviceToHost));
+  // measured time per unit of table cost in every current range; ranges the table got right have the same ratio
+  const std::vector<int2> old = p->ranges_host;
+  const int G = (int)p->groups_host.size();
+  std::vector<CostPiece> pieces;
+  std::vector<double> model((size_t)p->n_ctas, 0.0);
+  std::vector<int> owner;
+  for (int c = 0; c < p->n_ctas; ++c) {
+    const int64_t a = old[c].x, b = old[c + 1].x;
+    for (int gi = old[c].y; gi < G && (int64_t)p->groups_host[gi].slab_begin < b; ++gi) {
+      const SlabGroup& sg = p->groups_host[gi];
+      const int64_t lo = std::max<int64_t>(a, sg.slab_begin), hi = std::min<int64_t>(b, (int64_t)sg.slab_begin + sg.n_slabs);
+      if (hi <= lo) continue;
+      const double cs = slab_cost(p, sg);
+      pieces.push_back({gi, lo, hi - lo, cs});
+      owner.push_back(c);
+      model[c] += cs * (double)(hi - lo);
+    }
+  }
+  double sum_t = 0.0, sum_m = 0.0;
+  for (int c = 0; c < p->n_ctas; ++c) {
+    if (ns[c] == 0 && model[c] > 0.0) return DUALIP_OK;  // no launch since the last upload: nothing measured
+    sum_t += (double)ns[c];
+    sum_m += model[c];
+  }
+  if (!(sum_t > 0.0) || !(sum_m > 0.0)) return DUALIP_OK;
+  const double mean_scale = sum_t / sum_m;
+  for (size_t i = 0; i < pieces.size(); ++i) {
+    const int c = owner[i];
+    double rel = model[c] > 0.0 ? ((double)ns[c] / model[c]) / mean_scale : 1.0;
+    rel = std::min(4.0, std::max(0.25, rel));
+    pieces[i].cost *= pow(rel, 0.85);  // damped: moving a boundary changes what the neighbours contend for
+  }
+  const std::vector<int2> fresh = cut_ranges(p, pieces);
+  const int was_fixed = p->fixed_point, old_bits = p->fx_bits;
+  const float old_scale = p->fx_scale;
+  const double old_inv = p->fx_inv, old_bound = p->fx_bound, old_relerr = p->fx_relerr;
+  int rc = upload_ranges(p, fresh, stream);
+  if (rc != DUALIP_OK) return rc;
+  if (was_fixed) {
+    rc = choose_accumulator(p, stream, old_bits);
+    if (rc != DUALIP_OK || !p->fixed_point) {  // the new ranges do not admit the fixed-point sums: keep the old partition
+      p->fixed_point = was_fixed, p->fx_bits = old_bits, p->fx_scale = old_scale, p->fx_inv = old_inv;
+      p->fx_bound = old_bound, p->fx_relerr = old_relerr;
+      return upload_ranges(p, old, stream);
+    }
+  }
+  cudaMemsetAsync(p->cta_ns, 0, sizeof(unsigned int) * ns.size(), stream);
+  ++p->rebalances;
+  return DUALIP_OK;
 }
 
 int dualip_plan_info(const dualip_plan* p, int64_t* out, int cap) {

@@ -7,6 +7,7 @@ CUDA-only: tensors must live on a CUDA device and be float32.  There is no CPU f
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -245,6 +246,8 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
         torch.cuda.synchronize(self.device)
         _native.check(_native.lib().dualip_plan_create(ctypes.byref(handle), ctypes.byref(desc)), "dualip_plan_create")
         self._plan = handle
+        self._launches = 0
+        self._rebalance_at = (4, 8, 16, 32, 64, 128) if os.environ.get("DUALIP_REBALANCE", "1") != "0" else ()
         self._scal = torch.zeros(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=self.device)
         self._grad = torch.empty(self.m, dtype=torch.float32, device=self.device)
         self._partial = torch.empty(self.m + 2, dtype=torch.float32, device=self.device)
@@ -275,6 +278,16 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
     # -- raw launches (device pointers; used by the Maximizer's fused loop) ---------------------------------
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def launched(self) -> None:
+        """Self-tuning of the plan, called by `calculate` and by the Maximizer's loop after every evaluation: after 4, 8,
+        ..., 128 launches the per-CTA slab ranges are re-cut from the per-CTA times the kernel recorded
+        (dualip_plan_rebalance; a stream synchronisation each, six in the life of an objective).  Results are unaffected;
+        DUALIP_REBALANCE=0 disables it.  The raw launch_* methods do not call it: a caller that drives several shards of
+        one exchange group from ONE host thread must not synchronise one of them while its peers have not launched."""
+        self._launches += 1
+        if self._launches in self._rebalance_at:
+            _native.check(_native.lib().dualip_plan_rebalance(self._plan, self._stream()), "dualip_plan_rebalance")
 
     def launch_calc(self, lam_ptr: int, gamma: float, grad_ptr: int, scal_ptr: int, x_ptr: Optional[int] = None,
                     diag_ptr: Optional[int] = None) -> None:
@@ -359,6 +372,7 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
                 self._plan, self._h_lam.data_ptr(), self.b_vec.data_ptr() if self.b_vec is not None else None,
                 float(self.gamma), self._h_grad.data_ptr(), self._h_scal.data_ptr(), self._stream())
         _native.check(rc, "dualip_matching_calc_host")
+        self.launched()
         return _host_result(self._h_grad.clone(), self._h_scal.clone(), self.is_distributed)
 
     def host_io_bytes(self) -> tuple:
@@ -400,6 +414,7 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
                 self.launch_calc(lam.data_ptr(), self.gamma, grad.data_ptr(), scal.data_ptr(),
                                  x.data_ptr() if x is not None else None, diag.data_ptr() if diag is not None else None)
             s32 = scal.to(torch.float32)
+            self.launched()
         if not self.is_distributed:
             res = ObjectiveResult(
                 dual_gradient=grad,
@@ -528,6 +543,7 @@ class MatchingSolverDualObjectiveFunctionDistributed(BaseObjective):
             scal = torch.empty(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=self.device)
             self.launch_partial_and_reduce(lam.data_ptr(), self.gamma, partial, lam)
             self.launch_epilogue(partial.data_ptr(), lam.data_ptr(), self.gamma, grad.data_ptr(), scal.data_ptr())
+            self.local_objective.launched()
             if host_io:
                 self._h_grad.copy_(grad, non_blocking=True)
                 self._h_scal.copy_(scal, non_blocking=True)

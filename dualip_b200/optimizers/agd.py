@@ -321,6 +321,9 @@ class FusedAscentLoop:
 
         self.one_launch = (not self.block_entries and os.environ.get("DUALIP_ONE_LAUNCH", "1") != "0"
                            and isinstance(local, MatchingSolverDualObjectiveFunction))
+        # plan self-tuning needs a host synchronisation now and then: fine for one shard per process (every rank does it at
+        # the same iteration), not offered to objectives without a plan
+        self._tune = local if hasattr(local, "launched") else None
         self.primal = None
         self.kernel_events = None  # optional list of (start, end) CUDA events per step, for measurement
         self.kernel_events_base = 1
@@ -429,6 +432,8 @@ class FusedAscentLoop:
                               "dualip_agd_step")
             if decay_now:
                 solver.gamma = solver.gamma * factor
+            if self._tune is not None:
+                self._tune.launched()  # re-cuts the plan's per-CTA ranges after a few launches (a stream sync each time)
         self.steps_done = max(self.steps_done, i)
 
     def _peer_timed_out(self):

@@ -103,6 +103,12 @@ const char* dualip_last_error(void);
 int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* desc);
 void dualip_plan_destroy(dualip_plan* plan);
 
+/* Re-cuts the per-CTA slab ranges of the plan from the per-CTA durations the hot kernel recorded in its last launch (the
+ * plan starts from a fitted cost table; the cost of a simplex column depends on the iterate).  Synchronises `stream`.
+ * Results do not change: columns are projected independently of the partition and the fixed-point gradient sums are exact
+ * integers (their scale is kept unless a range's overflow bound forces it down).  Call it a few times early in a solve. */
+int dualip_plan_rebalance(dualip_plan* plan, void* stream);
+
 /* Introspection: fills up to `cap` int64 values:
  * [0] n_slabs [1] n_long_cols [2] n_ctas [3] threads/cta [4] smem bytes/cta [5] row index bits
  * [6] smem mode (0: lambda+grad in smem, 1: grad in smem, 2: neither) [7] stored slab elements (incl. padding)
