@@ -18,7 +18,7 @@ namespace dualip {
 
 template <bool FROM_PARTIAL>
 __global__ void __launch_bounds__(1024) agd_step_kernel(const AgdStepArgs A) {
-  agd_step_body<FROM_PARTIAL>(A);
+  agd_step_body<FROM_PARTIAL>(A, step_dyn_of(A));
 }
 
 // ceil((m+2) / 4096) CTAs of 1024 threads.  CTA 0 tells every peer that this rank's partial sums (written by the preceding
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(1024) agd_step_peer_kernel(const AgdStepArgs A
   } else {
     __syncthreads();  // P.sum is read below by other threads of this CTA
   }
-  agd_step_body<true>(A);
+  agd_step_body<true>(A, step_dyn_of(A));
 }
 
 }  // namespace dualip
@@ -105,8 +105,44 @@ void dualip_agd_destroy(dualip_agd* a) {
   cudaFree(a->eqmask);
   cudaFree(a->log_obj);
   cudaFree(a->log_step);
+  cudaFree(a->sched_gamma);
+  cudaFree(a->sched_beta);
+  cudaFree(a->sched_decay);
   delete a;
 }
+
+int dualip_agd_set_schedule(dualip_agd* a, int32_t n_iters, const double* gamma_host, const float* beta_host,
+                            const uint8_t* decay_now_host, double decay_factor) {
+  if (!a || n_iters <= 0 || !gamma_host || !beta_host) {
+    set_error("bad argument");
+    return DUALIP_EINVAL;
+  }
+  for (int i = 0; i < n_iters; ++i)
+    if (!(gamma_host[i] > 0.0) && !(gamma_host[i] < 0.0)) {
+      set_error("gamma must be non-zero (iteration %d)", i);
+      return DUALIP_EINVAL;
+    }
+  DeviceGuard g(a->device);
+  DUALIP_CUDA_TRY(cudaDeviceSynchronize());  // launches that read an earlier schedule have finished
+  cudaFree(a->sched_gamma);
+  cudaFree(a->sched_beta);
+  cudaFree(a->sched_decay);
+  a->sched_gamma = nullptr, a->sched_beta = nullptr, a->sched_decay = nullptr, a->sched_n = 0;
+  DUALIP_CUDA_TRY(cudaMalloc(&a->sched_gamma, sizeof(double) * n_iters));
+  DUALIP_CUDA_TRY(cudaMalloc(&a->sched_beta, sizeof(float) * n_iters));
+  DUALIP_CUDA_TRY(cudaMalloc(&a->sched_decay, n_iters));
+  DUALIP_CUDA_TRY(cudaMemcpy(a->sched_gamma, gamma_host, sizeof(double) * n_iters, cudaMemcpyHostToDevice));
+  DUALIP_CUDA_TRY(cudaMemcpy(a->sched_beta, beta_host, sizeof(float) * n_iters, cudaMemcpyHostToDevice));
+  if (decay_now_host)
+    DUALIP_CUDA_TRY(cudaMemcpy(a->sched_decay, decay_now_host, n_iters, cudaMemcpyHostToDevice));
+  else
+    DUALIP_CUDA_TRY(cudaMemset(a->sched_decay, 0, n_iters));
+  a->sched_n = n_iters;
+  a->sched_factor = decay_factor;
+  return DUALIP_OK;
+}
+
+long long dualip_agd_steps_launched(const dualip_agd* a) { return a ? a->launched : -1; }
 
 int dualip_agd_reserve_log(dualip_agd* a, int32_t capacity) {
   if (!a || capacity < 0) {

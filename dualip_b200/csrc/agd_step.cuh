@@ -31,10 +31,36 @@ struct AgdStepArgs {
   double gamma;
   float* grad_out;
   dualip_scalars* scal_out;
+  int log_cap;  // entries of log_obj / log_step (scheduled launches check the device-side iteration index against it)
 };
 
+// What changes from one iteration to the next.  Launches issued one by one pass these as kernel arguments (AgdStepArgs);
+// scheduled launches -- identical kernel arguments every iteration, hence capturable in a CUDA graph that is replayed --
+// read them from a device-resident schedule at index `*pushes` (the number of steps the state has taken).
+struct StepDyn {
+  float beta;
+  int decay_now;
+  int iter_index;
+  double gamma;
+  bool log;
+};
+struct SchedArgs {
+  const double* gamma;         // n entries: gamma of iteration i (null: not scheduled)
+  const float* beta;           // n entries: momentum of iteration i (agd.py:93-100)
+  const unsigned char* decay;  // n entries: 1 where the step cap is lowered after the iteration (agd.py:102-109)
+  int n;
+  long long seq_base;          // sharded: exchange step number of iteration i is seq_base + i + 1
+};
+__device__ __forceinline__ StepDyn step_dyn_of(const AgdStepArgs& A) {
+  return StepDyn{A.beta, A.decay_now, A.iter_index, A.gamma, A.log_obj != nullptr};
+}
+__device__ __forceinline__ StepDyn step_dyn_sched(const AgdStepArgs& A, const SchedArgs& S, long long it) {
+  const int i = (int)(it < (long long)S.n ? it : (long long)S.n - 1);
+  return StepDyn{S.beta[i], (int)S.decay[i], (int)it, S.gamma[i], A.log_obj != nullptr && it < (long long)A.log_cap};
+}
+
 template <bool FROM_PARTIAL>
-__device__ __forceinline__ void agd_step_body(const AgdStepArgs& A) {
+__device__ __forceinline__ void agd_step_body(const AgdStepArgs& A, const StepDyn& D) {
   float* __restrict__ x = A.x;
   float* __restrict__ y = A.y;
   float* __restrict__ gh = A.gh;
@@ -46,11 +72,11 @@ __device__ __forceinline__ void agd_step_body(const AgdStepArgs& A) {
   const float* grad = A.grad;
   const dualip_scalars* __restrict__ scal = A.scal;
   const int m = A.m, H = A.H;
-  const float beta = A.beta;
-  const int decay_now = A.decay_now, iter_index = A.iter_index;
-  const double decay_factor = A.decay_factor, gamma = A.gamma;
-  double* log_obj = A.log_obj;
-  double* log_step = A.log_step;
+  const float beta = D.beta;
+  const int decay_now = D.decay_now, iter_index = D.iter_index;
+  const double decay_factor = A.decay_factor, gamma = D.gamma;
+  double* log_obj = D.log ? A.log_obj : nullptr;
+  double* log_step = D.log ? A.log_step : nullptr;
   const float* __restrict__ b = A.b;
   float* grad_out = A.grad_out;
   dualip_scalars* __restrict__ scal_out = A.scal_out;
@@ -261,16 +287,16 @@ __device__ __forceinline__ float4 ld_relaxed_sys_f4(const float* p) {
 // The exchange by ONE CTA (the slab kernel's last CTA, after it has written this rank's packed sums into its slot): tell
 // every peer that the slot is ready, wait until all peers have said the same, fetch all slots -- W float4 loads in flight
 // per thread -- and add them in rank order, so that every rank computes bit-identical sums.  Result in P.sum.
-__device__ __forceinline__ void peer_exchange_cta(const PeerArgs& P, int m2) {
+__device__ __forceinline__ void peer_exchange_cta(const PeerArgs& P, int m2, unsigned long long seq) {
   const int tid = threadIdx.x, nt = blockDim.x;
   __threadfence_system();  // the slot written by this CTA's threads is visible system-wide before the flag
   __syncthreads();
   if (tid < P.world) {
-    st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.win[tid]) + P.rank, P.seq);
+    st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.win[tid]) + P.rank, seq);
     const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(P.win[P.rank]) + tid;
     const unsigned long long t0 = global_timer_ns();
     // once a wait has timed out the run is invalid (the host raises): later steps must not wait the full time-out again
-    while (*reinterpret_cast<volatile int*>(P.status) == 0 && ld_relaxed_sys_u64(mine) < P.seq) {
+    while (*reinterpret_cast<volatile int*>(P.status) == 0 && ld_relaxed_sys_u64(mine) < seq) {
       if (global_timer_ns() - t0 > P.timeout_ns) {
         *reinterpret_cast<volatile int*>(P.status) = 1;
         *reinterpret_cast<volatile int*>(P.status_host) = 1;
@@ -280,7 +306,7 @@ __device__ __forceinline__ void peer_exchange_cta(const PeerArgs& P, int m2) {
     asm volatile("fence.acq_rel.sys;" ::: "memory");  // the peers' slots are read after their flags
   }
   __syncthreads();
-  const size_t slot_off = (size_t)kPeerFlagBytes + (size_t)(P.seq & 1ull) * P.slot_bytes;
+  const size_t slot_off = (size_t)kPeerFlagBytes + (size_t)(seq & 1ull) * P.slot_bytes;
   for (int i4 = tid * 4; i4 < m2; i4 += nt * 4) {  // slots are padded to 128 bytes: a float4 never leaves the slot
     float4 v[DUALIP_PEER_MAX_WORLD];
 #pragma unroll
@@ -325,6 +351,13 @@ struct dualip_agd {
   double* log_obj = nullptr;
   double* log_step = nullptr;
   int log_cap = 0;
+  long long launched = 0;  // steps enqueued so far (host count; the device's `pushes` reaches it when the stream drains)
+  // device-resident schedule (dualip_agd_set_schedule)
+  double* sched_gamma = nullptr;
+  float* sched_beta = nullptr;
+  unsigned char* sched_decay = nullptr;
+  int sched_n = 0;
+  double sched_factor = 1.0;
 };
 
 struct dualip_peer {
@@ -370,6 +403,8 @@ static inline dualip::AgdStepArgs step_args(dualip_agd* a, const float* grad, co
   A.gamma = gamma;
   A.grad_out = grad_out;
   A.scal_out = scal_out;
+  A.log_cap = a->log_cap;
+  ++a->launched;
   return A;
 }
 

@@ -137,6 +137,7 @@ struct dualip_plan {
   // long columns (owned, compact copies)
   LongCol* longcols = nullptr;
   int64_t n_long = 0;
+  int64_t long_total = 0;         // entries of all long columns
   float* long_a = nullptr;
   float* long_c = nullptr;
   uint32_t* long_row = nullptr;
@@ -154,6 +155,9 @@ struct dualip_plan {
   double fx_inv = 1.0;         // 2^-F
   double fx_bound = 0.0;       // largest possible |row sum| inside one CTA
   double fx_relerr = 0.0;      // worst-row rounding error estimate relative to the row's largest possible sum
+  bool fx_bounded = false;     // every class bounds x and the kernel variant supports fixed point (only the resolution can fail)
+  std::vector<float> row_total_host;  // per row: sum |a| * xmax over all its entries (the row's largest possible sum)
+  float* row_unscale = nullptr;  // m floats 2^-k_r, or null: rows are stored scaled by 2^k_r (power-of-two row equilibration)
   double* acc_scal = nullptr;  // [c.x, ||x||^2], zero between calls
   unsigned int* counter = nullptr;
   float* lambda_stage = nullptr;  // m floats, for *_calc_host
@@ -304,6 +308,7 @@ struct KArgs {
   int* acc_hi;
   float fx_scale;            // 2^F
   double fx_inv;             // 2^-F
+  const float* row_unscale;  // m floats 2^-k_r (rows are stored as a * 2^k_r), or null
   double* acc_scal;          // 2 doubles
   unsigned int* counter;
   float* grad_out;           // calc mode
@@ -328,6 +333,10 @@ struct KArgs {
   int fuse;
   AgdStepArgs agd;
   PeerArgs peer;
+  // scheduled launch (fuse != 0 only): gamma, momentum, decay flag, log slot and exchange step number come from a
+  // device-resident schedule at index *agd.pushes, so the kernel arguments are the same for every iteration and a sequence
+  // of launches can be captured once in a CUDA graph and replayed (dualip_ascent_graph_*).  sched.gamma == null: off.
+  SchedArgs sched;
 };
 
 template <bool ROW16>
@@ -339,9 +348,9 @@ __device__ __forceinline__ uint32_t ld_row(const void* row_t, size_t idx) {
 // SMODE 0: scaled lambda and the gradient accumulator live in shared memory; 1: accumulator only (lambda is
 // gathered from global/L2); 2: neither (global atomics; only for very large m).
 template <int SMODE>
-__device__ __forceinline__ float lam_scaled(const KArgs& k, const float* s_lam, uint32_t r) {
+__device__ __forceinline__ float lam_scaled(const KArgs& k, float s, const float* s_lam, uint32_t r) {
   if (SMODE == 0) return s_lam[r];
-  return __fmul_rn(k.s, __ldg(k.lambda + r));
+  return __fmul_rn(s, __ldg(k.lambda + r));
 }
 template <int SMODE, int ACC>
 __device__ __forceinline__ void grad_add(const KArgs& k, float* s_grad, uint32_t r, float g) {
@@ -530,6 +539,14 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     }
   };
   stamp(0);
+  // per-iteration scalars: kernel arguments, or (scheduled launch) the schedule's entry for the iteration the optimizer
+  // state is at.  The counter is advanced by the last CTA of a launch, after every CTA has passed this point.
+  float s_run = k.s;
+  if (k.sched.gamma != nullptr) {
+    const long long it = __ldcg(k.agd.pushes);
+    const double g = __ldg(k.sched.gamma + (it < (long long)k.sched.n ? it : (long long)k.sched.n - 1));
+    s_run = (float)(-1.0 / g);  // matching.py:136 in Python double, rounded once when it meets the fp32 tensor
+  }
   constexpr bool FAST = ROW16 && (SMODE == 0);  // register path (slab_fast.cuh)
   const uint32_t s_grad_u32 = pin_u32(smem_u32(s_grad));
 
@@ -558,10 +575,13 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       mbar_wait(bar, 0);
       for (int i = (m & ~3) + tid; i < m; i += THREADS) s_lam[i] = k.lambda[i];
       __syncthreads();
-      for (int i = tid; i < m; i += THREADS) s_lam[i] = __fmul_rn(k.s, s_lam[i]);
+      for (int i = tid; i < m; i += THREADS) s_lam[i] = __fmul_rn(s_run, s_lam[i]);
     } else {
-      for (int i = tid; i < m; i += THREADS) s_lam[i] = __fmul_rn(k.s, k.lambda[i]);
+      for (int i = tid; i < m; i += THREADS) s_lam[i] = __fmul_rn(s_run, k.lambda[i]);
     }
+    // rows stored as a * 2^k_r: fl(a*2^k * fl(s*lambda)*2^-k) == fl(a * fl(s*lambda)), powers of two commute with rounding
+    if (k.row_unscale != nullptr)
+      for (int i = tid; i < m; i += THREADS) s_lam[i] = __fmul_rn(s_lam[i], __ldg(k.row_unscale + i));
   }
   __syncthreads();
 
@@ -575,7 +595,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   //      segment.  Inside a block of segments of equal length the warps start at different segments (rotation by warp
   //      index): at any time some warps of the SM run compute-heavy simplex slabs and others bandwidth-heavy clamp slabs. ----
   double cx = 0.0, xx = 0.0;
-  const float s = k.s;
+  const float s = s_run;
   using RowT = typename std::conditional<ROW16, unsigned short, uint32_t>::type;
   constexpr uint32_t RB = (uint32_t)row32_bytes(ROW16 ? 16 : 32);  // bytes per row of 32 entries
   const int2 range0 = k.cta_range[blockIdx.x];
@@ -768,7 +788,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       // ---- box / cone / identity: one streaming pass (box.py:16, cone.py:21-28) ----
       const float lo = active ? pc.lo : 0.f, hi = active ? pc.hi : 0.f;  // padding lanes produce x = 0
       auto body = [&](float a, float c, uint32_t r) {
-        const float v = make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c);
+        const float v = make_v(a, lam_scaled<SMODE>(k, s, s_lam, r), s, c);
         const float x = fminf(fmaxf(v, lo), hi);
         const float g = __fmul_rn(a, x);
         if (g != 0.f) grad_add<SMODE, ACC>(k, s_grad, r, g);
@@ -822,7 +842,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       const bool is_eq = pc.kind == DUALIP_PROJ_SIMPLEX_EQ;
       double Sd = 0.0;  // simplex_eq: the column sum in double (css_d of the reference's scan)
       auto track = [&](float a, float c, uint32_t r, int kq) {
-        const float u = fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);
+        const float u = fmaxf(make_v(a, lam_scaled<SMODE>(k, s, s_lam, r), s, c), 0.f);
         if (stash) su[kq * kSlabW] = u;
         if (is_eq) Sd += (double)u;
         S = __fadd_rn(S, u);  // column sum in entry order
@@ -942,7 +962,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
             float a, c;
             uint32_t r;
             ld1(kq, a, c, r);
-            return fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);
+            return fmaxf(make_v(a, lam_scaled<SMODE>(k, s, s_lam, r), s, c), 0.f);
           };
           // Newton steps from below on f(t) = sum max(u - t, 0) - z (Michelot): t <- (sum_{u>t} u - z)/#{u>t}.  Lower
           // bounds to start from: (S - z)/d, max - z, and the top-3 scan value t3 (the scan thresholds increase while
@@ -1020,7 +1040,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
             if (ST)
               u = su[kq * kSlabW];
             else
-              u = fmaxf(make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c), 0.f);
+              u = fmaxf(make_v(a, lam_scaled<SMODE>(k, s, s_lam, r), s, c), 0.f);
             const float x = (branch == 0) ? u : fmaxf(__fsub_rn(u, theta), 0.f);
             if (need_p2 && x != 0.f) {
               const float g = __fmul_rn(a, x);
@@ -1074,7 +1094,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
           float a, c;
           uint32_t r;
           ld1(kq, a, c, r);
-          const float v = make_v(a, lam_scaled<SMODE>(k, s_lam, r), s, c);
+          const float v = make_v(a, lam_scaled<SMODE>(k, s, s_lam, r), s, c);
           float x;
           if (branch < 0)
             x = fminf(fmaxf(v, pc.lo), pc.hi);
@@ -1173,11 +1193,12 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   const double cxv = __ldcg(&k.acc_scal[0]);
   const double xxv = __ldcg(&k.acc_scal[1]);
   auto sum_load = [&](int i) -> float {
+    const double un = k.row_unscale ? (double)__ldg(k.row_unscale + i) : 1.0;  // exact: a power of two
     if (ACC == 1) {
       const long long v = (long long)__ldcg(k.acc_hi + i) * 65536LL + (long long)__ldcg(k.acc_lo + i);
-      return (float)((double)v * k.fx_inv);
+      return (float)((double)v * k.fx_inv * un);
     }
-    return __ldcg(k.acc + i);
+    return (float)((double)__ldcg(k.acc + i) * un);
   };
   auto sum_clear = [&](int i) {  // leaves the accumulators zeroed for the next launch
     if (ACC == 1) {
@@ -1187,13 +1208,27 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       k.acc[i] = 0.f;
     }
   };
+  const bool scheduled = k.sched.gamma != nullptr;
+  // (read again rather than kept in registers across the main loop; the counter moves only inside agd_step_body, behind a
+  // CTA barrier that every thread reaches after this point)
+  long long sched_it = 0;
+  double gamma_run = k.gamma;
+  if (scheduled) {
+    sched_it = __ldcg(k.agd.pushes);
+    gamma_run = __ldg(k.sched.gamma + (sched_it < (long long)k.sched.n ? sched_it : (long long)k.sched.n - 1));
+  }
   if (k.do_epilogue) {
-    cta_epilogue(sum_load, sum_clear, cxv, xxv, k.lambda, k.b, m, k.gamma, k.grad_out, k.scalars_out, dscratch, fscratch);
+    cta_epilogue(sum_load, sum_clear, cxv, xxv, k.lambda, k.b, m, gamma_run, k.grad_out, k.scalars_out, dscratch, fscratch);
     if (k.fuse == 1) {
       __syncthreads();  // grad_out / scalars_out written above are read by other threads of this CTA
-      agd_step_body<false>(k.agd);
+      agd_step_body<false>(k.agd, scheduled ? step_dyn_sched(k.agd, k.sched, sched_it) : step_dyn_of(k.agd));
     }
   } else {
+    // sharded + scheduled: the exchange step number follows the device-side iteration count, and so does the slot
+    const unsigned long long seq = scheduled ? (unsigned long long)(k.sched.seq_base + sched_it + 1) : k.peer.seq;
+    float* partial_out = k.partial_out;
+    if (k.fuse == 2 && scheduled)
+      partial_out = reinterpret_cast<float*>(k.peer.win[k.peer.rank] + kPeerFlagBytes + (size_t)(seq & 1ull) * k.peer.slot_bytes);
     for (int base = tid; base < m; base += 4 * THREADS) {
       float raw[4];
 #pragma unroll
@@ -1202,16 +1237,16 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       for (int u = 0; u < 4; ++u)
         if (base + u * THREADS < m) {
           sum_clear(base + u * THREADS);
-          k.partial_out[base + u * THREADS] = raw[u];
+          partial_out[base + u * THREADS] = raw[u];
         }
     }
     if (tid == 0) {
-      k.partial_out[m] = (float)cxv;
-      k.partial_out[m + 1] = (float)xxv;
+      partial_out[m] = (float)cxv;
+      partial_out[m + 1] = (float)xxv;
     }
     if (k.fuse == 2) {
-      peer_exchange_cta(k.peer, m + 2);
-      agd_step_body<true>(k.agd);
+      peer_exchange_cta(k.peer, m + 2, seq);
+      agd_step_body<true>(k.agd, scheduled ? step_dyn_sched(k.agd, k.sched, sched_it) : step_dyn_of(k.agd));
     }
   }
   if (tid == 0) {
@@ -1235,6 +1270,11 @@ __global__ void __launch_bounds__(256) matching_long_kernel(const KArgs k, const
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   double cx = 0.0, xx = 0.0;
+  float s_run = k.s;
+  if (k.sched.gamma != nullptr) {  // scheduled launch: see matching_slab_kernel
+    const long long it = __ldcg(k.agd.pushes);
+    s_run = (float)(-1.0 / __ldg(k.sched.gamma + (it < (long long)k.sched.n ? it : (long long)k.sched.n - 1)));
+  }
   for (int64_t ci = warp_global; ci < n_long; ci += n_warps) {
     const LongCol lc = cols[ci];
     const dualip_proj_class pc = k.classes[lc.cls];
@@ -1245,7 +1285,9 @@ __global__ void __launch_bounds__(256) matching_long_kernel(const KArgs k, const
       av = __ldg(a + e);
       cv = __ldg(c + e);
       rv = __ldg(row + e);
-      return make_v(av, __fmul_rn(k.s, __ldg(k.lambda + rv)), k.s, cv);
+      float ls = __fmul_rn(s_run, __ldg(k.lambda + rv));
+      if (k.row_unscale != nullptr) ls = __fmul_rn(ls, __ldg(k.row_unscale + rv));  // long_a holds a * 2^k_r
+      return make_v(av, ls, s_run, cv);
     };
     const bool is_sx = pc.kind != DUALIP_PROJ_CLAMP;
     float theta = 0.f;
@@ -1461,6 +1503,7 @@ struct FuseSpec {
   int mode = 0;
   AgdStepArgs agd = {};
   PeerArgs peer = {};
+  SchedArgs sched = {};
 };
 
 static int launch_eval(dualip_plan* p, const float* lambda, const float* b, double gamma, float* grad_out,
@@ -1488,6 +1531,7 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.acc_hi = p->acc_hi;
   k.fx_scale = p->fx_scale;
   k.fx_inv = p->fx_inv;
+  k.row_unscale = p->row_unscale;
   k.acc_scal = p->acc_scal;
   k.counter = p->counter;
   k.grad_out = grad_out;
@@ -1510,9 +1554,11 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   if (fuse) {
     k.agd = fuse->agd;
     k.peer = fuse->peer;
+    k.sched = fuse->sched;
   } else {
     memset(&k.agd, 0, sizeof(k.agd));
     memset(&k.peer, 0, sizeof(k.peer));
+    memset(&k.sched, 0, sizeof(k.sched));
   }
   if (p->n_long > 0) {
     const int blocks = (int)std::min<int64_t>((p->n_long + 7) / 8, (int64_t)p->n_sms * 8);
@@ -1708,6 +1754,7 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
       p->class_used[c.cls & 0xff] = true;
     }
     BS_TRY(cudaMemcpyAsync(p->longcols, lc.data(), sizeof(LongCol) * n_long, cudaMemcpyHostToDevice, stream));
+    p->long_total = tot;
     BS_TRY(cudaMalloc(&p->long_a, sizeof(float) * tot));
     BS_TRY(cudaMalloc(&p->long_c, sizeof(float) * tot));
     BS_TRY(cudaMalloc(&p->long_row, sizeof(uint32_t) * tot));
@@ -1826,6 +1873,7 @@ static int build_cta_ranges(dualip_plan* p) {
 // keep_bits < 0: plan construction.  keep_bits >= 0: re-check after the CTA ranges moved; F stays at keep_bits if it still fits.
 static int choose_accumulator(dualip_plan* p, cudaStream_t stream, int keep_bits = -1) {
   p->fixed_point = 0;
+  p->fx_bounded = false;
   const char* env = getenv("DUALIP_ACCUM");
   if (env && strcmp(env, "f32") == 0) return DUALIP_OK;
   if (p->row_bits != 16 || p->smode != 0) return DUALIP_OK;
@@ -1893,11 +1941,14 @@ static int choose_accumulator(dualip_plan* p, cudaStream_t stream, int keep_bits
   cleanup();
 #undef CA_TRY
   double bmax = 0.0, total_max = 0.0;
+  p->row_total_host.assign((size_t)m, 0.f);
   for (int r = 0; r < m; ++r) {
     bmax = std::max(bmax, (double)h_max[r]);
     total_max = std::max(total_max, (double)h_sum[r] + (double)h_long[r]);
+    p->row_total_host[r] = h_sum[r] + h_long[r];
   }
   if (!(bmax < INFINITY) || !(total_max < INFINITY)) return DUALIP_OK;
+  p->fx_bounded = true;
   // the float table itself carries rounding error: 1.001 covers it.  B * 2^F <= 2^30 leaves 2^30 of headroom for the
   // +-1/2 per term of the integer rounding (up to 2^31 terms).
   // One more bit is left free at plan time so that dualip_plan_rebalance can move the CTA ranges without changing F (the
@@ -1921,6 +1972,75 @@ static int choose_accumulator(dualip_plan* p, cudaStream_t stream, int keep_bits
   const bool forced = env && strcmp(env, "fixed") == 0;
   if (relerr <= 2.4e-7 || forced) p->fixed_point = 1;
   return DUALIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Power-of-two row equilibration (plan time).  The fixed-point accumulator has ONE quantum 2^-F for all rows, sized by the
+// largest row sum a CTA can see; rows whose entries are orders of magnitude smaller (no Jacobi scaling, heavy-tailed row
+// scales) would lose relative precision and the plan used to fall back to fp32 compare-and-swap atomics.  Instead the plan
+// stores row r as a * 2^k_r, k_r = -floor(log2(sum_r |a| xmax)), and hands the kernel lambda' = fl(s*lambda_r) * 2^-k_r:
+// fl(a*2^k * lambda') == fl(a * fl(s*lambda_r)) bit for bit (a power of two commutes with rounding; |k_r| <= 40 keeps every
+// factor normal for data within 2^+-40 of 1), so v, the projection and x are unchanged, while the scatter adds
+// fl(a*x) * 2^(k_r + F): every row gets its own quantum.  The m-length tail multiplies the row sums by 2^-k_r (exact).
+// ------------------------------------------------------------------------------------------
+template <typename RowT>
+__global__ void scale_slab_rows_kernel(unsigned char* __restrict__ data, const SlabHdr* __restrict__ hdr, int64_t n_slabs,
+                                       const float* __restrict__ row_scale) {
+  const int lane = threadIdx.x & 31;
+  int64_t sl = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (; sl < n_slabs; sl += nw) {
+    const SlabHdr h = hdr[sl];
+    float* a_t = reinterpret_cast<float*>(data + (size_t)h.off32 * (size_t)row32_bytes(8 * (int)sizeof(RowT)));
+    const RowT* row_t = reinterpret_cast<const RowT*>(a_t + 2 * (size_t)h.d * kSlabW);
+    for (int i = lane; i < (int)h.d * kSlabW; i += 32) a_t[i] = __fmul_rn(a_t[i], row_scale[(uint32_t)row_t[i]]);  // padding: a = 0, row 0
+  }
+}
+__global__ void scale_long_rows_kernel(float* __restrict__ la, const uint32_t* __restrict__ lrow, int64_t total,
+                                       const float* __restrict__ row_scale) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < total; i += (int64_t)gridDim.x * blockDim.x) la[i] = __fmul_rn(la[i], row_scale[lrow[i]]);
+}
+
+// Called when the single-quantum accumulator lacks resolution: scales the stored rows and re-runs the choice.
+static int equilibrate_rows(dualip_plan* p, cudaStream_t stream) {
+  const int m = p->m;
+  std::vector<float> scale((size_t)m, 1.f), unscale((size_t)m, 1.f);
+  bool any = false;
+  for (int r = 0; r < m; ++r) {
+    const float A = p->row_total_host[r];
+    if (!(A > 0.f) || !(A < INFINITY)) continue;
+    int e = 0;
+    frexpf(A, &e);  // A = f * 2^e, f in [0.5, 1)
+    const int kr = std::max(-40, std::min(40, 1 - e));  // A * 2^kr in [1, 2)
+    if (kr != 0) any = true;
+    scale[r] = ldexpf(1.f, kr);
+    unscale[r] = ldexpf(1.f, -kr);
+  }
+  if (!any) return DUALIP_OK;
+  float* scale_d = nullptr;
+  if (cudaMalloc(&scale_d, sizeof(float) * m) != cudaSuccess || cudaMalloc(&p->row_unscale, sizeof(float) * m) != cudaSuccess) {
+    cudaFree(scale_d);
+    cudaFree(p->row_unscale);
+    p->row_unscale = nullptr;
+    cudaGetLastError();
+    return DUALIP_OK;  // no room: the plan keeps its fp32 accumulator
+  }
+  cudaMemcpyAsync(scale_d, scale.data(), sizeof(float) * m, cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(p->row_unscale, unscale.data(), sizeof(float) * m, cudaMemcpyHostToDevice, stream);
+  if (p->n_slabs > 0) {
+    const int blocks = (int)std::min<int64_t>((p->n_slabs + 7) / 8, (int64_t)p->n_sms * 16);
+    scale_slab_rows_kernel<unsigned short><<<blocks, 256, 0, stream>>>(p->data, p->hdr, p->n_slabs, scale_d);
+  }
+  if (p->n_long > 0 && p->long_total > 0)
+    scale_long_rows_kernel<<<p->n_sms * 8, 256, 0, stream>>>(p->long_a, p->long_row, p->long_total, scale_d);
+  cudaError_t e = cudaStreamSynchronize(stream);  // the host vectors are read by the copies above
+  cudaFree(scale_d);
+  if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
+    set_error("row equilibration failed: %s", cudaGetErrorString(e));
+    return DUALIP_ECUDA;
+  }
+  return choose_accumulator(p, stream);
 }
 
 }  // namespace dualip
@@ -1947,6 +2067,7 @@ void dualip_plan_destroy(dualip_plan* p) {
   cudaFree(p->long_row);
   cudaFree(p->classes_dev);
   cudaFree(p->pad_dev);
+  cudaFree(p->row_unscale);
   cudaFree(p->acc);
   cudaFree(p->acc_lo);
   cudaFree(p->timeline);
@@ -2098,6 +2219,11 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   {
     int rc = choose_accumulator(p, stream);
     if (rc != DUALIP_OK) return fail(rc);
+    const char* ers = getenv("DUALIP_ROW_SCALE");
+    if (!p->fixed_point && p->fx_bounded && !(ers && strcmp(ers, "0") == 0)) {
+      rc = equilibrate_rows(p, stream);  // one quantum does not resolve every row: per-row powers of two
+      if (rc != DUALIP_OK) return fail(rc);
+    }
   }
   // small state
   DUALIP_TRY_FAIL(cudaMalloc(&p->acc_lo, sizeof(int) * (m_pad + 4)));
@@ -2237,10 +2363,10 @@ int dualip_plan_info(const dualip_plan* p, int64_t* out, int cap) {
     set_error("null argument");
     return DUALIP_EINVAL;
   }
-  const int64_t v[16] = {p->n_slabs, p->n_long, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
+  const int64_t v[17] = {p->n_slabs, p->n_long, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
                          p->smode,   p->rows32 * kSlabW, (p->n_long > 0) ? 2 : 1, (int64_t)p->owned_bytes, p->n_short, p->nnz,
-                         p->fixed_point, p->fx_bits, (int64_t)(p->fx_relerr * 1e12), p->stage};
-  for (int i = 0; i < cap && i < 16; ++i) out[i] = v[i];
+                         p->fixed_point, p->fx_bits, (int64_t)(p->fx_relerr * 1e12), p->stage, p->row_unscale ? 1 : 0};
+  for (int i = 0; i < cap && i < 17; ++i) out[i] = v[i];
   return DUALIP_OK;
 }
 
@@ -2305,6 +2431,160 @@ int dualip_matching_ascent_step_peer(dualip_plan* p, dualip_agd* a, dualip_peer*
   float* slot = reinterpret_cast<float*>(peer->window + kPeerFlagBytes + (size_t)(f.peer.seq & 1ull) * peer->slot_bytes);
   f.agd = step_args(a, peer->sum, nullptr, beta, decay_now, decay_factor, iter_index, b_dev, gamma, grad_out_dev, scalars_out_dev);
   return launch_eval(p, a->x, nullptr, gamma, nullptr, nullptr, slot, nullptr, nullptr, 0, (cudaStream_t)stream, &f);
+}
+
+// Scheduled launch: dualip_matching_ascent_step[_peer] with gamma / beta / decay / log slot / exchange step number taken
+// from the schedule installed by dualip_agd_set_schedule at the device-side iteration count.  The kernel arguments do not
+// depend on the iteration, so the launch can be captured once and replayed.
+static int launch_scheduled(dualip_plan* p, dualip_agd* a, dualip_peer* peer, const float* b_dev, float* grad_out_dev,
+                            dualip_scalars* scalars_out_dev, cudaStream_t stream) {
+  FuseSpec f;
+  f.sched.gamma = a->sched_gamma;
+  f.sched.beta = a->sched_beta;
+  f.sched.decay = a->sched_decay;
+  f.sched.n = a->sched_n;
+  f.sched.seq_base = 0;
+  if (peer) {
+    f.mode = 2;
+    f.sched.seq_base = (long long)peer->seq - a->launched;  // invariant: both advance by one per step
+    f.peer = peer_args(peer, true);
+    f.agd = step_args(a, peer->sum, nullptr, 0.f, 0, a->sched_factor, 0, b_dev, 1.0, grad_out_dev, scalars_out_dev);
+  } else {
+    f.mode = 1;
+    f.agd = step_args(a, grad_out_dev, scalars_out_dev, 0.f, 0, a->sched_factor, 0, nullptr, 0.0, nullptr, nullptr);
+  }
+  f.agd.log_obj = a->log_obj;  // the kernel checks the iteration index against log_cap
+  f.agd.log_step = a->log_step;
+  // gamma = 1.0 below is a placeholder that passes launch_eval's argument check; scheduled kernels never read it
+  return launch_eval(p, a->x, peer ? nullptr : b_dev, 1.0, peer ? nullptr : grad_out_dev, peer ? nullptr : scalars_out_dev,
+                     nullptr, nullptr, nullptr, peer ? 0 : 1, stream, &f);
+}
+
+static int check_scheduled(dualip_plan* p, dualip_agd* a, dualip_peer* peer, float* grad_out_dev, dualip_scalars* scalars_out_dev) {
+  if (!p || !a || !grad_out_dev || !scalars_out_dev) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  if (a->m != p->m || a->device != p->device) {
+    set_error("optimizer state does not match the plan (m or device)");
+    return DUALIP_EINVAL;
+  }
+  if (a->sched_n <= 0) {
+    set_error("no schedule installed (dualip_agd_set_schedule)");
+    return DUALIP_EINVAL;
+  }
+  if (peer && (!peer->connected || peer->m != a->m || peer->device != a->device)) {
+    set_error("exchange window does not match the plan, or is not connected");
+    return DUALIP_EINVAL;
+  }
+  return DUALIP_OK;
+}
+
+int dualip_matching_ascent_step_scheduled(dualip_plan* p, dualip_agd* a, dualip_peer* peer, const float* b_dev,
+                                          float* grad_out_dev, dualip_scalars* scalars_out_dev, void* stream) {
+  int rc = check_scheduled(p, a, peer, grad_out_dev, scalars_out_dev);
+  if (rc != DUALIP_OK) return rc;
+  if (a->launched >= (long long)a->sched_n) {
+    set_error("the schedule holds %d iterations and all of them have been launched", a->sched_n);
+    return DUALIP_ERANGE;
+  }
+  DeviceGuard g(p->device);
+  return launch_scheduled(p, a, peer, b_dev, grad_out_dev, scalars_out_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+struct dualip_ascent_graph {
+  int device = 0;
+  int chunk = 0;
+  dualip_agd* agd = nullptr;
+  dualip_peer* peer = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+};
+
+extern "C" {
+
+void dualip_ascent_graph_destroy(dualip_ascent_graph* g) {
+  if (!g) return;
+  DeviceGuard dg(g->device);
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+}
+
+int dualip_ascent_graph_create(dualip_ascent_graph** out, dualip_plan* p, dualip_agd* a, dualip_peer* peer, const float* b_dev,
+                               float* grad_out_dev, dualip_scalars* scalars_out_dev, int32_t chunk) {
+  if (!out || chunk <= 0) {
+    set_error("bad argument");
+    return DUALIP_EINVAL;
+  }
+  *out = nullptr;
+  int rc = check_scheduled(p, a, peer, grad_out_dev, scalars_out_dev);
+  if (rc != DUALIP_OK) return rc;
+  DeviceGuard dg(p->device);
+  dualip_ascent_graph* g = new (std::nothrow) dualip_ascent_graph();
+  if (!g) return DUALIP_ENOMEM;
+  g->device = p->device;
+  g->chunk = chunk;
+  g->agd = a;
+  g->peer = peer;
+  // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured); the captured
+  // launches are not executed, so the host-side step counters are restored afterwards
+  cudaStream_t cs = nullptr;
+  const long long launched0 = a->launched;
+  const unsigned long long seq0 = peer ? peer->seq : 0ull;
+  cudaError_t e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) {
+    set_error("starting the stream capture failed: %s", cudaGetErrorString(e));
+    if (cs) cudaStreamDestroy(cs);
+    delete g;
+    return DUALIP_ECUDA;
+  }
+  for (int i = 0; i < chunk && rc == DUALIP_OK; ++i) {
+    rc = launch_scheduled(p, a, peer, b_dev, grad_out_dev, scalars_out_dev, cs);
+    // every captured launch must carry the SAME arguments: undo the counters so that seq_base / slot stay what they are
+    a->launched = launched0;
+    if (peer) peer->seq = seq0;
+  }
+  e = cudaStreamEndCapture(cs, &g->graph);
+  if (rc == DUALIP_OK && e != cudaSuccess) {
+    set_error("ending the stream capture failed: %s", cudaGetErrorString(e));
+    rc = DUALIP_ECUDA;
+  }
+  if (rc == DUALIP_OK) {
+    e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (e != cudaSuccess) {
+      set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+      rc = DUALIP_ECUDA;
+    }
+  }
+  cudaStreamDestroy(cs);
+  if (rc != DUALIP_OK) {
+    cudaGetLastError();
+    dualip_ascent_graph_destroy(g);
+    return rc;
+  }
+  *out = g;
+  return DUALIP_OK;
+}
+
+int dualip_ascent_graph_launch(dualip_ascent_graph* g, void* stream) {
+  if (!g || !g->exec) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  if (g->agd->launched + g->chunk > (long long)g->agd->sched_n) {
+    set_error("the schedule holds %d iterations: %lld launched, the graph takes %d more", g->agd->sched_n, g->agd->launched,
+              g->chunk);
+    return DUALIP_ERANGE;
+  }
+  DeviceGuard dg(g->device);
+  DUALIP_CUDA_TRY(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+  g->agd->launched += g->chunk;
+  if (g->peer) g->peer->seq += (unsigned long long)g->chunk;
+  return DUALIP_OK;
 }
 
 int dualip_matching_epilogue(const float* partial_sum_dev, int32_t m, const float* lambda_dev, const float* b_dev,

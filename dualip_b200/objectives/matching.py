@@ -263,11 +263,11 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
 
     # -- introspection -------------------------------------------------------------------------------------
     def plan_info(self) -> dict:
-        buf = (ctypes.c_int64 * 16)()
-        _native.check(_native.lib().dualip_plan_info(self._plan, buf, 16))
+        buf = (ctypes.c_int64 * 17)()
+        _native.check(_native.lib().dualip_plan_info(self._plan, buf, 17))
         names = ["n_slabs", "n_long_cols", "n_ctas", "threads", "smem_bytes", "row_bits", "smem_mode", "slab_elems",
                  "launches_per_calc", "owned_bytes", "n_slab_cols", "nnz", "fixed_point", "fixed_point_bits",
-                 "fixed_point_relerr_e12", "staged_degree"]
+                 "fixed_point_relerr_e12", "staged_degree", "row_scaled"]
         return dict(zip(names, list(buf)))
 
     def algorithmic_bytes(self, save_primal: bool = False) -> int:
@@ -288,6 +288,14 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
         self._launches += 1
         if self._launches in self._rebalance_at:
             _native.check(_native.lib().dualip_plan_rebalance(self._plan, self._stream()), "dualip_plan_rebalance")
+
+    def plan_settled(self) -> bool:
+        """True once no further re-cut of the plan is due (a CUDA graph captured from then on stays valid)."""
+        return not self._rebalance_at or self._launches >= self._rebalance_at[-1]
+
+    def launched_many(self, k: int) -> None:
+        """Accounts for k launches replayed from a CUDA graph (only taken when the plan has settled)."""
+        self._launches += k
 
     def launch_calc(self, lam_ptr: int, gamma: float, grad_ptr: int, scal_ptr: int, x_ptr: Optional[int] = None,
                     diag_ptr: Optional[int] = None) -> None:

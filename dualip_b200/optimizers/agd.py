@@ -137,8 +137,7 @@ class AcceleratedGradientDescent:
     def _maximize_fused(self, f, initial_value: torch.Tensor, rank: int) -> SolverResult:
         loop = FusedAscentLoop(self, f, initial_value, rank)
         try:
-            for i in range(1, self.max_iter + 1):
-                loop.step(i)
+            loop.run(1, self.max_iter)
             return loop.finish()
         finally:
             loop.close()
@@ -327,6 +326,77 @@ class FusedAscentLoop:
         self.primal = None
         self.kernel_events = None  # optional list of (start, end) CUDA events per step, for measurement
         self.kernel_events_base = 1
+        # CUDA-graph replay (run()): the one-launch iteration with its per-iteration scalars read from a device-resident
+        # schedule, so that `chunk` identical launches are captured once and replayed as one submission
+        self.graph_chunk = int(os.environ.get("DUALIP_GRAPH_CHUNK", "50"))
+        self.graphable = (self.one_launch and not solver._user_callback_active() and (not self.sharded or self.peer is not None)
+                          and os.environ.get("DUALIP_GRAPH", "1") != "0" and self.graph_chunk > 0)
+        self._graph = ctypes.c_void_p()
+        self.graph_launches = 0
+        if self.graphable:
+            self._install_schedule()
+
+    def _install_schedule(self) -> None:
+        """gamma / beta / decay flag of every iteration, exactly as step() would pass them (agd.py:93-109)."""
+        solver, n = self.solver, max(self.solver.max_iter, 1)
+        g = solver.gamma if solver.gamma is not None else self.f.gamma
+        gammas, flags = [], []
+        steps = solver.gamma_decay_params["decay_steps"] if self.decay else 0
+        factor = float(solver.gamma_decay_params["decay_factor"]) if self.decay else 1.0
+        for i in range(1, n + 1):
+            gammas.append(float(g))
+            d = 1 if (self.decay and i % steps == 0) else 0
+            flags.append(d)
+            if d:
+                g = g * factor
+        gammas.append(float(g))
+        self._gamma_sched = gammas  # [k] = gamma before iteration k+1; [n] = after the last
+        beta = (ctypes.c_float * n)(*self.beta[:n])
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.dualip_agd_set_schedule(self.handle, n, (ctypes.c_double * n)(*gammas[:n]), beta,
+                                                           (ctypes.c_uint8 * n)(*flags), factor), "dualip_agd_set_schedule")
+
+    def run(self, first: int, last: int) -> None:
+        """Iterations first..last (1-based, inclusive).  Whole chunks go out as CUDA-graph replays once the plan has stopped
+        re-cutting its ranges; everything else (the first launches of an objective, a last iteration that writes the primal,
+        the remainder, measurement with per-kernel events) is launched one by one through step()."""
+        i = first
+        while i <= last:
+            c = self.graph_chunk
+            end = i + c - 1
+            if (self.graphable and self.kernel_events is None and end <= last and self.steps_done == i - 1
+                    and not (self.solver.save_primal and end >= self.solver.max_iter)
+                    and (self._tune is None or self._tune.plan_settled())):
+                self._launch_graph(i)
+                i = end + 1
+            else:
+                self.step(i)
+                i += 1
+
+    def _launch_graph(self, i: int) -> None:
+        solver, f = self.solver, self.f
+        local = f.local_objective if self.sharded else f
+        with torch.cuda.device(self.device):
+            if not self._graph:
+                b_ptr = f.b_vec.data_ptr() if f.b_vec is not None else None
+                _native.check(self.lib.dualip_ascent_graph_create(
+                    ctypes.byref(self._graph), local._plan, self.handle, self.peer.handle if self.peer is not None else None,
+                    b_ptr, self.grad.data_ptr(), self.scal.data_ptr(), self.graph_chunk), "dualip_ascent_graph_create")
+            _native.check(self.lib.dualip_ascent_graph_launch(self._graph, torch.cuda.current_stream(self.device).cuda_stream),
+                          "dualip_ascent_graph_launch")
+        self.graph_launches += 1
+        end = i + self.graph_chunk - 1
+        g = self._gamma_sched[end]
+        if self.decay:
+            solver.gamma = g
+        f.gamma = g
+        if self.sharded:
+            f.local_objective.gamma = g
+        if self._tune is not None:
+            self._tune.launched_many(self.graph_chunk)
+        if self.peer is not None and self.peer.status_nowait():
+            self._peer_timed_out()
+        self.steps_done = end
 
     def step(self, i: int) -> None:
         solver, f = self.solver, self.f
@@ -483,6 +553,9 @@ class FusedAscentLoop:
                             dual_objective_log=dual_obj_log, step_size_log=step_size_log)
 
     def close(self) -> None:
+        if self._graph:
+            self.lib.dualip_ascent_graph_destroy(self._graph)
+            self._graph = ctypes.c_void_p()
         if self.handle:
             self.lib.dualip_agd_destroy(self.handle)
             self.handle = ctypes.c_void_p()

@@ -115,7 +115,8 @@ int dualip_plan_rebalance(dualip_plan* plan, void* stream);
  * [8] kernel launches per calc  [9] plan-owned device bytes [10] columns stored in slabs [11] nnz
  * [12] 1 if the gradient is accumulated in 32-bit fixed point (deterministic), 0 for fp32 atomics
  * [13] F: fixed-point fraction bits (value * 2^F)  [14] worst-row rounding-error estimate * 1e12
- * [15] longest column whose slab is staged through shared memory by the TMA engine (0: plain vector loads) */
+ * [15] longest column whose slab is staged through shared memory by the TMA engine (0: plain vector loads)
+ * [16] 1 if the rows are stored scaled by per-row powers of two (fixed-point resolution per row; results unchanged) */
 int dualip_plan_info(const dualip_plan* plan, int64_t* out, int cap);
 
 /* One evaluation of the dual at lambda on this shard, epilogue included (single device).
@@ -252,6 +253,29 @@ int dualip_matching_ascent_step(dualip_plan* plan, dualip_agd* agd, const float*
 int dualip_matching_ascent_step_peer(dualip_plan* plan, dualip_agd* agd, dualip_peer* peer, const float* b_dev, double gamma,
                                      float* grad_out_dev, dualip_scalars* scalars_out_dev, float beta, int32_t decay_now,
                                      double decay_factor, int32_t iter_index, void* stream);
+
+/* ---- scheduled launches and CUDA-graph replay (reference loop: optimizers/agd.py:150-206) ----
+ * dualip_matching_ascent_step takes gamma, beta, the decay flag and the log slot as arguments, so every iteration is a
+ * different launch.  With a device-resident schedule the kernel looks them up itself at the number of steps the state
+ * has taken (a device counter): the launch is then IDENTICAL for every iteration, and `chunk` launches captured once in a
+ * CUDA graph replay as one submission.  gamma_host[i] / beta_host[i]: values of iteration i (0-based) exactly as the
+ * host loop would pass them (gamma already decayed, agd.py:102-109; beta from agd.py:93-100); decay_now_host[i] != 0
+ * where max_step_size = step * decay_factor follows iteration i (may be NULL).  Synchronises the device. */
+int dualip_agd_set_schedule(dualip_agd* agd, int32_t n_iters, const double* gamma_host, const float* beta_host,
+                            const uint8_t* decay_now_host, double decay_factor);
+/* Steps enqueued on this state so far (host-side count; the schedule index of the next launch). */
+long long dualip_agd_steps_launched(const dualip_agd* agd);
+/* One scheduled iteration: dualip_matching_ascent_step (peer == NULL) or dualip_matching_ascent_step_peer. */
+int dualip_matching_ascent_step_scheduled(dualip_plan* plan, dualip_agd* agd, dualip_peer* peer, const float* b_dev,
+                                          float* grad_out_dev, dualip_scalars* scalars_out_dev, void* stream);
+/* `chunk` scheduled iterations as one CUDA graph (captured on a private stream; nothing is executed by create).  The
+ * pointers are baked into the graph: plan, state, window and buffers must outlive it, and a dualip_plan_rebalance after
+ * the capture invalidates it (build the graph once the plan has settled).  launch enqueues the whole chunk on `stream`. */
+typedef struct dualip_ascent_graph dualip_ascent_graph;
+int dualip_ascent_graph_create(dualip_ascent_graph** out, dualip_plan* plan, dualip_agd* agd, dualip_peer* peer,
+                               const float* b_dev, float* grad_out_dev, dualip_scalars* scalars_out_dev, int32_t chunk);
+int dualip_ascent_graph_launch(dualip_ascent_graph* graph, void* stream);
+void dualip_ascent_graph_destroy(dualip_ascent_graph* graph);
 
 /* ---- host-resident twin of the Maximizer state: for callers that keep the dual iterate in host memory and hand it to
  * dualip_matching_calc_host every iteration (the host-buffer path).  Same update as dualip_agd_step (agd.py:163-187,
