@@ -113,6 +113,16 @@ SIGNATURES = {
                                       C.c_void_p]),
     "dualip_scale_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "dualip_project_block": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(ProjClass), C.c_void_p]),
+    "dualip_csc_left_multiply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                                           C.c_void_p]),
+    "dualip_csc_row_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "dualip_csc_gather_block": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                          C.c_int32, C.c_void_p]),
+    "dualip_csc_scatter_block": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                           C.c_int32, C.c_void_p]),
+    "dualip_fair_calc": (C.c_int, [C.POINTER(CscDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dualip_fair_work_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "dualip_jacobi_precondition": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
                                              C.c_void_p, C.c_int32, C.c_void_p]),
 }

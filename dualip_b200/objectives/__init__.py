@@ -5,7 +5,9 @@ from .matching import (
     MatchingSolverDualObjectiveFunctionDistributed,
 )
 
+from .matching_fairness import MatchingFairnessDualObjectiveFunction, build_fairness_constraints
 from .miplib import MIPLIB2017ObjectiveFunction, MIPLIBInputArgs
 
 __all__ = ["BaseInputArgs", "BaseObjective", "MatchingInputArgs", "MatchingSolverDualObjectiveFunction",
-           "MatchingSolverDualObjectiveFunctionDistributed", "MIPLIBInputArgs", "MIPLIB2017ObjectiveFunction"]
+           "MatchingSolverDualObjectiveFunctionDistributed", "MIPLIBInputArgs", "MIPLIB2017ObjectiveFunction",
+           "MatchingFairnessDualObjectiveFunction", "build_fairness_constraints"]

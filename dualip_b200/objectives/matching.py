@@ -36,6 +36,16 @@ class MatchingInputArgs(BaseInputArgs):
     equality_mask: torch.Tensor = None
 
 
+def calc_grad(dual_grad: torch.Tensor, dual_obj: torch.Tensor, dual_val: torch.Tensor, b_vec: torch.Tensor,
+              reg_penalty: torch.Tensor) -> tuple:
+    """grad - b and c.x + reg + lambda.(grad - b) (reference matching.py:25-34).  The stock objectives do this in the fused
+    kernel's m-length tail; the function is public because the reference's extension recipe calls it
+    (docs/demo/matching_complex.rst:139)."""
+    dual_grad = dual_grad - b_vec
+    dual_obj = dual_obj + reg_penalty + torch.dot(dual_val, dual_grad)
+    return dual_grad, dual_obj
+
+
 def _indices_to_device(indices, device) -> torch.Tensor:
     if isinstance(indices, range):
         if indices.step == 1:

@@ -129,9 +129,10 @@ class AcceleratedGradientDescent:
             return f.device == initial_value.device
         if isinstance(f, MatchingSolverDualObjectiveFunction):
             return not f.is_distributed and f.device == initial_value.device
+        from dualip_b200.objectives.matching_fairness import MatchingFairnessDualObjectiveFunction
         from dualip_b200.objectives.miplib import MIPLIB2017ObjectiveFunction
 
-        return isinstance(f, MIPLIB2017ObjectiveFunction) and f.device == initial_value.device
+        return isinstance(f, (MIPLIB2017ObjectiveFunction, MatchingFairnessDualObjectiveFunction)) and f.device == initial_value.device
 
     # -- fused device-resident loop ------------------------------------------------------------------------
     def _maximize_fused(self, f, initial_value: torch.Tensor, rank: int) -> SolverResult:

@@ -312,6 +312,34 @@ int dualip_scale_rows(float* a_dev, const void* row_dev, int32_t index_bits, int
 int dualip_project_block(const float* x_dev, float* out_dev, int64_t L, int64_t K, const dualip_proj_class* cls,
                          void* stream);
 
+/* ---- stand-alone CSC operators: the reference's public extension recipe (docs/demo/matching_complex.rst:82-168) is
+ * written with them (src/dualip/utils/sparse_utils.py).  The stock objective does not call them (its chain is fused into
+ * one kernel); they exist so that user subclasses composed from these operators run on the device through this library.
+ * All asynchronous on `stream`; index_bits = width of the row / ccol entries (32 or 64). */
+/* left_multiply_sparse (sparse_utils.py:54-85): out[e] = vals[e] * v[row[e]]   (diag(v) @ M on the values) */
+int dualip_csc_left_multiply(const float* vals_dev, const void* row_dev, int32_t index_bits, int64_t nnz, const float* v_dev,
+                             float* out_dev, int32_t device, void* stream);
+/* row_sums_csc (sparse_utils.py:223-243): out[r] = sum of the values stored in row r; out (m floats) is overwritten */
+int dualip_csc_row_sums(const float* vals_dev, const void* row_dev, int32_t index_bits, int64_t nnz, int32_t m,
+                        float* out_dev, int32_t device, void* stream);
+/* The two halves of apply_F_to_columns (sparse_utils.py:133-220): the zero-padded row-major [L x K] block of columns
+ * cols[0..K) (NULL: columns 0..K-1), block[i][k] = i-th stored value of column cols[k] or 0, and the write-back of a
+ * projected block into a values array (positions of other columns are left untouched). */
+int dualip_csc_gather_block(const void* ccol_dev, int32_t index_bits, const float* vals_dev, const int64_t* cols_dev, int64_t K,
+                            int64_t L, float* block_dev, int32_t device, void* stream);
+int dualip_csc_scatter_block(const void* ccol_dev, int32_t index_bits, const float* block_dev, const int64_t* cols_dev, int64_t K,
+                             int64_t L, float* vals_out_dev, int32_t device, void* stream);
+
+/* ---- the demo's fairness-row objective (docs/demo/matching_complex.rst:82-168) as one kernel ----
+ * A matching LP whose constraint matrix carries two extra dense rows +-A_fairness (same sparsity pattern as A, values
+ * f_dev); lambda, b and grad have n_rows + 2 entries.  desc: the caller's CSC arrays (borrowed, not copied; pad_len /
+ * classes / col_class as for dualip_plan_create).  x_out_dev: nnz floats (always written: it is the kernel's scratch).
+ * work_dev: dualip_fair_work_bytes(n_rows, n_classes) bytes of device memory, zeroed once by the caller. */
+int dualip_fair_calc(const dualip_csc_desc* desc, const float* f_dev, const float* lambda_dev, const float* b_dev,
+                     double gamma, float* grad_out_dev, dualip_scalars* scalars_out_dev, float* x_out_dev, float* work_dev,
+                     void* stream);
+int64_t dualip_fair_work_bytes(int32_t n_rows, int32_t n_classes);
+
 #ifdef __cplusplus
 }
 #endif
