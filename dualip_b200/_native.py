@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("DUALIP_B200_LIB") or os.path.join(_HERE, "_lib", "lib
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 OK, EINVAL, ECUDA, ENOMEM, ERANGE = 0, -1, -2, -3, -4
-PROJ_CLAMP, PROJ_SIMPLEX, PROJ_SIMPLEX_EQ = 0, 1, 2
+PROJ_CLAMP, PROJ_SIMPLEX, PROJ_SIMPLEX_EQ, PROJ_SIMPLEX_BISECT, PROJ_SIMPLEX_EQ_BISECT = 0, 1, 2, 3, 4
+MAX_BISECT_COLUMN = 1024  # longest column the fused kernel projects with a bisection class
 PROJ_FLAG_D1_UNPADDED = 1
 PEER_HANDLE_BYTES, PEER_MAX_WORLD = 64, 16
 

@@ -681,7 +681,8 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       const Seg S = s_seg[idx];
       p_sl = S.a + warp;
       p_end = S.b;
-      p_bytes = (S.d > kRegDeg) ? 0xffffffffu : (uint32_t)S.d * RB;  // generic path: never staged
+      // generic path (long columns, bisection classes): never staged
+      p_bytes = (S.d > kRegDeg || s_cls[S.cls].kind >= DUALIP_PROJ_SIMPLEX_BISECT) ? 0xffffffffu : (uint32_t)S.d * RB;
       p_off = S.off32_a + (uint32_t)warp * S.d;
       p_stride = (uint32_t)NW * S.d;
     };
@@ -716,7 +717,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       uint32_t boff = S.off32_a + (uint32_t)warp * S.d;  // in rows of 32 entries
       const uint32_t stride = (uint32_t)NW * S.d;
       const dualip_proj_class pc = s_cls[cls];
-      if (FAST && d <= kRegDeg) {
+      if (FAST && d <= kRegDeg && pc.kind <= DUALIP_PROJ_SIMPLEX_EQ) {
         // ---- register path: the whole column lives in registers, code specialised on d ----
         const unsigned char* s_lam_b = reinterpret_cast<const unsigned char*>(s_lam);
         StageCtx st{use_stage, region, my_stage, my_bars};
@@ -823,6 +824,79 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
         kk += 2;
       }
       if (d & 1) batch(std::integral_constant<int, 1>{}, kk);
+    } else if (pc.kind >= DUALIP_PROJ_SIMPLEX_BISECT) {
+      // ---- method="bisection_search" (simplex.py:6-123) on the zero-padded column of the reference's block: no pre-clamp;
+      //      every sum runs down the block's rows in fp32 (torch's outer-dimension reduction), the padding after the entries ----
+      const float z = pc.z;
+      const int n0 = pad_len_of(k, cls, d) - d;  // zero rows below this column in its bucket's block
+      auto vq = [&](int kq) -> float {
+        float a, c;
+        uint32_t r;
+        ld1(kq, a, c, r);
+        return make_v(a, lam_scaled<SMODE>(k, s, s_lam, r), s, c);
+      };
+      float ssum = 0.f, vmin = INFINITY, t0 = -INFINITY, t1 = -INFINITY;  // column sum, smallest entry, two largest of x/z
+      int am = -1;
+      for (int kq = 0; kq < d; ++kq) {
+        const float v = vq(kq);
+        ssum = __fadd_rn(ssum, v);
+        vmin = fminf(vmin, v);
+        const float xn = __fdiv_rn(v, z);
+        if (xn > t0) {
+          t1 = t0, t0 = xn, am = kq;
+        } else if (xn > t1) {
+          t1 = xn;
+        }
+      }
+      if (n0 > 0) {  // the padding's zeros take part in the top-2 (a stable sort puts an entry before an equal padding zero)
+        if (0.f > t0) {
+          t1 = (n0 > 1) ? 0.f : t0, t0 = 0.f, am = -1;
+        } else if (0.f > t1) {
+          t1 = 0.f;
+        }
+      }
+      const bool feas = (pc.kind == DUALIP_PROJ_SIMPLEX_BISECT) && (ssum <= pc.z_thr) && (vmin >= -1e-6f);  // :40 (padding: 0 >= -tol)
+      const bool shortc = !feas && (d + n0 > 1) && (__fsub_rn(t0, t1) > 1.0f);                                                 // :52-67
+      float nu = 0.f;
+      if (feas) {
+        branch = 4;  // x = v, unclamped (:41)
+      } else if (shortc) {
+        branch = 1, rho = 1, i1 = am;  // one-hot at the maximum (:69-75); am < 0: it fell on a padding row
+      } else {
+        branch = 3;
+        theta = t0;  // max(x/z): the shift (:86-89)
+        float lo = -1.f, hi = 0.f, prev = 0.f;
+        bool act = true;
+        for (int it = 0; it < 50 && act; ++it) {  // :95-118; every column of a block halves the same interval
+          const float mid = __fmul_rn(__fadd_rn(lo, hi), 0.5f);
+          if (it > 0 && fabsf(__fsub_rn(mid, prev)) < 1e-6f) break;
+          float sm = 0.f;
+          for (int kq = 0; kq < d; ++kq) sm = __fadd_rn(sm, fmaxf(__fsub_rn(__fsub_rn(vq(kq), t0), mid), 0.f));
+          const float tp = fmaxf(__fsub_rn(__fsub_rn(0.f, t0), mid), 0.f);
+          for (int q0 = 0; q0 < n0; ++q0) sm = __fadd_rn(sm, tp);
+          const bool high = sm > 1.0f;
+          lo = high ? mid : lo;
+          hi = high ? hi : mid;
+          act = !(__fsub_rn(hi, lo) < 1e-6f);
+          prev = mid;
+        }
+        nu = __fmul_rn(__fadd_rn(lo, hi), 0.5f);
+      }
+      if (active) {
+        for (int kq = 0; kq < d; ++kq) {
+          float a, c;
+          uint32_t r;
+          ld1(kq, a, c, r);
+          const float v = make_v(a, lam_scaled<SMODE>(k, s, s_lam, r), s, c);
+          const float x = branch == 4 ? v : (branch == 1 ? (kq == i1 ? z : 0.f) : __fmul_rn(fmaxf(__fsub_rn(__fsub_rn(v, theta), nu), 0.f), z));
+          const float g = __fmul_rn(a, x);
+          if (g != 0.f) grad_add<SMODE, ACC>(k, s_grad, r, g);
+          cxs = fmaf(c, x, cxs);
+          xxs = fmaf(x, x, xxs);
+          if (OUT && k.x_out) k.x_out[k.orig_start[(int64_t)sl * kSlabW + lane] + kq] = x;
+        }
+      }
+      branch = -2;  // the output pass below is done
     } else {
       // ---- simplex (simplex.py:143-236 per column at its true length) ----
       // Pass 1 streams the column once: column sum, the two largest entries with their positions, the third largest
@@ -1086,7 +1160,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     cx += (double)cxs;
     xx += (double)xxs;
 
-    if (OUT && active) {
+    if (OUT && active && branch != -2) {
       // ---- primal / diagnostics output (save_primal on the last iteration, tests): plain re-stream ----
       const int64_t os = k.orig_start[(int64_t)sl * kSlabW + lane];
       if (k.x_out) {
@@ -1752,6 +1826,11 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
       c.off = tot;
       tot += c.len;
       p->class_used[c.cls & 0xff] = true;
+      if (p->classes_host[c.cls & 0xff].kind >= DUALIP_PROJ_SIMPLEX_BISECT) {
+        set_error("bisection-search classes are limited to columns of at most %d entries (a column has %d)", kMaxThreadDeg, c.len);
+        cleanup();
+        return DUALIP_ERANGE;
+      }
     }
     BS_TRY(cudaMemcpyAsync(p->longcols, lc.data(), sizeof(LongCol) * n_long, cudaMemcpyHostToDevice, stream));
     p->long_total = tot;
@@ -1787,6 +1866,7 @@ static double slab_cost(const dualip_plan* p, const SlabGroup& g) {
   const bool fast = p->row_bits == 16 && p->smode == 0;
   const bool simplex = p->classes_host[g.cls].kind != DUALIP_PROJ_CLAMP;
   const double d = (double)g.d;
+  if (p->classes_host[g.cls].kind >= DUALIP_PROJ_SIMPLEX_BISECT) return 30.0 * d;  // ~20 passes over the column (generic path)
   if (!fast || g.d > kRegDeg) return simplex ? 6.7 * d : 2.7 * d;
   if (simplex) return g.d <= 14 ? 4.0 + d : (g.d <= 16 ? 1.27 * d : 1.61 * d);
   return g.d <= 14 ? 2.8 + 0.56 * d : 0.76 * d;
@@ -1881,6 +1961,7 @@ static int choose_accumulator(dualip_plan* p, cudaStream_t stream, int keep_bits
   for (int i = 0; i < p->n_classes; ++i) {
     const dualip_proj_class& pc = p->classes_host[i];
     xmax[i] = (pc.kind == DUALIP_PROJ_CLAMP) ? fmaxf(fabsf(pc.lo), fabsf(pc.hi)) : pc.z;
+    if (pc.kind >= DUALIP_PROJ_SIMPLEX_BISECT) xmax[i] = INFINITY;  // (v - max(v/z) + 1) * z: no bound for z != 1
     if (!p->class_used[i]) xmax[i] = 0.f;
     if (!(xmax[i] < INFINITY)) return DUALIP_OK;  // open cone / identity: no bound
   }
@@ -2108,7 +2189,7 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   }
   for (int i = 0; i < d->n_classes; ++i) {
     const dualip_proj_class& pc = d->classes[i];
-    if (pc.kind < DUALIP_PROJ_CLAMP || pc.kind > DUALIP_PROJ_SIMPLEX_EQ) {
+    if (pc.kind < DUALIP_PROJ_CLAMP || pc.kind > DUALIP_PROJ_SIMPLEX_EQ_BISECT) {
       set_error("class %d: unknown projection kind %d", i, pc.kind);
       return DUALIP_EINVAL;
     }
@@ -2234,7 +2315,7 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   DUALIP_TRY_FAIL(cudaMemcpy(p->classes_dev, p->classes_host, sizeof(dualip_proj_class) * p->n_classes, cudaMemcpyHostToDevice));
   if (d->pad_len != nullptr) {
     bool any_eq = false;
-    for (int i = 0; i < p->n_classes; ++i) any_eq = any_eq || p->classes_host[i].kind == DUALIP_PROJ_SIMPLEX_EQ;
+    for (int i = 0; i < p->n_classes; ++i) any_eq = any_eq || p->classes_host[i].kind >= DUALIP_PROJ_SIMPLEX_EQ;
     if (any_eq) {
       const size_t bytes = sizeof(int) * (size_t)p->n_classes * DUALIP_PAD_BUCKETS;
       DUALIP_TRY_FAIL(cudaMalloc(&p->pad_dev, bytes));

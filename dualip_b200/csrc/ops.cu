@@ -340,6 +340,11 @@ int dualip_fair_calc(const dualip_csc_desc* d, const float* f_dev, const float* 
     set_error("gamma must be non-zero");
     return DUALIP_EINVAL;
   }
+  for (int i = 0; i < d->n_classes; ++i)
+    if (d->classes[i].kind < DUALIP_PROJ_CLAMP || d->classes[i].kind > DUALIP_PROJ_SIMPLEX_EQ) {
+      set_error("class %d: the fairness objective projects with box / cone / simplex / simplex_eq (Duchi) only", i);
+      return DUALIP_EINVAL;
+    }
   DeviceGuard g(d->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int m = d->n_rows;

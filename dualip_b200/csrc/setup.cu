@@ -139,6 +139,48 @@ __global__ void project_block_kernel(const float* __restrict__ x, float* __restr
     for (long long i = 0; i < L; ++i) out[i * K + j] = fminf(fmaxf(x[i * K + j], pc.lo), pc.hi);
     return;
   }
+  if (pc.kind >= DUALIP_PROJ_SIMPLEX_BISECT) {
+    // method="bisection_search" (simplex.py:6-123): no pre-clamp; sums run down the rows in fp32 like torch's outer-dimension
+    // reduction; every column of a block halves the same interval [-1, 0] (19 halvings until 2^-20 < tol)
+    float ssum = 0.f, vmin = INFINITY, t0 = -INFINITY, t1 = -INFINITY;
+    long long am = 0;
+    for (long long i = 0; i < L; ++i) {
+      const float v = x[i * K + j];
+      ssum = __fadd_rn(ssum, v);
+      vmin = fminf(vmin, v);
+      const float xn = __fdiv_rn(v, pc.z);
+      if (xn > t0) {
+        t1 = t0, t0 = xn, am = i;
+      } else if (xn > t1) {
+        t1 = xn;
+      }
+    }
+    if (pc.kind == DUALIP_PROJ_SIMPLEX_BISECT && ssum <= pc.z_thr && vmin >= -1e-6f) {  // :40-41
+      for (long long i = 0; i < L; ++i) out[i * K + j] = x[i * K + j];
+      return;
+    }
+    if (L > 1 && __fsub_rn(t0, t1) > 1.0f) {  // :52-75
+      for (long long i = 0; i < L; ++i) out[i * K + j] = (i == am) ? pc.z : 0.f;
+      return;
+    }
+    float lo = -1.f, hi = 0.f, prev = 0.f;
+    bool act = true;
+    for (int it = 0; it < 50 && act; ++it) {  // :95-118
+      const float mid = __fmul_rn(__fadd_rn(lo, hi), 0.5f);
+      if (it > 0 && fabsf(__fsub_rn(mid, prev)) < 1e-6f) break;
+      float sm = 0.f;
+      for (long long i = 0; i < L; ++i) sm = __fadd_rn(sm, fmaxf(__fsub_rn(__fsub_rn(x[i * K + j], t0), mid), 0.f));
+      const bool high = sm > 1.0f;
+      lo = high ? mid : lo;
+      hi = high ? hi : mid;
+      act = !(__fsub_rn(hi, lo) < 1e-6f);
+      prev = mid;
+    }
+    const float nu = __fmul_rn(__fadd_rn(lo, hi), 0.5f);
+    for (long long i = 0; i < L; ++i)
+      out[i * K + j] = __fmul_rn(fmaxf(__fsub_rn(__fsub_rn(x[i * K + j], t0), nu), 0.f), pc.z);  // :120-122
+    return;
+  }
   float S = 0.f, m1 = -1.f, m2 = -1.f;
   long long am = 0;
   for (long long i = 0; i < L; ++i) {

@@ -124,6 +124,14 @@ def _build_class_table(ccol: torch.Tensor, n_cols: int, projection_map, batching
         op = project(entry.proj_type, **entry.proj_params)  # raises ValueError for unknown names, like the reference
         cls = op.native_class() if hasattr(op, "native_class") else None
         idx = None if single_full else _indices_to_device(entry.indices, device)
+        if cls is not None and cls.kind >= _native.PROJ_SIMPLEX_BISECT:
+            # the fused kernel's bisection handles columns of up to 1024 entries; an entry with a longer column keeps the
+            # padded-block route (same operator, dualip_project_block)
+            if lengths is None:
+                lengths = ccol[1:] - ccol[:-1]
+            sel = lengths if idx is None else lengths[idx]
+            if sel.numel() and int(sel.max()) > _native.MAX_BISECT_COLUMN:
+                cls = None
         if cls is None:
             # not implemented by the fused kernel: its columns produce x = 0 there (clamp to [0, 0]) and are projected
             # through padded blocks by the objective (_BlockEntry)
@@ -165,13 +173,16 @@ def _build_pad_table(ccol: torch.Tensor, n_cols: int, projection_map, batching: 
     falls in (matching.py:87-114: buckets (0,2], (2,4], (4,8], ..., (2^k, m]; batching=False: one bucket per entry;
     utils/sparse_utils.py:197,207).  Returns a ctypes int32 array n_classes x 32 indexed by ceil(log2(d)), or None."""
     entries = list(projection_map.items())
-    if not any(e.proj_type == "simplex_eq" and e.proj_params.get("method", "duchi") == "duchi" for _, e in entries):
+    def needs_pad(e):  # simplex_eq (Duchi: SURVEY App. A #4) and both bisection variants (the padding is part of their block)
+        return e.proj_type in ("simplex", "simplex_eq") and (e.proj_type == "simplex_eq" or e.proj_params.get("method") == "bisection_search")
+
+    if not any(needs_pad(e) for _, e in entries):
         return None
     table = np.zeros((n_classes, _native.PAD_BUCKETS), dtype=np.int32)
     lengths = ccol[1:] - ccol[:-1]
     first = n_classes - len(entries)  # class 0 is the identity class when the map does not cover every column
     for i, (_, entry) in enumerate(entries):
-        if entry.proj_type != "simplex_eq":
+        if not needs_pad(entry):
             continue
         ind = entry.indices
         full = isinstance(ind, range) and ind.start == 0 and ind.step == 1 and ind.stop == n_cols

@@ -37,6 +37,11 @@ extern "C" {
 #define DUALIP_PROJ_CLAMP 0       /* box(lower,upper), cone(lower) / cone(upper) / cone(): x = min(max(v,lo),hi); +-inf = open */
 #define DUALIP_PROJ_SIMPLEX 1     /* "simplex":    {x>=0, sum x <= z}, batched Duchi with pre-clamp (simplex.py:126-236, :248-255) */
 #define DUALIP_PROJ_SIMPLEX_EQ 2  /* "simplex_eq": {x>=0, sum x  = z}, same routine without the feasibility branch (:267-274)      */
+#define DUALIP_PROJ_SIMPLEX_BISECT 3     /* "simplex",    method="bisection_search" (simplex.py:6-123, inequality=True): no pre-clamp,
+                                            feasible needs every entry >= -1e-6, top-2 shortcut, 19 halvings of [-1, 0]       */
+#define DUALIP_PROJ_SIMPLEX_EQ_BISECT 4  /* "simplex_eq", method="bisection_search" (inequality=False)                          */
+/* Both bisection kinds depend on the padded length L of the reference's block (pad_len below): the zero padding takes part in
+ * the maximum, the top-2 test and the sums.  They run in the fused kernel for columns of up to 1024 entries. */
 
 /* flags of a projection class */
 #define DUALIP_PROJ_FLAG_D1_UNPADDED 1u /* 1-nnz columns of this class sit in a bucket whose padded length L is 1, so the
@@ -72,9 +77,10 @@ typedef struct dualip_csc_desc {
   const int32_t* pad_len;  /* host array n_classes x DUALIP_PAD_BUCKETS, or NULL: the padded length L of the reference's
                               [L x K] block that a column of class k with d entries is projected in
                               (utils/sparse_utils.py:197,207), at pad_len[k*DUALIP_PAD_BUCKETS + ceil(log2(d))]; 0 = d.
-                              Only "simplex_eq" depends on it (simplex.py:160-161): a column whose
-                              clamped sum is below z gets (z - sum)/L added to every entry.  The reference derives L from
-                              its length buckets (objectives/matching.py:87-114). */
+                              "simplex_eq" depends on it (simplex.py:160-161): a column whose
+                              clamped sum is below z gets (z - sum)/L added to every entry; so do both bisection kinds
+                              (the padding is part of the block they search on).  The reference derives L from its length
+                              buckets (objectives/matching.py:87-114). */
 } dualip_csc_desc;
 #define DUALIP_PAD_BUCKETS 32
 
