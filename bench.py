@@ -28,6 +28,8 @@ WORKLOADS = {
     # name: (entities, duals, sparsity, mixed projection map?, jacobi?)
     "c3": (100_000_000, 10_000, 1e-3, True, True),
     "c2": (1_000_000, 1_000, 1e-2, False, False),
+    "c1": (138_493, 26_744, None, False, False),  # MovieLens-shaped (benchmark/extra_workloads.py)
+    "c5": (150, 7_822, None, False, False),       # MIPLIB-2017 example LP (benchmark/extra_workloads.py)
     "c3_small": (10_000_000, 10_000, 1e-3, True, True),
     "tiny": (200_000, 1_000, 1e-2, True, True),
 }
@@ -593,6 +595,16 @@ def main():
     args.sparsity = args.sparsity or sp
     args.mixed, args.jacobi = mixed, jac
     args.warmup = max(args.warmup, 3)
+    if args.workload in ("c1", "c5"):
+        # single-GPU side configurations (BASELINE.json configs[0] and configs[4]); their line carries the reference's CPU run
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.impl == "reference":
+            raise SystemExit("--workload c1 / c5 run on one GPU with the native arm (cpu_baseline holds the reference's CPU run)")
+        import sys as _sys
+
+        from benchmark import extra_workloads as X
+
+        (X.run_c1 if args.workload == "c1" else X.run_c5)(args, _sys.modules[__name__])
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -110,3 +110,53 @@ def capacity_vector(total_greedy_load: torch.Tensor, num_destinations: int, targ
     """b_j = rho_j * (load_j + 1e-8) with rho ~ U(0.5, 1) (generate_synthetic_data.py:159-162)."""
     dp = destination_params(num_destinations, target_sparsity, seed, device)
     return (dp["rho"] * (total_greedy_load.to(device) + 1e-8)).float()
+
+
+def generate_movielens_shaped(n_users: int, n_movies: int, seed: int, device, mean_log_deg: float = 4.3, sigma_log_deg: float = 1.0):
+    """configs[0]-shaped data (reference examples/movielens_matching/movies_lens_matching.py:49-116): one column per user,
+    one row per movie, a == 1, c = -rating in {0.5, ..., 5}; column lengths heavy-tailed like ml-20m's (at least 20 ratings
+    per user, mean ~140, a few users with thousands), movie popularity log-normal.  ml-20m itself is not available
+    offline, so the ratings are drawn.  Returns (SyntheticShard, b) with one budget per movie: half the number of users whose
+    best-rated movie it is, plus a little (so that popular rows bind)."""
+    device = torch.device(device)
+    gen = torch.Generator(device=device).manual_seed(seed)
+    deg = torch.exp(mean_log_deg + sigma_log_deg * torch.randn(n_users, device=device, generator=gen)).to(torch.int64)
+    deg.clamp_(min=20, max=min(n_movies, 9254))  # ml-20m: 20 .. 9254 ratings per user
+    pop = torch.exp(1.2 * torch.randn(n_movies, device=device, generator=gen, dtype=torch.float64))
+    cdf = torch.cumsum(pop / pop.sum(), 0)
+    cdf[-1] = 1.0
+    draws = (deg.double() * 1.15).to(torch.int64) + 4  # oversample: duplicates within a column are dropped
+    total = int(draws.sum().item())
+    col = torch.repeat_interleave(torch.arange(n_users, device=device), draws, output_size=total)
+    dest = torch.searchsorted(cdf, torch.rand(total, device=device, dtype=torch.float64, generator=gen)).clamp_(max=n_movies - 1)
+    key, _ = torch.sort(col * n_movies + dest)
+    keep = torch.ones(total, dtype=torch.bool, device=device)
+    keep[1:] = key[1:] != key[:-1]
+    key = key[keep]
+    col = torch.div(key, n_movies, rounding_mode="floor")
+    row = key - col * n_movies
+    # trim every column to its target length (entries are sorted by row within a column: drop a random subset instead of a tail)
+    r = torch.rand(key.numel(), device=device, generator=gen)
+    have = torch.bincount(col, minlength=n_users)
+    frac = (deg.double() / have.clamp(min=1).double()).clamp(max=1.0).float()
+    sel = r <= frac[col]
+    col, row = col[sel], row[sel]
+    lens = torch.bincount(col, minlength=n_users)
+    ccol = torch.zeros(n_users + 1, dtype=torch.int64, device=device)
+    torch.cumsum(lens, 0, out=ccol[1:])
+    E = int(row.numel())
+    probs = torch.tensor([.01, .03, .02, .07, .05, .2, .12, .28, .08, .14], device=device)
+    rating = 0.5 * (1 + torch.multinomial(probs, E, replacement=True, generator=gen).float())
+    c = -rating
+    a = torch.ones(E, dtype=torch.float32, device=device)
+    cmin = torch.full((n_users,), float("inf"), device=device).scatter_reduce_(0, col, c, reduce="amin", include_self=True)
+    best = c == cmin[col]
+    first_best = torch.ones(E, dtype=torch.bool, device=device)
+    pos = torch.arange(E, device=device)
+    first_pos = torch.full((n_users,), E, dtype=torch.int64, device=device).scatter_reduce_(0, col[best], pos[best], reduce="amin",
+                                                                                            include_self=True)
+    first_best = pos == first_pos[col]
+    load = torch.zeros(n_movies, dtype=torch.float64, device=device)
+    load.index_add_(0, row[first_best], torch.ones(int(first_best.sum().item()), dtype=torch.float64, device=device))
+    b = (0.5 * load + 0.05).float()
+    return SyntheticShard(ccol, row, a, c, load, n_movies, 0, n_users), b

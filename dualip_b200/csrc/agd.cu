@@ -292,12 +292,15 @@ int dualip_peer_create(dualip_peer** out, int32_t m, int32_t rank, int32_t world
   p->m = m;
   p->rank = rank;
   p->world = world;
+  if (const char* env = getenv("DUALIP_PEER_PUSH")) p->push = atoi(env) != 0 ? 1 : 0;
   if (const char* env = getenv("DUALIP_PEER_TIMEOUT_MS")) {
     const long long ms = atoll(env);
     if (ms > 0) p->timeout_ns = (unsigned long long)ms * 1000000ull;
   }
   p->slot_bytes = (sizeof(float) * (size_t)(m + 2) + 127) & ~(size_t)127;
-  p->window_bytes = kPeerFlagBytes + 2 * p->slot_bytes;
+  // [arrival flags | two pull slots (this rank's sums, read by the peers) | 2 x world push slots (every rank's sums, written
+  //  by that rank: the one-launch path, see peer_push_exchange_cta)]
+  p->window_bytes = kPeerFlagBytes + 2 * p->slot_bytes + 2 * (size_t)world * p->slot_bytes;
   cudaError_t e = cudaMalloc(&p->window, p->window_bytes);
   if (e == cudaSuccess) e = cudaMemset(p->window, 0, p->window_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&p->sum, sizeof(float) * (m + 8));

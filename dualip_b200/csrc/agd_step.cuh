@@ -251,6 +251,7 @@ struct PeerArgs {
   float* sum;   // local m+2 floats (padded to a multiple of 4): the reduced packed sums
   int* status;       // local device word: set to 1 when a wait timed out (checked before every wait)
   int* status_host;  // the same flag in mapped host memory, written on a time-out only: the host polls it without a sync
+  int push;          // one-launch path: 1 = sums are pushed into every peer's window (stores), 0 = peers pull them (loads)
 };
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
@@ -333,6 +334,58 @@ __device__ __forceinline__ void peer_exchange_cta(const PeerArgs& P, int m2, uns
   __syncthreads();  // P.sum is read by other threads of this CTA
 }
 
+// Push variant used by the slab kernel's fused tail.  The CTA has ALREADY written this rank's packed sums into slot
+// [parity][rank] of EVERY rank's window (posted stores over NVLink: no read round trip, peer_push_slot() gives the address);
+// here it tells the peers so, waits for theirs, and adds the W slots of its OWN window -- local memory -- in rank order.
+// One NVLink one-way latency per step instead of ceil(m / (4 threads)) dependent remote-read rounds.
+__device__ __forceinline__ float* peer_push_slot(const PeerArgs& P, int target, int writer, unsigned long long seq) {
+  return reinterpret_cast<float*>(P.win[target] + kPeerFlagBytes + 2 * P.slot_bytes +
+                                  ((size_t)(seq & 1ull) * (size_t)P.world + (size_t)writer) * P.slot_bytes);
+}
+__device__ __forceinline__ void peer_push_exchange_cta(const PeerArgs& P, int m2, unsigned long long seq) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __threadfence_system();  // this CTA's stores into the peers' windows are performed before the flags
+  __syncthreads();
+  if (tid < P.world) {
+    st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.win[tid]) + P.rank, seq);
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(P.win[P.rank]) + tid;
+    const unsigned long long t0 = global_timer_ns();
+    while (*reinterpret_cast<volatile int*>(P.status) == 0 && ld_relaxed_sys_u64(mine) < seq) {
+      if (global_timer_ns() - t0 > P.timeout_ns) {
+        *reinterpret_cast<volatile int*>(P.status) = 1;
+        *reinterpret_cast<volatile int*>(P.status_host) = 1;
+        break;
+      }
+    }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");  // the slots the peers wrote are read after their flags
+  }
+  __syncthreads();
+  for (int i4 = tid * 4; i4 < m2; i4 += nt * 4) {  // slots are padded to 128 bytes: a float4 never leaves the slot
+    float4 v[DUALIP_PEER_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < DUALIP_PEER_MAX_WORLD; ++r)
+      if (r < P.world) v[r] = ld_relaxed_sys_f4(peer_push_slot(P, P.rank, r, seq) + i4);
+    float4 acc = v[0];
+#pragma unroll
+    for (int r = 1; r < DUALIP_PEER_MAX_WORLD; ++r) {
+      if (r < P.world) {
+        acc.x = __fadd_rn(acc.x, v[r].x);
+        acc.y = __fadd_rn(acc.y, v[r].y);
+        acc.z = __fadd_rn(acc.z, v[r].z);
+        acc.w = __fadd_rn(acc.w, v[r].w);
+      }
+    }
+    if (i4 + 3 < m2) {
+      *reinterpret_cast<float4*>(P.sum + i4) = acc;
+    } else {
+      P.sum[i4] = acc.x;
+      if (i4 + 1 < m2) P.sum[i4 + 1] = acc.y;
+      if (i4 + 2 < m2) P.sum[i4 + 2] = acc.z;
+    }
+  }
+  __syncthreads();  // P.sum is read by other threads of this CTA
+}
+
 }  // namespace dualip
 
 // ---- host-side state behind the opaque C handles (shared by agd.cu and calc.cu) ----
@@ -374,6 +427,7 @@ struct dualip_peer {
   unsigned int* ticket = nullptr;  // ticket of the multi-CTA step kernel
   unsigned long long seq = 0;  // steps taken
   unsigned long long timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;  // DUALIP_PEER_TIMEOUT_MS overrides
+  int push = 1;  // DUALIP_PEER_PUSH=0: the one-launch path pulls like dualip_agd_step_peer
 };
 
 static inline dualip::AgdStepArgs step_args(dualip_agd* a, const float* grad, const dualip_scalars* scal, float beta, int decay_now,
@@ -422,5 +476,6 @@ static inline dualip::PeerArgs peer_args(dualip_peer* p, bool advance) {
   P.status = p->status;
   P.status_host = p->status_host_dev;
   P.ticket = p->ticket;
+  P.push = p->push;
   return P;
 }

@@ -1303,6 +1303,10 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     float* partial_out = k.partial_out;
     if (k.fuse == 2 && scheduled)
       partial_out = reinterpret_cast<float*>(k.peer.win[k.peer.rank] + kPeerFlagBytes + (size_t)(seq & 1ull) * k.peer.slot_bytes);
+    const bool push = k.fuse == 2 && k.peer.push != 0;
+    float* pslot[DUALIP_PEER_MAX_WORLD];  // push: this rank's slot in every rank's window
+#pragma unroll
+    for (int r = 0; r < DUALIP_PEER_MAX_WORLD; ++r) pslot[r] = (push && r < k.peer.world) ? peer_push_slot(k.peer, r, k.peer.rank, seq) : nullptr;
     for (int base = tid; base < m; base += 4 * THREADS) {
       float raw[4];
 #pragma unroll
@@ -1311,15 +1315,30 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       for (int u = 0; u < 4; ++u)
         if (base + u * THREADS < m) {
           sum_clear(base + u * THREADS);
-          partial_out[base + u * THREADS] = raw[u];
+          if (push) {
+#pragma unroll
+            for (int r = 0; r < DUALIP_PEER_MAX_WORLD; ++r)
+              if (r < k.peer.world) pslot[r][base + u * THREADS] = raw[u];  // posted stores over NVLink (own window: local)
+          } else {
+            partial_out[base + u * THREADS] = raw[u];
+          }
         }
     }
     if (tid == 0) {
-      partial_out[m] = (float)cxv;
-      partial_out[m + 1] = (float)xxv;
+      if (push) {
+#pragma unroll
+        for (int r = 0; r < DUALIP_PEER_MAX_WORLD; ++r)
+          if (r < k.peer.world) pslot[r][m] = (float)cxv, pslot[r][m + 1] = (float)xxv;
+      } else {
+        partial_out[m] = (float)cxv;
+        partial_out[m + 1] = (float)xxv;
+      }
     }
     if (k.fuse == 2) {
-      peer_exchange_cta(k.peer, m + 2, seq);
+      if (push)
+        peer_push_exchange_cta(k.peer, m + 2, seq);
+      else
+        peer_exchange_cta(k.peer, m + 2, seq);
       agd_step_body<true>(k.agd, scheduled ? step_dyn_sched(k.agd, k.sched, sched_it) : step_dyn_of(k.agd));
     }
   }
