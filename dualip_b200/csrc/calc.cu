@@ -135,8 +135,11 @@ struct dualip_plan {
   int64_t rows32 = 0;             // total slab rows (32 elements each)
   int64_t n_short = 0;            // columns stored in slabs
   // long columns (owned, compact copies)
-  LongCol* longcols = nullptr;
+  LongCol* longcols = nullptr;    // sorted by length: [0, n_mid) mid columns (<= kMaxThreadDeg entries, warp per column inside the
+                                  // slab kernel), [n_mid, n_long) long columns (matching_long_kernel)
   int64_t n_long = 0;
+  int64_t n_mid = 0;
+  int* mid_range = nullptr;       // n_ctas + 1: every CTA's contiguous share of the mid columns (equal cost)
   int64_t long_total = 0;         // entries of all long columns
   float* long_a = nullptr;
   float* long_c = nullptr;
@@ -177,10 +180,29 @@ namespace dualip {
 // ------------------------------------------------------------------------------------------
 // Plan construction (setup time)
 // ------------------------------------------------------------------------------------------
+// Histogram of the column lengths 0..kMaxThreadDeg (longer ones in the last bin): the plan chooses from it where the slab layout ends.
+template <typename IdxT>
+__global__ void length_hist_kernel(const IdxT* __restrict__ ccol, int64_t n_cols, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int s_h[kMaxThreadDeg + 2];
+  for (int i = threadIdx.x; i < kMaxThreadDeg + 2; i += blockDim.x) s_h[i] = 0u;
+  __syncthreads();
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; j < n_cols; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t d = (int64_t)ccol[j + 1] - (int64_t)ccol[j];
+    atomicAdd(&s_h[d < 0 ? 0 : (d > kMaxThreadDeg ? kMaxThreadDeg + 1 : (int)d)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMaxThreadDeg + 2; i += blockDim.x)
+    if (s_h[i]) atomicAdd(&hist[i], s_h[i]);
+}
+
+// slab_max_deg: columns longer than this leave the slab layout for the compact column-contiguous arrays (warp per column):
+// kRegDeg for plans with the register path, kMaxThreadDeg otherwise.  cls_slab_only[c] != 0 keeps class c in slabs up to
+// kMaxThreadDeg whatever the plan (bisection classes: only the slab kernel's generic path implements them).
 template <typename IdxT>
 __global__ void column_keys_kernel(const IdxT* __restrict__ ccol, const uint8_t* __restrict__ col_class, int64_t n_cols,
-                                   int n_classes, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                   unsigned int* bad) {
+                                   int n_classes, int slab_max_deg, const uint8_t* __restrict__ cls_slab_only,
+                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned int* bad) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; j < n_cols; j += stride) {
@@ -192,7 +214,7 @@ __global__ void column_keys_kernel(const IdxT* __restrict__ ccol, const uint8_t*
     uint32_t key;
     if (d <= 0)
       key = kKeyEmpty;
-    else if (d > kMaxThreadDeg)
+    else if (d > kMaxThreadDeg || (d > slab_max_deg && !((int)cls < n_classes && cls_slab_only[cls])))
       key = kKeyLong;
     else
       key = make_key(cls, (uint32_t)d);
@@ -327,6 +349,8 @@ struct KArgs {
   const float* long_a;
   const float* long_c;
   const uint32_t* long_row;
+  const LongCol* mid_cols;   // columns of kRegDeg+1 .. kMaxThreadDeg entries, warp per column (mid_col.cuh), or null
+  const int* mid_range;      // gridDim.x + 1 entries
   // fused tail: the CTA that finishes last also takes the accelerated step on the optimizer state (one launch per
   // iteration).  0: none; 1: after the objective's tail (single device); 2: sharded -- this rank's packed sums go into
   // its exchange slot, the peers' sums are fetched over NVLink, then the tail and the step (dualip_agd_step_peer's work).
@@ -384,6 +408,7 @@ __device__ __forceinline__ int pad_len_of(const KArgs& k, int cls, int d) {
 
 }  // namespace dualip
 #include "slab_fast.cuh"
+#include "mid_col.cuh"
 namespace dualip {
 
 // Generic-path loads of N consecutive entries k0 .. k0+N-1 of this lane's column (N = 8/4: whole 4-entry chunks,
@@ -1187,6 +1212,11 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     }    // segments
   }      // batches
 
+  // ---- this CTA's share of the mid columns, a warp per column (plans with the register path only) ----
+  if (FAST && k.mid_cols != nullptr)
+    mid_columns_of_cta<ACC, OUT, NW>(k, k.mid_cols, k.mid_range[blockIdx.x], k.mid_range[blockIdx.x + 1], warp, lane, s_cls, s_lam,
+                                     s_grad, s, cx, xx);
+
   // ---- flush per-CTA partial sums ----
   __syncthreads();
   if (tid == 0 && k.cta_ns != nullptr) {  // how long this CTA's range took: feedback for dualip_plan_rebalance
@@ -1504,7 +1534,9 @@ template <typename RowT>
 __global__ void cta_row_bound_kernel(const unsigned char* __restrict__ data,
                                      const SlabHdr* __restrict__ hdr, const int2* __restrict__ cta_range, int64_t n_slabs,
                                      const float* __restrict__ cls_xmax,
-                                     int m, float* __restrict__ table, unsigned int* __restrict__ row_cnt) {
+                                     int m, float* __restrict__ table, unsigned int* __restrict__ row_cnt,
+                                     const LongCol* __restrict__ mid_cols, const int* __restrict__ mid_range,
+                                     const float* __restrict__ long_a, const uint32_t* __restrict__ long_row) {
   extern __shared__ __align__(16) unsigned char bound_smem[];
   float* s_bound = reinterpret_cast<float*>(bound_smem);              // m floats: this CTA's row bounds
   unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_bound + m);  // m counters
@@ -1526,6 +1558,17 @@ __global__ void cta_row_bound_kernel(const unsigned char* __restrict__ data,
       const uint32_t r = (uint32_t)row_t[idx];
       atomicAdd(&s_bound[r], fabsf(a_t[idx]) * xmax);
       atomicAdd(&s_cnt[r], 1u);
+    }
+  }
+  if (mid_cols != nullptr) {  // the CTA's mid columns add to the same shared-memory accumulator
+    for (int ci = mid_range[blockIdx.x] + warp; ci < mid_range[blockIdx.x + 1]; ci += NW) {
+      const LongCol lc = mid_cols[ci];
+      const float xmax = cls_xmax[lc.cls];
+      for (int e = lane; e < lc.len; e += 32) {
+        const uint32_t r = long_row[lc.off + e];
+        atomicAdd(&s_bound[r], fabsf(long_a[lc.off + e]) * xmax);
+        atomicAdd(&s_cnt[r], 1u);
+      }
     }
   }
   __syncthreads();
@@ -1643,6 +1686,8 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.long_a = p->long_a;
   k.long_c = p->long_c;
   k.long_row = p->long_row;
+  k.mid_cols = p->n_mid > 0 ? p->longcols : nullptr;
+  k.mid_range = p->mid_range;
   k.fuse = fuse ? fuse->mode : 0;
   if (fuse) {
     k.agd = fuse->agd;
@@ -1653,12 +1698,13 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
     memset(&k.peer, 0, sizeof(k.peer));
     memset(&k.sched, 0, sizeof(k.sched));
   }
-  if (p->n_long > 0) {
-    const int blocks = (int)std::min<int64_t>((p->n_long + 7) / 8, (int64_t)p->n_sms * 8);
+  if (p->n_long > p->n_mid) {
+    const int64_t nl = p->n_long - p->n_mid;
+    const int blocks = (int)std::min<int64_t>((nl + 7) / 8, (int64_t)p->n_sms * 8);
     if (p->fixed_point)
-      matching_long_kernel<1><<<blocks, 256, 0, stream>>>(k, p->longcols, p->n_long);
+      matching_long_kernel<1><<<blocks, 256, 0, stream>>>(k, p->longcols + p->n_mid, nl);
     else
-      matching_long_kernel<0><<<blocks, 256, 0, stream>>>(k, p->longcols, p->n_long);
+      matching_long_kernel<0><<<blocks, 256, 0, stream>>>(k, p->longcols + p->n_mid, nl);
   }
   SlabKernel kern = plan_kernel(p, x_out != nullptr || diag != nullptr);
   kern<<<p->n_ctas, p->threads, p->smem_bytes, stream>>>(k);
@@ -1682,8 +1728,10 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
   void* tmp = nullptr;
   int64_t *g_start_d = nullptr, *g_slab_d = nullptr, *g_off_d = nullptr;
   uint32_t* g_key_d = nullptr;
+  uint8_t* slab_only_d = nullptr;
   int rc = DUALIP_OK;
   auto cleanup = [&]() {
+    cudaFree(slab_only_d);
     cudaFree(bad);
     cudaFree(keys);
     cudaFree(vals);
@@ -1724,7 +1772,39 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
   if (n > 0) {
     const int tb = 256;
     const int nb = (int)std::min<int64_t>((n + tb - 1) / tb, (int64_t)p->n_sms * 32);
-    column_keys_kernel<IdxT><<<nb, tb, 0, stream>>>(ccol, d->col_class_dev, n, p->n_classes, keys, vals, bad);
+    {
+      uint8_t slab_only[kMaxClasses + 1] = {};
+      for (int i = 0; i < p->n_classes; ++i) slab_only[i] = p->classes_host[i].kind >= DUALIP_PROJ_SIMPLEX_BISECT ? 1 : 0;
+      BS_TRY(cudaMalloc(&slab_only_d, kMaxClasses + 1));
+      BS_TRY(cudaMemcpyAsync(slab_only_d, slab_only, kMaxClasses + 1, cudaMemcpyHostToDevice, stream));
+      BS_TRY(cudaStreamSynchronize(stream));
+    }
+    // Where the slab layout ends.  Plans with the register path hand longer columns to the warp-per-column path -- except
+    // that MANY columns just above kRegDeg are cheaper lane-per-column (32 columns advance together in a warp, and up to
+    // stage_region / 128 entries per lane fit the warp's shared-memory stash), while a FEW of them would leave each warp a
+    // serial chain of slow slabs.  The length histogram decides.  DUALIP_MID=0: slabs up to 1024 entries (generic path);
+    // DUALIP_MID=<d>: slabs up to d entries.
+    const bool fast_plan = p->row_bits == 16 && p->smode == 0;
+    const char* env_mid = getenv("DUALIP_MID");
+    int slab_max_deg = kMaxThreadDeg;
+    if (fast_plan) {
+      slab_max_deg = kRegDeg;
+      unsigned int* hist_d = nullptr;
+      std::vector<unsigned int> hist(kMaxThreadDeg + 2, 0u);
+      BS_TRY(cudaMalloc(&hist_d, sizeof(unsigned int) * hist.size()));
+      cudaError_t he = cudaMemsetAsync(hist_d, 0, sizeof(unsigned int) * hist.size(), stream);
+      length_hist_kernel<IdxT><<<nb, tb, 0, stream>>>(ccol, n, hist_d);
+      if (he == cudaSuccess) he = cudaMemcpyAsync(hist.data(), hist_d, sizeof(unsigned int) * hist.size(), cudaMemcpyDeviceToHost, stream);
+      if (he == cudaSuccess) he = cudaStreamSynchronize(stream);
+      cudaFree(hist_d);
+      BS_TRY(he);
+      const int stash_cap = p->stage ? std::min(p->stage_region / (kSlabW * (int)sizeof(float)), 64) : 0;
+      int64_t short_cols = 0;
+      for (int dd = kRegDeg + 1; dd <= stash_cap; ++dd) short_cols += hist[dd];
+      if (short_cols > (int64_t)8 * p->n_sms * (p->threads / 32)) slab_max_deg = stash_cap;
+      if (env_mid) slab_max_deg = atoi(env_mid) <= 0 ? kMaxThreadDeg : std::max(kRegDeg, std::min(atoi(env_mid), kMaxThreadDeg));
+    }
+    column_keys_kernel<IdxT><<<nb, tb, 0, stream>>>(ccol, d->col_class_dev, n, p->n_classes, slab_max_deg, slab_only_d, keys, vals, bad);
     size_t b1 = 0, b2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, b1, keys, keys_s, vals, perm, (int)n, 0, kKeyBits, stream);
     cub::DeviceRunLengthEncode::Encode(nullptr, b2, keys_s, uniq, counts, n_runs_dev, (int)n, stream);
@@ -1840,8 +1920,13 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
     std::vector<LongCol> lc(n_long);
     BS_TRY(cudaMemcpyAsync(lc.data(), p->longcols, sizeof(LongCol) * n_long, cudaMemcpyDeviceToHost, stream));
     BS_TRY(cudaStreamSynchronize(stream));
+    // by length: the mid columns (warp per column inside the slab kernel) come first, and a warp's consecutive columns take
+    // the same specialisation
+    std::stable_sort(lc.begin(), lc.end(), [](const LongCol& x, const LongCol& y) { return x.len < y.len; });
     int64_t tot = 0;
+    p->n_mid = 0;
     for (auto& c : lc) {
+      if (c.len <= kMaxThreadDeg) ++p->n_mid;
       c.off = tot;
       tot += c.len;
       p->class_used[c.cls & 0xff] = true;
@@ -1965,6 +2050,35 @@ static int build_cta_ranges(dualip_plan* p) {
   return upload_ranges(p, cut_ranges(p, pieces), 0);
 }
 
+// Every CTA's contiguous share of the (length-sorted) mid columns, cut to equal cost: a column costs its length plus a fixed
+// part (two warp-wide passes over its registers per search round, the reductions, the column header).
+static int build_mid_ranges(dualip_plan* p) {
+  if (p->n_mid <= 0) return DUALIP_OK;
+  std::vector<LongCol> lc((size_t)p->n_mid);
+  if (cudaMemcpy(lc.data(), p->longcols, sizeof(LongCol) * lc.size(), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("reading the mid-column table failed");
+    return DUALIP_ECUDA;
+  }
+  auto cost = [](const LongCol& c) { return (double)c.len + 48.0; };
+  double total = 0.0;
+  for (const LongCol& c : lc) total += cost(c);
+  std::vector<int> r((size_t)p->n_ctas + 1, 0);
+  double acc = 0.0;
+  size_t i = 0;
+  for (int c = 0; c < p->n_ctas; ++c) {
+    r[c] = (int)i;
+    const double target = total * (double)(c + 1) / (double)p->n_ctas;
+    while (i < lc.size() && acc + 0.5 * cost(lc[i]) < target) acc += cost(lc[i++]);
+  }
+  r[p->n_ctas] = (int)lc.size();
+  if (cudaMalloc(&p->mid_range, sizeof(int) * r.size()) != cudaSuccess ||
+      cudaMemcpy(p->mid_range, r.data(), sizeof(int) * r.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("uploading the mid-column ranges failed");
+    return DUALIP_ECUDA;
+  }
+  return DUALIP_OK;
+}
+
 // Chooses the accumulation mode of a plan.  Fixed point needs (a) a finite bound on x for every class, (b) the register /
 // shared-memory configuration it is built for (uint16 rows, lambda + accumulator in shared memory), and (c) enough
 // resolution: with quantum q = 2^-F the rounding error of a row sum of N terms is ~ q*sqrt(N/12); it must stay below a
@@ -2019,15 +2133,17 @@ static int choose_accumulator(dualip_plan* p, cudaStream_t stream, int keep_bits
   CA_TRY(cudaMemsetAsync(table, 0, sizeof(float) * tab, stream));
   CA_TRY(cudaMemsetAsync(long_bound, 0, sizeof(float) * m, stream));
   CA_TRY(cudaMemsetAsync(row_cnt, 0, sizeof(unsigned int) * m, stream));
-  if (p->n_slabs > 0) {
+  if (p->n_slabs > 0 || p->n_mid > 0) {
     const size_t bsm = 8 * (size_t)m;  // fits: mode 0 already keeps 8*m bytes of lambda + accumulator in shared memory
     CA_TRY(cudaFuncSetAttribute((const void*)cta_row_bound_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
     cta_row_bound_kernel<unsigned short><<<p->n_ctas, p->threads, bsm, stream>>>(
-        p->data, p->hdr, p->cta_range, p->n_slabs, xmax_d, m, table, row_cnt);
+        p->data, p->hdr, p->cta_range, p->n_slabs, xmax_d, m, table, row_cnt, p->n_mid > 0 ? p->longcols : nullptr, p->mid_range,
+        p->long_a, p->long_row);
   }
-  if (p->n_long > 0) {
-    const int blocks = (int)std::min<int64_t>((p->n_long + 7) / 8, (int64_t)p->n_sms * 8);
-    long_row_bound_kernel<<<blocks, 256, 0, stream>>>(p->longcols, p->n_long, p->long_a, p->long_row, xmax_d, long_bound, row_cnt);
+  if (p->n_long > p->n_mid) {
+    const int64_t nl = p->n_long - p->n_mid;
+    const int blocks = (int)std::min<int64_t>((nl + 7) / 8, (int64_t)p->n_sms * 8);
+    long_row_bound_kernel<<<blocks, 256, 0, stream>>>(p->longcols + p->n_mid, nl, p->long_a, p->long_row, xmax_d, long_bound, row_cnt);
   }
   bound_reduce_kernel<<<(m + 255) / 256, 256, 0, stream>>>(table, p->n_ctas, m, row_max, row_sum);
   std::vector<float> h_max(m), h_sum(m), h_long(m);
@@ -2162,6 +2278,7 @@ void dualip_plan_destroy(dualip_plan* p) {
   cudaFree(p->hdr);
   cudaFree(p->orig_start);
   cudaFree(p->longcols);
+  cudaFree(p->mid_range);
   cudaFree(p->long_a);
   cudaFree(p->long_c);
   cudaFree(p->long_row);
@@ -2309,11 +2426,14 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   // do not launch more warps than there are slabs (tiny problems)
   {
     const int64_t warps_per_cta = p->threads / 32;
-    const int64_t want = std::max<int64_t>(1, (p->n_slabs + warps_per_cta - 1) / warps_per_cta);
+    const int64_t want = std::max<int64_t>(1, std::max((p->n_slabs + warps_per_cta - 1) / warps_per_cta,
+                                                       (p->n_mid + warps_per_cta - 1) / warps_per_cta));
     if (!(env_ctas && atoi(env_ctas) > 0) && want < p->n_ctas) p->n_ctas = (int)want;
   }
   {
     int rc = build_cta_ranges(p);
+    if (rc != DUALIP_OK) return fail(rc);
+    rc = build_mid_ranges(p);
     if (rc != DUALIP_OK) return fail(rc);
   }
   {
@@ -2463,10 +2583,10 @@ int dualip_plan_info(const dualip_plan* p, int64_t* out, int cap) {
     set_error("null argument");
     return DUALIP_EINVAL;
   }
-  const int64_t v[17] = {p->n_slabs, p->n_long, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
-                         p->smode,   p->rows32 * kSlabW, (p->n_long > 0) ? 2 : 1, (int64_t)p->owned_bytes, p->n_short, p->nnz,
-                         p->fixed_point, p->fx_bits, (int64_t)(p->fx_relerr * 1e12), p->stage, p->row_unscale ? 1 : 0};
-  for (int i = 0; i < cap && i < 17; ++i) out[i] = v[i];
+  const int64_t v[18] = {p->n_slabs, p->n_long - p->n_mid, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
+                         p->smode,   p->rows32 * kSlabW, (p->n_long > p->n_mid) ? 2 : 1, (int64_t)p->owned_bytes, p->n_short, p->nnz,
+                         p->fixed_point, p->fx_bits, (int64_t)(p->fx_relerr * 1e12), p->stage, p->row_unscale ? 1 : 0, p->n_mid};
+  for (int i = 0; i < cap && i < 18; ++i) out[i] = v[i];
   return DUALIP_OK;
 }
 

@@ -284,11 +284,11 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
 
     # -- introspection -------------------------------------------------------------------------------------
     def plan_info(self) -> dict:
-        buf = (ctypes.c_int64 * 17)()
-        _native.check(_native.lib().dualip_plan_info(self._plan, buf, 17))
+        buf = (ctypes.c_int64 * 18)()
+        _native.check(_native.lib().dualip_plan_info(self._plan, buf, 18))
         names = ["n_slabs", "n_long_cols", "n_ctas", "threads", "smem_bytes", "row_bits", "smem_mode", "slab_elems",
                  "launches_per_calc", "owned_bytes", "n_slab_cols", "nnz", "fixed_point", "fixed_point_bits",
-                 "fixed_point_relerr_e12", "staged_degree", "row_scaled"]
+                 "fixed_point_relerr_e12", "staged_degree", "row_scaled", "n_mid_cols"]
         return dict(zip(names, list(buf)))
 
     def algorithmic_bytes(self, save_primal: bool = False) -> int:

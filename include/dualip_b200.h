@@ -122,7 +122,9 @@ int dualip_plan_rebalance(dualip_plan* plan, void* stream);
  * [12] 1 if the gradient is accumulated in 32-bit fixed point (deterministic), 0 for fp32 atomics
  * [13] F: fixed-point fraction bits (value * 2^F)  [14] worst-row rounding-error estimate * 1e12
  * [15] longest column whose slab is staged through shared memory by the TMA engine (0: plain vector loads)
- * [16] 1 if the rows are stored scaled by per-row powers of two (fixed-point resolution per row; results unchanged) */
+ * [16] 1 if the rows are stored scaled by per-row powers of two (fixed-point resolution per row; results unchanged)
+ * [17] n_mid_cols: columns of 21..1024 entries kept column-contiguous and processed a warp per column inside the same
+ *      launch ([1] counts only the columns beyond 1024 entries, which take the separate long-column kernel) */
 int dualip_plan_info(const dualip_plan* plan, int64_t* out, int cap);
 
 /* One evaluation of the dual at lambda on this shard, epilogue included (single device).

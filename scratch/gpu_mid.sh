@@ -1,0 +1,31 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_midcols.py -m gpu -x -q 2>&1 | grep -v "Warning\|sparse_csc" | tail -5
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
+grep -v "Warning\|sparse_csc" gpurun_out/pytest.log | tail -6
+timeout 900 python bench.py --workload c1 --steps 100 --warmup 10 --no-cpu > gpurun_out/c1_n1.json 2> gpurun_out/c1_n1.err; echo "c1 rc=$?"
+timeout 600 python bench.py --workload c2 --steps 2000 --warmup 50 --no-cpu > gpurun_out/c2_n1.json 2> gpurun_out/c2_n1.err; echo "c2 rc=$?"
+timeout 900 python bench.py --no-cpu > gpurun_out/c3_n1.json 2> gpurun_out/c3_n1.err; echo "c3 rc=$?"
+python - <<'PY'
+import json
+for f in ["c1_n1","c2_n1","c3_n1"]:
+    try:
+        d=json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1])
+        print(f, "it/s %.1f ms/step %.4f kernel_ms %.4f (min %.4f max %.4f) frac %.3f e2e %.1f launches %s"%(d["value"],d["ms_per_step"],d["roofline"]["kernel_ms"],d["roofline"]["kernel_ms_min"],d["roofline"]["kernel_ms_max"],d["roofline"]["frac"], d["e2e"]["value"], d["gpu_launches"]))
+        pl=d["setup"]["plan"]; print("   mid", pl.get("n_mid_cols"), "long", pl["n_long_cols"], "slabs", pl["n_slabs"], "fixed", pl["fixed_point"])
+    except Exception as e:
+        print(f, "ERR", e); print(open(f"gpurun_out/{f}.err").read()[-800:])
+PY
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/c1_launches.csv python bench.py --workload c1 --steps 5 --warmup 3 --warm-start-iters 20 --no-cpu --no-e2e > /dev/null 2>&1
+python - <<'PY'
+import csv, collections
+rows=[r for r in csv.reader(open("gpurun_out/c1_launches.csv")) if len(r)>5]
+hdr=None; agg=collections.defaultdict(list)
+for r in rows:
+    if r[0]=="ID": hdr=r; continue
+    if hdr is None: continue
+    d=dict(zip(hdr,r))
+    try: agg[d["Kernel Name"][:60]].append(float(d["Metric Value"].replace(",","")))
+    except Exception: pass
+for k,v in agg.items(): print("  %-62s n=%3d last5 mean %.1f us"%(k,len(v),sum(v[-5:])/len(v[-5:])/1e3))
+PY

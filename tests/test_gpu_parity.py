@@ -197,7 +197,7 @@ def test_mixed_projection_map_against_oracles(case):
     A, C = _csc(p)
     obj = MatchingSolverDualObjectiveFunction(MatchingInputArgs(A, C, pm, torch.from_numpy(p["b"]).to(DEV)), gamma=gamma)
     info = obj.plan_info()
-    assert info["n_slab_cols"] + info["n_long_cols"] == int((deg > 0).sum())
+    assert info["n_slab_cols"] + info["n_mid_cols"] + info["n_long_cols"] == int((deg > 0).sum())
     r = obj.calculate(torch.from_numpy(p["lam"]).to(DEV), save_primal=True, diagnostics=True)
     x = r.primal_var.cpu().numpy()
     ref_c = c_oracle.calculate(p["ccol"], p["row"], p["a"], p["c"], m, classes, p["lam"], gamma, p["b"], col_class)
