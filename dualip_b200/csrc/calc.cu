@@ -139,6 +139,7 @@ struct dualip_plan {
                                   // slab kernel), [n_mid, n_long) long columns (matching_long_kernel)
   int64_t n_long = 0;
   int64_t n_mid = 0;
+  int64_t n_ctalong = 0;          // of the long columns, those that fit the CTA-per-column kernel's stash: [n_mid, n_mid + n_ctalong)
   int* mid_range = nullptr;       // n_ctas + 1: every CTA's contiguous share of the mid columns (equal cost)
   int64_t long_total = 0;         // entries of all long columns
   float* long_a = nullptr;
@@ -409,6 +410,7 @@ __device__ __forceinline__ int pad_len_of(const KArgs& k, int cls, int d) {
 }  // namespace dualip
 #include "slab_fast.cuh"
 #include "mid_col.cuh"
+#include "long_col.cuh"
 namespace dualip {
 
 // Generic-path loads of N consecutive entries k0 .. k0+N-1 of this lane's column (N = 8/4: whole 4-entry chunks,
@@ -1698,13 +1700,21 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
     memset(&k.peer, 0, sizeof(k.peer));
     memset(&k.sched, 0, sizeof(k.sched));
   }
-  if (p->n_long > p->n_mid) {
-    const int64_t nl = p->n_long - p->n_mid;
+  if (p->n_ctalong > 0) {  // 1025 .. kLongStash entries: a CTA per column, u in shared memory
+    const int stash_bytes = kLongStash * (int)sizeof(float);  // the attribute was raised at plan creation (per device)
+    const int blocks = (int)std::min<int64_t>(p->n_ctalong, (int64_t)p->n_sms * 4);
+    if (p->fixed_point)
+      matching_long_cta_kernel<1><<<blocks, kLongThreads, stash_bytes, stream>>>(k, p->longcols + p->n_mid, (int)p->n_ctalong);
+    else
+      matching_long_cta_kernel<0><<<blocks, kLongThreads, stash_bytes, stream>>>(k, p->longcols + p->n_mid, (int)p->n_ctalong);
+  }
+  if (p->n_long > p->n_mid + p->n_ctalong) {  // longer still: warp per column, re-streamed
+    const int64_t nl = p->n_long - p->n_mid - p->n_ctalong;
     const int blocks = (int)std::min<int64_t>((nl + 7) / 8, (int64_t)p->n_sms * 8);
     if (p->fixed_point)
-      matching_long_kernel<1><<<blocks, 256, 0, stream>>>(k, p->longcols + p->n_mid, nl);
+      matching_long_kernel<1><<<blocks, 256, 0, stream>>>(k, p->longcols + p->n_mid + p->n_ctalong, nl);
     else
-      matching_long_kernel<0><<<blocks, 256, 0, stream>>>(k, p->longcols + p->n_mid, nl);
+      matching_long_kernel<0><<<blocks, 256, 0, stream>>>(k, p->longcols + p->n_mid + p->n_ctalong, nl);
   }
   SlabKernel kern = plan_kernel(p, x_out != nullptr || diag != nullptr);
   kern<<<p->n_ctas, p->threads, p->smem_bytes, stream>>>(k);
@@ -1925,8 +1935,12 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
     std::stable_sort(lc.begin(), lc.end(), [](const LongCol& x, const LongCol& y) { return x.len < y.len; });
     int64_t tot = 0;
     p->n_mid = 0;
+    const char* env_lc = getenv("DUALIP_LONG_CTA");  // DUALIP_LONG_CTA=0: all long columns take the warp-per-column kernel
+    const bool use_ctalong = !(env_lc && atoi(env_lc) == 0);
+    p->n_ctalong = 0;
     for (auto& c : lc) {
       if (c.len <= kMaxThreadDeg) ++p->n_mid;
+      else if (use_ctalong && c.len <= kLongStash) ++p->n_ctalong;
       c.off = tot;
       tot += c.len;
       p->class_used[c.cls & 0xff] = true;
@@ -2484,6 +2498,12 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
     const int max_dyn = (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes;
     DUALIP_TRY_FAIL(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   }
+  if (p->n_ctalong > 0) {
+    DUALIP_TRY_FAIL(cudaFuncSetAttribute((const void*)matching_long_cta_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kLongStash * (int)sizeof(float)));
+    DUALIP_TRY_FAIL(cudaFuncSetAttribute((const void*)matching_long_cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kLongStash * (int)sizeof(float)));
+  }
   DUALIP_TRY_FAIL(cudaDeviceSynchronize());
 #undef DUALIP_TRY_FAIL
   *out = p;
@@ -2584,7 +2604,7 @@ int dualip_plan_info(const dualip_plan* p, int64_t* out, int cap) {
     return DUALIP_EINVAL;
   }
   const int64_t v[18] = {p->n_slabs, p->n_long - p->n_mid, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
-                         p->smode,   p->rows32 * kSlabW, (p->n_long > p->n_mid) ? 2 : 1, (int64_t)p->owned_bytes, p->n_short, p->nnz,
+                         p->smode,   p->rows32 * kSlabW, 1 + (p->n_ctalong > 0 ? 1 : 0) + (p->n_long > p->n_mid + p->n_ctalong ? 1 : 0), (int64_t)p->owned_bytes, p->n_short, p->nnz,
                          p->fixed_point, p->fx_bits, (int64_t)(p->fx_relerr * 1e12), p->stage, p->row_unscale ? 1 : 0, p->n_mid};
   for (int i = 0; i < cap && i < 18; ++i) out[i] = v[i];
   return DUALIP_OK;

@@ -110,3 +110,46 @@ def test_movielens_shaped_ascent_agrees_on_both_paths(monkeypatch):
     assert np.allclose(a.dual_objective_log, bb.dual_objective_log, rtol=1e-5)
     assert np.allclose(a.step_size_log, bb.step_size_log, rtol=1e-3)
     assert torch.allclose(a.dual_val, bb.dual_val, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("which", ["simplex", "mixed"])
+@pytest.mark.parametrize("gamma", [0.1, 5.0])
+def test_long_columns_cta_per_column_kernel_against_the_oracle(monkeypatch, which, gamma):
+    """Columns beyond 1024 entries: a CTA per column with u in a shared-memory stash (csrc/long_col.cuh) up to 12288 entries,
+    the warp-per-column kernel above.  x and the projection branch must equal the numpy restatement of the reference; with
+    DUALIP_LONG_CTA=0 every long column takes the older kernel, whose x must agree to rounding."""
+    rng = np.random.default_rng(5)
+    m = 14000
+    deg = np.concatenate([rng.integers(1025, 9000, 24), [12288, 12289, 13000, 1025, 1026, 4096, 4097], rng.integers(2, 60, 30)]).astype(np.int64)
+    n = deg.size
+    ccol = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(deg, out=ccol[1:])
+    row = np.concatenate([np.sort(rng.choice(m, size=d, replace=False)) for d in deg]).astype(np.int64)
+    E = row.size
+    c = (-rng.choice(np.arange(0.5, 5.01, 0.5), size=E)).astype(np.float32)
+    a = np.where(rng.random(E) < 0.5, 1.0, rng.lognormal(0, 0.5, E)).astype(np.float32)
+    p = dict(ccol=ccol, row=row, a=a, c=c, b=np.full(m, 0.3, dtype=np.float32), lam=(rng.random(m) * 4.0).astype(np.float32), n_rows=m)
+    lam = torch.from_numpy(p["lam"]).to(DEV)
+    obj = _objective(p, _maps(n)[which], gamma)
+    info = obj.plan_info()
+    assert info["n_long_cols"] == 31 and info["launches_per_calc"] == 3  # CTA-per-column kernel, warp-per-column kernel, slab kernel
+    r = obj.calculate(lam, save_primal=True, diagnostics=True)
+    if which == "mixed":
+        opm = {"s": O.ProjEntry("simplex", {"z": 1.0}, np.arange(0, n, 3)), "e": O.ProjEntry("simplex_eq", {"z": 2.5}, np.arange(1, n, 3)),
+               "b": O.ProjEntry("box", {"lower": 0.0, "upper": 0.7}, np.arange(2, n, 3))}
+    else:
+        opm = {"s": O.ProjEntry("simplex", {"z": 1.0}, np.arange(n))}
+    ref = O.matching_calculate(p["ccol"], p["row"], p["a"], p["c"], m, opm, p["lam"], gamma, p["b"])
+    x = r.primal_var.cpu().numpy()
+    bad = np.flatnonzero(x != ref.primal_var)
+    assert bad.size == 0, f"x differs from the oracle at {bad[:5]} (columns {np.searchsorted(ccol, bad[:5], side='right') - 1})"
+    d = r.projection_diag.cpu().numpy()
+    is_sx = ref.branch >= 0
+    assert np.array_equal((d[ccol[:-1]] & 3)[is_sx], ref.branch[is_sx])
+    assert abs(float(r.scalars64[0]) - ref.dual_objective) <= 1e-5 * abs(ref.dual_objective)
+    assert np.allclose(r.dual_gradient.cpu().numpy(), ref.dual_gradient, rtol=1e-5, atol=1e-4)
+    monkeypatch.setenv("DUALIP_LONG_CTA", "0")
+    old = _objective(p, _maps(n)[which], gamma)
+    assert old.plan_info()["launches_per_calc"] == 2
+    r_old = old.calculate(lam, save_primal=True)
+    assert torch.allclose(r_old.primal_var, r.primal_var, rtol=1e-5, atol=1e-6)
