@@ -94,6 +94,10 @@ SIGNATURES = {
                                               C.c_float, C.c_int32, C.c_double, C.c_int32, C.c_void_p]),
     "dualip_matching_ascent_step_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
                                                    C.c_void_p, C.c_float, C.c_int32, C.c_double, C.c_int32, C.c_void_p]),
+    "dualip_matching_calc_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]),
+    "dualip_matching_calc_peer_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p]),
     "dualip_agd_set_schedule": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),
     "dualip_agd_steps_launched": (C.c_longlong, [C.c_void_p]),
     "dualip_matching_ascent_step_scheduled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

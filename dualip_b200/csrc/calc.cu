@@ -1333,9 +1333,9 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     // sharded + scheduled: the exchange step number follows the device-side iteration count, and so does the slot
     const unsigned long long seq = scheduled ? (unsigned long long)(k.sched.seq_base + sched_it + 1) : k.peer.seq;
     float* partial_out = k.partial_out;
-    if (k.fuse == 2 && scheduled)
+    if (k.fuse == 2 && scheduled)  // (fuse == 3 is never scheduled)
       partial_out = reinterpret_cast<float*>(k.peer.win[k.peer.rank] + kPeerFlagBytes + (size_t)(seq & 1ull) * k.peer.slot_bytes);
-    const bool push = k.fuse == 2 && k.peer.push != 0;
+    const bool push = (k.fuse == 2 || k.fuse == 3) && k.peer.push != 0;
     float* pslot[DUALIP_PEER_MAX_WORLD];  // push: this rank's slot in every rank's window
 #pragma unroll
     for (int r = 0; r < DUALIP_PEER_MAX_WORLD; ++r) pslot[r] = (push && r < k.peer.world) ? peer_push_slot(k.peer, r, k.peer.rank, seq) : nullptr;
@@ -1366,12 +1366,20 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
         partial_out[m + 1] = (float)xxv;
       }
     }
-    if (k.fuse == 2) {
+    if (k.fuse == 2 || k.fuse == 3) {
       if (push)
         peer_push_exchange_cta(k.peer, m + 2, seq);
       else
         peer_exchange_cta(k.peer, m + 2, seq);
-      agd_step_body<true>(k.agd, scheduled ? step_dyn_sched(k.agd, k.sched, sched_it) : step_dyn_of(k.agd));
+      if (k.fuse == 2) {
+        agd_step_body<true>(k.agd, scheduled ? step_dyn_sched(k.agd, k.sched, sched_it) : step_dyn_of(k.agd));
+      } else {
+        // sharded evaluation for a caller that keeps the iterate itself (host-buffer path): the m-length tail on the summed
+        // vector, no optimizer step
+        const float* sum = k.peer.sum;
+        cta_epilogue([&](int i) { return sum[i]; }, [](int) {}, (double)sum[m], (double)sum[m + 1], k.lambda, k.b, m, gamma_run,
+                     k.grad_out, k.scalars_out, dscratch, fscratch);
+      }
     }
   }
   if (tid == 0) {
@@ -2824,6 +2832,45 @@ int dualip_ascent_graph_launch(dualip_ascent_graph* g, void* stream) {
   DUALIP_CUDA_TRY(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
   g->agd->launched += g->chunk;
   if (g->peer) g->peer->seq += (unsigned long long)g->chunk;
+  return DUALIP_OK;
+}
+
+int dualip_matching_calc_peer(dualip_plan* p, dualip_peer* peer, const float* lambda_dev, const float* b_dev, double gamma,
+                              float* grad_out_dev, dualip_scalars* scalars_out_dev, void* stream) {
+  if (!p || !peer || !lambda_dev || !grad_out_dev || !scalars_out_dev) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  if (!peer->connected || peer->m != p->m || peer->device != p->device) {
+    set_error("exchange window does not match the plan, or is not connected");
+    return DUALIP_EINVAL;
+  }
+  DeviceGuard g(p->device);
+  FuseSpec f;
+  f.mode = 3;
+  f.peer = peer_args(peer, true);
+  float* slot = reinterpret_cast<float*>(peer->window + kPeerFlagBytes + (size_t)(f.peer.seq & 1ull) * peer->slot_bytes);
+  return launch_eval(p, lambda_dev, b_dev, gamma, grad_out_dev, scalars_out_dev, slot, nullptr, nullptr, 0, (cudaStream_t)stream, &f);
+}
+
+int dualip_matching_calc_peer_host(dualip_plan* p, dualip_peer* peer, const float* lambda_host, const float* b_dev, double gamma,
+                                   float* grad_out_host, dualip_scalars* scalars_out_host, void* stream) {
+  if (!p || !peer || !lambda_host || !grad_out_host || !scalars_out_host) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  DeviceGuard g(p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  DUALIP_CUDA_TRY(cudaMemcpyAsync(p->lambda_stage, lambda_host, sizeof(float) * p->m, cudaMemcpyHostToDevice, st));
+  int rc = dualip_matching_calc_peer(p, peer, p->lambda_stage, b_dev, gamma, p->grad_stage, p->scal_stage, stream);
+  if (rc != DUALIP_OK) return rc;
+  DUALIP_CUDA_TRY(cudaMemcpyAsync(grad_out_host, p->grad_stage, sizeof(float) * p->m, cudaMemcpyDeviceToHost, st));
+  DUALIP_CUDA_TRY(cudaMemcpyAsync(scalars_out_host, p->scal_stage, sizeof(dualip_scalars), cudaMemcpyDeviceToHost, st));
+  DUALIP_CUDA_TRY(cudaStreamSynchronize(st));
+  if (*peer->status_host != 0) {
+    set_error("peer exchange: a rank did not arrive within the time-out");
+    return DUALIP_ECUDA;
+  }
   return DUALIP_OK;
 }
 

@@ -104,8 +104,10 @@ __device__ __forceinline__ void mid_column(const KArgs& k, const LongCol& lc, co
     } else {
       float S = 0.f;
 #pragma unroll
-      for (int i = 0; i < NPL; ++i)
-        for (int l = 0; l < 32; ++l) S = __fadd_rn(S, __shfl_sync(FULL, u[i], l));  // entry l + 32 i, in order
+      for (int i = 0; i < NPL; ++i) {
+#pragma unroll 1
+        for (int l = 0; l < 32; ++l) S = __fadd_rn(S, __shfl_sync(FULL, u[i], l));  // entry l + 32 i, in order (rare: not unrolled)
+      }
       feasible = S <= pc.z_thr;
     }
   }
@@ -216,8 +218,24 @@ template <int ACC, bool OUT, int NW>
 __device__ __forceinline__ void mid_columns_of_cta(const KArgs& k, const LongCol* __restrict__ cols, int begin, int end, int warp,
                                                    int lane, const dualip_proj_class* s_cls, const float* s_lam, float* s_grad,
                                                    float s, double& cx, double& xx) {
+  // The work on a column is a chain of dependent steps (header -> a/c/row -> lambda gather -> reductions), and a warp has
+  // only 15 others to hide behind: the header of the column after next is loaded, and the data of the next column is pulled
+  // into L2 (one prefetch per lane covers up to 4 KB of each array), while the current column is processed.
+  const LongCol none = {0, 0, 0, 0};
+  LongCol nxt = (begin + warp < end) ? cols[begin + warp] : none;
+  LongCol nxt2 = (begin + warp + NW < end) ? cols[begin + warp + NW] : none;
   for (int ci = begin + warp; ci < end; ci += NW) {
-    const LongCol lc = cols[ci];
+    const LongCol lc = nxt;
+    nxt = nxt2;
+    if (ci + NW < end) {
+      const size_t span = (size_t)nxt.len * 4 + 127;
+      if ((size_t)lane * 128 < span) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(k.long_a + nxt.off) + lane * 128));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(k.long_c + nxt.off) + lane * 128));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(k.long_row + nxt.off) + lane * 128));
+      }
+    }
+    nxt2 = (ci + 2 * NW < end) ? cols[ci + 2 * NW] : none;
     const dualip_proj_class pc = s_cls[lc.cls];
     const int npl = (lc.len + 31) >> 5;
     if (npl <= 1)

@@ -267,6 +267,9 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
         torch.cuda.synchronize(self.device)
         _native.check(_native.lib().dualip_plan_create(ctypes.byref(handle), ctypes.byref(desc)), "dualip_plan_create")
         self._plan = handle
+        # the plan holds a COPY of A's and c's values in its own layout; the reference reads the tensors at every call
+        # (matching.py:136-142).  An in-place edit after construction would be silently ignored, so it is detected instead.
+        self._value_versions = (self._a_vals._version, self._c_vals._version)
         self._launches = 0
         self._rebalance_at = (4, 8, 16, 32, 64, 128) if os.environ.get("DUALIP_REBALANCE", "1") != "0" else ()
         self._scal = torch.zeros(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=self.device)
@@ -299,6 +302,13 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
     # -- raw launches (device pointers; used by the Maximizer's fused loop) ---------------------------------
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def check_inputs_unchanged(self) -> None:
+        """Raises if A.values() or c.values() were modified in place since the plan was built (e.g. jacobi_precondition called
+        after the constructor): the plan's snapshot would no longer describe the tensors."""
+        if (self._a_vals._version, self._c_vals._version) != self._value_versions:
+            raise RuntimeError("A.values() or c.values() were modified in place after the objective was built; dualip_b200 keeps a "
+                               "snapshot of them in its own layout (apply preprocessing first, or build a new objective)")
 
     def launched(self) -> None:
         """Self-tuning of the plan, called by `calculate` and by the Maximizer's loop after every evaluation: after 4, 8,
@@ -414,6 +424,7 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
         the per-column projection branch / support size as `result.projection_diag` (uint8 per nnz position)."""
         if gamma is not None and gamma != self.gamma:
             self.gamma = gamma  # no O(E) rescaling pass: the kernel forms -(a*lambda + c)/gamma in registers
+        self.check_inputs_unchanged()
         if isinstance(dual_val, torch.Tensor) and dual_val.device.type == "cpu":
             if save_primal or kwargs.get("diagnostics"):
                 raise ValueError("save_primal / diagnostics need a device-resident dual_val")
@@ -562,7 +573,23 @@ class MatchingSolverDualObjectiveFunctionDistributed(BaseObjective):
                 self._h_grad = torch.empty(self.m, dtype=torch.float32).pin_memory()
                 self._h_scal = torch.empty(len(_native.SCALAR_FIELDS), dtype=torch.float64).pin_memory()
                 self._d_lam = torch.empty(self.m, dtype=torch.float32, device=self.device)
+            if dual_val.dtype != torch.float32 or dual_val.numel() != self.m:
+                raise ValueError(f"dual_val must be float32 with {self.m} entries")
             self._h_lam.copy_(dual_val.reshape(-1))
+            peer = self.peer_exchange()  # COLLECTIVE on first use: every rank evaluates in lockstep anyway
+            if peer is not None:
+                # lambda host->device, shard kernel whose last CTA exchanges the sums through peer memory and runs the m-length
+                # tail, grad + scalars device->host: ONE native call, no collective call, no tensor allocation on the device
+                self.local_objective.check_inputs_unchanged()
+                with torch.cuda.device(self.device):
+                    rc = _native.lib().dualip_matching_calc_peer_host(
+                        self.local_objective._plan, peer.handle, self._h_lam.data_ptr(), self.b_vec.data_ptr(), float(self.gamma),
+                        self._h_grad.data_ptr(), self._h_scal.data_ptr(), self.local_objective._stream())
+                if rc != _native.OK and peer.status_nowait():
+                    self._peer_failed, self._peer = True, None
+                _native.check(rc, "dualip_matching_calc_peer_host")
+                self.local_objective.launched()
+                return _host_result(self._h_grad.clone(), self._h_scal.clone(), False)
             self._d_lam.copy_(self._h_lam, non_blocking=True)
             dual_val = self._d_lam
         lam = self.local_objective._check_dual(dual_val)

@@ -306,6 +306,8 @@ class FusedAscentLoop:
             self.grad = torch.empty(self.m, dtype=torch.float32, device=self.device)
             self.scal = torch.zeros(len(_native.SCALAR_FIELDS), dtype=torch.float64, device=self.device)
             local = f.local_objective if self.sharded else f
+            if hasattr(local, "check_inputs_unchanged"):
+                local.check_inputs_unchanged()  # the raw launches below bypass calculate()
             self.block_entries = bool(getattr(local, "has_block_entries", False))  # user-registered projections
             need_partial = self.sharded or self.block_entries
             self.partial = torch.empty(self.m + 2, dtype=torch.float32, device=self.device) if need_partial else None

@@ -38,6 +38,7 @@ def jacobi_precondition(A: torch.Tensor, b: torch.Tensor, norms_save_path: str =
             _native.check(_native.lib().dualip_scale_rows(vals.data_ptr(), row.data_ptr(), bits, vals.numel(),
                                                           rec.data_ptr(), vals.device.index, stream))
             b.mul_(rec)
+        vals[:0].zero_()  # the kernel wrote through a raw pointer: bump the tensor's version counter (objectives check it)
         if norms_save_path:
             torch.save(norms, Path(norms_save_path))
         return norms
@@ -47,6 +48,8 @@ def jacobi_precondition(A: torch.Tensor, b: torch.Tensor, norms_save_path: str =
             vals.data_ptr(), row.data_ptr(), 32 if row.dtype == torch.int32 else 64, vals.numel(), b.data_ptr(), m,
             norms.data_ptr(), vals.device.index, torch.cuda.current_stream().cuda_stream)
     _native.check(rc, "dualip_jacobi_precondition")
+    vals[:0].zero_()  # in-place change made through a raw pointer: bump the version counter (objectives check it)
+    b[:0].zero_()
     if norms_save_path:
         torch.save(norms, Path(norms_save_path))
     return norms

@@ -262,6 +262,16 @@ int dualip_matching_ascent_step_peer(dualip_plan* plan, dualip_agd* agd, dualip_
                                      float* grad_out_dev, dualip_scalars* scalars_out_dev, float beta, int32_t decay_now,
                                      double decay_factor, int32_t iter_index, void* stream);
 
+/* Sharded evaluation for a caller that keeps the dual iterate itself (the host-buffer path; a per-iteration callback):
+ * dualip_matching_partial + the exchange through peer memory + dualip_matching_epilogue in ONE launch, no optimizer step.
+ * Replaces the distributed calculate (objectives/matching.py:247-307) including its three dist.reduce + barrier.
+ * COLLECTIVE: every rank must make the same sequence of exchange calls.  The _host variant copies lambda host->device and
+ * grad / scalars device->host and synchronises the stream (and reports a timed-out exchange as an error). */
+int dualip_matching_calc_peer(dualip_plan* plan, dualip_peer* peer, const float* lambda_dev, const float* b_dev, double gamma,
+                              float* grad_out_dev, dualip_scalars* scalars_out_dev, void* stream);
+int dualip_matching_calc_peer_host(dualip_plan* plan, dualip_peer* peer, const float* lambda_host, const float* b_dev,
+                                   double gamma, float* grad_out_host, dualip_scalars* scalars_out_host, void* stream);
+
 /* ---- scheduled launches and CUDA-graph replay (reference loop: optimizers/agd.py:150-206) ----
  * dualip_matching_ascent_step takes gamma, beta, the decay flag and the log slot as arguments, so every iteration is a
  * different launch.  With a device-resident schedule the kernel looks them up itself at the number of steps the state

@@ -166,3 +166,45 @@ def test_peer_wait_is_bounded(monkeypatch):
     with pytest.raises(ValueError):
         PeerExchange(m, 0, _native.PEER_MAX_WORLD + 1, torch.device(DEV))
     lib.dualip_agd_destroy(r.agd)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("push", ["1", "0"])
+def test_sharded_evaluation_through_peer_memory_without_a_step(world, push, monkeypatch):
+    """dualip_matching_calc_peer: shard kernel + exchange + m-length tail in one launch, no optimizer step (the host-buffer
+    path of the sharded objective, reference matching.py:247-307).  Every rank obtains the same bits, and they equal the
+    unsharded evaluation up to the order of the shard sums; a second call reuses the other slot parity."""
+    monkeypatch.setenv("DUALIP_PEER_TIMEOUT_MS", "3000")
+    monkeypatch.setenv("DUALIP_PEER_PUSH", push)
+    lib = _native.lib()
+    p = random_problem(31, 5003, 200, 8.0, scale_c=10.0, lam_scale=0.5)
+    n, m, gamma = p["n_cols"], p["n_rows"], 2e-2
+    A, C = _csc(p)
+    b = torch.from_numpy(p["b"]).to(DEV)
+    pm = create_projection_map("simplex", {"z": 1.0}, n)
+    whole = MatchingSolverDualObjectiveFunction(MatchingInputArgs(A, C, pm, b), gamma)
+    a_s, c_s, index_map = split_tensors_to_devices(A, C, [DEV] * world)
+    objs = [MatchingSolverDualObjectiveFunction(MatchingInputArgs(a_s[k], c_s[k], global_to_local_projection_map(pm, index_map[k]), None), gamma)
+            for k in range(world)]
+    ex = [PeerExchange(m, k, world, torch.device(DEV)) for k in range(world)]
+    PeerExchange.connect_local(ex)
+    streams = [torch.cuda.Stream(device=DEV) for _ in range(world)]
+    grads = [torch.empty(m, device=DEV) for _ in range(world)]
+    scals = [torch.zeros(N_SCAL, dtype=torch.float64, device=DEV) for _ in range(world)]
+    rng = np.random.default_rng(0)
+    for call in range(3):
+        lam = torch.from_numpy((rng.random(m) * 0.5).astype(np.float32)).to(DEV)
+        torch.cuda.synchronize()
+        for k in range(world):
+            with torch.cuda.stream(streams[k]):
+                _native.check(lib.dualip_matching_calc_peer(objs[k]._plan, ex[k].handle, lam.data_ptr(), b.data_ptr(), gamma,
+                                                            grads[k].data_ptr(), scals[k].data_ptr(), streams[k].cuda_stream))
+        torch.cuda.synchronize()
+        assert [e.status() for e in ex] == [0] * world
+        ref = whole.calculate(lam)
+        for k in range(world):
+            assert torch.equal(grads[k], grads[0]) and torch.equal(scals[k], scals[0]), "ranks must obtain identical bits"
+        assert torch.allclose(grads[0], ref.dual_gradient, rtol=1e-5, atol=1e-5)
+        assert abs(float(scals[0][0]) - float(ref.scalars64[0])) <= 1e-6 * abs(float(ref.scalars64[0]))
+    for e in ex:
+        e.close()

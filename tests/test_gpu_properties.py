@@ -150,3 +150,39 @@ def test_tma_staged_slabs_are_bit_identical_to_plain_loads(big, monkeypatch, sta
         assert torch.equal(r1.primal_var, r0.primal_var)
         assert torch.equal(r1.dual_gradient, r0.dual_gradient)
         assert abs(float(r1.scalars64[0]) - float(r0.scalars64[0])) <= 1e-9 * abs(float(r0.scalars64[0]))
+
+
+def test_in_place_edits_after_construction_are_detected():
+    """The plan snapshots A's and c's values (the reference reads the tensors at every call, matching.py:136-142): an in-place
+    change after the objective was built -- an element-wise op, or jacobi_precondition called too late -- raises instead of
+    being silently ignored, through calculate() and through the Maximizer's raw launches."""
+    from conftest import random_problem
+    from dualip_b200.objectives.matching import MatchingInputArgs, MatchingSolverDualObjectiveFunction
+    from dualip_b200.optimizers.agd import AcceleratedGradientDescent, no_iteration_callback
+    from dualip_b200.preprocessing.precondition import jacobi_precondition
+    from dualip_b200.projections import create_projection_map
+
+    p = random_problem(9, 500, 32, 6.0)
+    n, m = p["ccol"].size - 1, 32
+    ccol, row = torch.from_numpy(p["ccol"]), torch.from_numpy(p["row"])
+
+    def build():
+        A = torch.sparse_csc_tensor(ccol, row, torch.from_numpy(p["a"]).clone(), size=(m, n)).to(DEV)
+        C = torch.sparse_csc_tensor(ccol, row, torch.from_numpy(p["c"]).clone(), size=(m, n)).to(DEV)
+        b = torch.from_numpy(p["b"]).to(DEV)
+        return A, C, b, MatchingSolverDualObjectiveFunction(MatchingInputArgs(A, C, create_projection_map("simplex", {"z": 1.0}, n), b), gamma=1e-2)
+
+    lam = torch.zeros(m, device=DEV)
+    A, C, b, obj = build()
+    obj.calculate(lam)
+    C.values().mul_(2.0)
+    with pytest.raises(RuntimeError, match="modified in place"):
+        obj.calculate(lam)
+    A, C, b, obj = build()
+    jacobi_precondition(A, b)
+    with pytest.raises(RuntimeError, match="modified in place"):
+        AcceleratedGradientDescent(max_iter=3, gamma=1e-2, iteration_callback=no_iteration_callback).maximize(obj, lam)
+    A, C, b, _ = build()
+    jacobi_precondition(A, b)  # preprocessing first, then the objective: fine
+    obj = MatchingSolverDualObjectiveFunction(MatchingInputArgs(A, C, create_projection_map("simplex", {"z": 1.0}, n), b), gamma=1e-2)
+    assert torch.isfinite(obj.calculate(lam).dual_objective)
