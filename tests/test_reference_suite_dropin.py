@@ -16,7 +16,10 @@ CASES = [
     ("test_agd.py", "", 2),        # AcceleratedGradientDescent on Python objectives, incl. the four known-answer trace values
     ("test_import.py", "", 1),
     ("test_equality_constraints.py", "test_project_on_nn_cone", 1),
-    ("preprocessing/test_input_validation.py", "", None),  # vectorised checks, same errors as the reference's per-column loop
+    ("preprocessing/test_input_validation.py", "", None),
+    # setup-time CSC helpers (index arithmetic, any device); the per-iteration operators of that module are CUDA kernels here and
+    # are covered by tests/test_gpu_operators.py with the same cases on device tensors
+    ("test_sparse_utils.py", "vstack or hstack or combined or right_multiply", 4),  # vectorised checks, same errors as the reference's per-column loop
 ]
 
 
