@@ -97,6 +97,34 @@ def main():
     lam = runs["peer"].dual_val.clone()
     gathered = all_gather(lam)
     assert all(torch.equal(g, gathered[0]) for g in gathered), "peer path: replicas must be bit-identical"
+    # 4) host-buffer evaluation of the sharded objective (lambda on the host): shard kernel + exchange through peer memory +
+    #    tail in one native call (dualip_matching_calc_peer_host) against the device-resident evaluation over NCCL
+    os.environ["DUALIP_PEER_EXCHANGE"] = "1"
+    local = MatchingInputArgs(a_s[rank].to(dev), c_s[rank].to(dev), global_to_local_projection_map(args.projection_map, index_map[rank]), None, None)
+    f = MatchingSolverDualObjectiveFunctionDistributed(local_matching_input_args=local, b_vec=args.b_vec, gamma=gamma, host_device=dev)
+    lam_host = runs["peer"].dual_val.cpu()
+    r_host = f.calculate(lam_host)
+    assert f._peer is not None and r_host.dual_gradient.device.type == "cpu"
+    r_dev = f.calculate(runs["peer"].dual_val)  # device tensors: partial kernel, all-reduce, epilogue kernel
+    assert torch.allclose(r_host.dual_gradient, r_dev.dual_gradient.cpu(), rtol=1e-5, atol=1e-5)
+    assert abs(float(r_host.dual_objective) - float(r_dev.dual_objective)) <= 1e-5 * abs(float(r_dev.dual_objective))
+    g_all = all_gather(r_host.dual_gradient.to(dev))
+    assert all(torch.equal(g, g_all[0]) for g in g_all), "host-buffer path: every rank must obtain the same bits"
+    host_run = AcceleratedGradientDescent(max_iter=12, gamma=gamma, initial_step_size=1e-3, max_step_size=0.1,
+                                          gamma_decay_type="step", gamma_decay_params={"decay_steps": 9, "decay_factor": 0.5},
+                                          iteration_callback=lambda i, r: None).maximize(f, torch.zeros(m), rank=rank)
+    assert np.allclose(host_run.dual_objective_log, runs["peer"].dual_objective_log[:12], rtol=1e-5)
+    # 5) sharded CUDA-graph replay: chunks of 8 iterations (exchange inside the captured launches) against single launches
+    os.environ["DUALIP_REBALANCE"] = "0"
+    outs = {}
+    for tag, graph in (("graph", "1"), ("single", "0")):
+        os.environ["DUALIP_GRAPH"], os.environ["DUALIP_GRAPH_CHUNK"] = graph, "8"
+        local = MatchingInputArgs(a_s[rank].to(dev), c_s[rank].to(dev), global_to_local_projection_map(args.projection_map, index_map[rank]), None, None)
+        f = MatchingSolverDualObjectiveFunctionDistributed(local_matching_input_args=local, b_vec=args.b_vec, gamma=gamma, host_device=dev)
+        outs[tag] = AcceleratedGradientDescent(max_iter=37, gamma=gamma, initial_step_size=1e-3, max_step_size=0.1,
+                                               gamma_decay_type="step", gamma_decay_params={"decay_steps": 9, "decay_factor": 0.5},
+                                               iteration_callback=no_iteration_callback).maximize(f, torch.zeros(m, device=dev), rank=rank)
+    assert outs["graph"].dual_objective_log == outs["single"].dual_objective_log and torch.equal(outs["graph"].dual_val, outs["single"].dual_val)
     dist.barrier()
     if rank == 0:
         print("DIST_WORKER_OK", world)
