@@ -112,6 +112,8 @@ SIGNATURES = {
     "dualip_agd_host_x": (C.c_void_p, [C.c_void_p]),
     "dualip_agd_host_y": (C.c_void_p, [C.c_void_p]),
     "dualip_agd_host_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_double, C.POINTER(C.c_double)]),
+    "dualip_matching_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_float, C.c_int32, C.c_double,
+                                            C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "dualip_agd_read_log": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dualip_agd_reserve_log": (C.c_int, [C.c_void_p, C.c_int32]),
     "dualip_row_sq_norms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,

@@ -2874,6 +2874,20 @@ int dualip_matching_calc_peer_host(dualip_plan* p, dualip_peer* peer, const floa
   return DUALIP_OK;
 }
 
+int dualip_matching_step_host(dualip_plan* p, dualip_peer* peer, dualip_agd_host* agd, const float* b_dev, double gamma, float beta,
+                              int32_t decay_now, double decay_factor, float* grad_out_host, dualip_scalars* scalars_out_host,
+                              double* step_out, void* stream) {
+  if (!p || !agd || !grad_out_host || !scalars_out_host) {
+    set_error("null argument");
+    return DUALIP_EINVAL;
+  }
+  const float* x_host = dualip_agd_host_x(agd);  // the evaluation point (pinned when a CUDA device is present)
+  int rc = peer ? dualip_matching_calc_peer_host(p, peer, x_host, b_dev, gamma, grad_out_host, scalars_out_host, stream)
+                : dualip_matching_calc_host(p, x_host, b_dev, gamma, grad_out_host, scalars_out_host, stream);
+  if (rc != DUALIP_OK) return rc;
+  return dualip_agd_host_step(agd, grad_out_host, beta, decay_now, decay_factor, step_out);
+}
+
 int dualip_matching_epilogue(const float* partial_sum_dev, int32_t m, const float* lambda_dev, const float* b_dev,
                              double gamma, float* grad_out_dev, dualip_scalars* scalars_out_dev, void* stream) {
   if (!partial_sum_dev || !lambda_dev || !grad_out_dev || !scalars_out_dev || m <= 0) {

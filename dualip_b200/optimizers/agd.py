@@ -200,6 +200,9 @@ class AcceleratedGradientDescent:
             dual_obj_log, step_size_log = [], []
             step = ctypes.c_double(0.0)
             dual_obj, objective_result = 0.0, None
+            fast = self._native_host_target(f)
+            if fast is not None and not (self.save_primal and self.max_iter >= 1):
+                return self._maximize_host_fused(f, fast, lib, handle, x, y, beta, decay, rank)
             for i in range(1, self.max_iter + 1):
                 kwargs = {"gamma": self.gamma} if self.gamma is not None else {}
                 if i == self.max_iter and self.save_primal:
@@ -227,6 +230,76 @@ class AcceleratedGradientDescent:
                                 dual_objective_log=dual_obj_log, step_size_log=step_size_log)
         finally:
             lib.dualip_agd_host_destroy(handle)
+
+    @staticmethod
+    def _native_host_target(f):
+        """(plan, peer handle or None, b_vec, local objective) when a whole host-buffer iteration can be ONE native call
+        (dualip_matching_step_host): a matching objective whose columns are all projected natively, on one GPU or sharded with
+        the peer-memory exchange.  COLLECTIVE for sharded objectives (the windows are set up on first use)."""
+        from dualip_b200.objectives.matching import (
+            MatchingSolverDualObjectiveFunction,
+            MatchingSolverDualObjectiveFunctionDistributed,
+        )
+
+        if os.environ.get("DUALIP_HOST_FUSED", "1") == "0":
+            return None
+        if isinstance(f, MatchingSolverDualObjectiveFunctionDistributed):
+            local = f.local_objective
+            if local.has_block_entries:
+                return None
+            peer = f.peer_exchange()
+            return None if peer is None else (local._plan, peer.handle, f.b_vec, local)
+        if type(f) is MatchingSolverDualObjectiveFunction and not f.is_distributed and not f.has_block_entries:
+            return (f._plan, None, f.b_vec, f)
+        return None
+
+    def _maximize_host_fused(self, f, target, lib, handle, x, y, beta, decay, rank) -> SolverResult:
+        """Host-buffer loop with one native call per iteration: lambda host->device, fused kernel (sharded: + exchange through
+        peer memory), gradient + scalars device->host, host-side accelerated step.  A callback still sees every iteration's
+        result (fresh tensors); without one no Python object is built per iteration."""
+        import numpy as np
+
+        plan, peer, b_vec, local = target
+        m = x.numel()
+        h_grad = torch.empty(m, dtype=torch.float32).pin_memory()
+        h_scal = torch.empty(len(_native.SCALAR_FIELDS), dtype=torch.float64).pin_memory()
+        scal_np = h_scal.numpy()
+        local.check_inputs_unchanged()
+        callback = rank == 0 and self._user_callback_active()
+        dual_obj_log, step_size_log = [], []
+        step = ctypes.c_double(0.0)
+        b_ptr = b_vec.data_ptr() if b_vec is not None else None
+
+        def result():
+            from dualip_b200.objectives.matching import _host_result
+
+            return _host_result(h_grad.clone(), h_scal.clone(), False)
+
+        objective_result = None
+        with torch.cuda.device(local.device):
+            stream = torch.cuda.current_stream(local.device).cuda_stream
+            for i in range(1, self.max_iter + 1):
+                gamma_i = self.gamma if self.gamma is not None else f.gamma
+                decay_now, factor = 0, 1.0
+                if decay and i % self.gamma_decay_params["decay_steps"] == 0:
+                    decay_now, factor = 1, float(self.gamma_decay_params["decay_factor"])
+                _native.check(lib.dualip_matching_step_host(plan, peer, handle, b_ptr, float(gamma_i), float(beta[i - 1]), decay_now, factor,
+                                                            h_grad.data_ptr(), h_scal.data_ptr(), ctypes.byref(step), stream),
+                              "dualip_matching_step_host")
+                local.launched()
+                dual_obj_log.append(float(scal_np[_IDX["dual_objective"]]))
+                step_size_log.append(step.value)
+                if callback:
+                    objective_result = result()
+                    self.iteration_callback(i, objective_result)
+                if decay_now:  # agd.py:102-109
+                    self.gamma = self.gamma * factor
+                    self.max_step_size = step.value * factor
+                    f.gamma = self.gamma
+        if objective_result is None or not callback:
+            objective_result = result() if self.max_iter >= 1 else None
+        return SolverResult(dual_val=y.clone(), dual_objective=dual_obj_log[-1] if dual_obj_log else 0.0, objective_result=objective_result,
+                            dual_objective_log=dual_obj_log, step_size_log=step_size_log)
 
     def _maximize_host_torch(self, f, initial_value: torch.Tensor, rank: int) -> SolverResult:
         """The reference's loop op for op (any device / dtype; rank-0 update + broadcasts for reference-style objectives)."""

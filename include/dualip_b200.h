@@ -308,6 +308,14 @@ float* dualip_agd_host_y(dualip_agd_host* agd);
 int dualip_agd_host_step(dualip_agd_host* agd, const float* grad_host, float beta, int32_t decay_now, double decay_factor,
                          double* step_out);
 
+/* One whole iteration for a dual iterate kept in host memory: the evaluation point of `agd` goes host->device, the dual is
+ * evaluated there (peer != NULL: sharded, sums exchanged through peer memory), gradient and scalars come back into the
+ * caller's (pinned) buffers, the stream is synchronised and the host state takes the accelerated step.  Replaces one turn of
+ * AcceleratedGradientDescent.maximize with CPU tensors (optimizers/agd.py:150-206) by ONE native call. */
+int dualip_matching_step_host(dualip_plan* plan, dualip_peer* peer, dualip_agd_host* agd, const float* b_dev, double gamma,
+                              float beta, int32_t decay_now, double decay_factor, float* grad_out_host,
+                              dualip_scalars* scalars_out_host, double* step_out, void* stream);
+
 /* Copies log entries [0,count) to host: dual_objective and step size per iteration. Synchronises. */
 int dualip_agd_read_log(dualip_agd* agd, int32_t count, double* dual_obj_host, double* step_host, void* stream);
 int dualip_agd_reserve_log(dualip_agd* agd, int32_t capacity);

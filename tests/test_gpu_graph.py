@@ -167,3 +167,33 @@ def test_row_equilibration_keeps_x_and_restores_the_fixed_point_accumulator(monk
     assert torch.equal(r1.dual_gradient, r2.dual_gradient)
     assert torch.allclose(r0.dual_gradient, r1.dual_gradient, rtol=2e-5, atol=1e-6)
     assert abs(float(r1.scalars64[0]) - ref.dual_objective) <= 1e-5 * abs(ref.dual_objective)
+
+
+@pytest.mark.parametrize("decay", [False, True])
+def test_host_buffer_loop_one_native_call_per_iteration(monkeypatch, decay):
+    """maximize() with a host-resident dual: dualip_matching_step_host (lambda up, fused kernel, gradient + scalars down, host
+    step: one call) against the loop that goes through calculate() and dualip_agd_host_step separately.  Same kernels, same
+    host arithmetic: identical iterates and step sizes; callbacks see every iteration's result as fresh tensors."""
+    monkeypatch.setenv("DUALIP_REBALANCE", "0")
+    p = random_problem(13, 5000, 80, 8.0)
+    n = p["ccol"].size - 1
+    kw = dict(max_iter=30, gamma=2e-2, initial_step_size=1e-3, max_step_size=0.1)
+    if decay:
+        kw.update(gamma_decay_type="step", gamma_decay_params={"decay_steps": 7, "decay_factor": 0.7})
+    lam0 = torch.zeros(80)
+    seen = {"0": [], "1": []}
+    outs = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("DUALIP_HOST_FUSED", fused)
+        cb = (lambda i, r, key=fused: seen[key].append((i, float(r.dual_objective), r.dual_gradient)))
+        outs[fused] = AcceleratedGradientDescent(iteration_callback=cb, **kw).maximize(_objective(p, _mixed_map(n), 2e-2), lam0)
+    a, b = outs["0"], outs["1"]
+    assert torch.equal(a.dual_val, b.dual_val) and a.step_size_log == b.step_size_log
+    assert np.allclose(a.dual_objective_log, b.dual_objective_log, rtol=1e-7)  # float32-rounded vs double log entries
+    assert len(seen["1"]) == 30 and [i for i, _, _ in seen["1"]] == list(range(1, 31))
+    for (_, o0, g0), (_, o1, g1) in zip(seen["0"], seen["1"]):
+        assert abs(o0 - o1) <= 1e-6 * abs(o0) and torch.equal(g0, g1)
+    assert len({g.data_ptr() for _, _, g in seen["1"]}) == 30, "callback results must not alias the loop's buffers"
+    assert b.dual_val.device.type == "cpu" and b.objective_result.dual_gradient.device.type == "cpu"
+    quiet = AcceleratedGradientDescent(iteration_callback=no_iteration_callback, **kw).maximize(_objective(p, _mixed_map(n), 2e-2), lam0)
+    assert torch.equal(quiet.dual_val, b.dual_val) and quiet.objective_result is not None
