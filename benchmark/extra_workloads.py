@@ -40,7 +40,8 @@ def run_c1(args, B):
     shard, b = generate_movielens_shaped(n, m, B.SEED, dev)
     A = torch.sparse_csc_tensor(shard.ccol, shard.row, shard.a, size=(m, n))
     C = torch.sparse_csc_tensor(shard.ccol, shard.row, shard.c, size=(m, n))
-    pm = create_projection_map("simplex", {"z": 1}, n)
+    proj = os.environ.get("DUALIP_C1_PROJ", "simplex")  # the example's own map is simplex z=1 (:163); BASELINE.json words it as box
+    pm = create_projection_map("simplex", {"z": 1}, n) if proj == "simplex" else create_projection_map("box", {"lower": 0.0, "upper": 1.0}, n)
     torch.cuda.synchronize()
     t_gen = time.time() - t0
     t0 = time.time()
@@ -94,13 +95,13 @@ def run_c1(args, B):
     # the unmodified reference on the same problem, CPU
     cpu = None
     if not args.no_cpu:
-        cpu = _reference_cpu_matching(shard, b, m, n, gamma, B, batching=True)
+        cpu = _reference_cpu_matching(shard, b, m, n, gamma, B, batching=True, proj=proj)
     it_s = K / (ms_total * 1e-3)
     line = {
         "metric": "dual-ascent iterations/sec", "value": it_s, "unit": "iterations/s", "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"MovieLens-shaped matching LP (configs[0]): {n} users x {m} movies, a=1, c=-rating, simplex z=1, "
+        "config": {"workload": f"MovieLens-shaped matching LP (configs[0]): {n} users x {m} movies, a=1, c=-rating, {'simplex z=1' if proj == 'simplex' else 'box [0,1]'}, "
                                f"gamma={gamma}; ratings drawn (ml-20m is not available offline)",
                    "workload_id": "c1", "entities": n, "duals": m, "nnz": info["nnz"], "parallelism": "single GPU",
                    "column_lengths": {"min": int(lens.min()), "mean": float(lens.float().mean()), "max": int(lens.max())},
@@ -122,7 +123,7 @@ def run_c1(args, B):
     print(json.dumps(line), flush=True)
 
 
-def _reference_cpu_matching(shard, b, m, n, gamma, B, batching, steps=4, warm=1):
+def _reference_cpu_matching(shard, b, m, n, gamma, B, batching, steps=4, warm=1, proj="simplex"):
     import torch
 
     from benchmark import reference_arm as R
@@ -140,7 +141,8 @@ def _reference_cpu_matching(shard, b, m, n, gamma, B, batching, steps=4, warm=1)
     ccol, row = shard.ccol.cpu(), shard.row.cpu()
     A = torch.sparse_csc_tensor(ccol, row, shard.a.cpu(), size=(m, n))
     C = torch.sparse_csc_tensor(ccol, row, shard.c.cpu(), size=(m, n))
-    args = MatchingInputArgs(A=A, c=C, projection_map=create_projection_map("simplex", {"z": 1}, n), b_vec=b.cpu(), equality_mask=None)
+    pm = create_projection_map("simplex", {"z": 1}, n) if proj == "simplex" else create_projection_map("box", {"lower": 0.0, "upper": 1.0}, n)
+    args = MatchingInputArgs(A=A, c=C, projection_map=pm, b_vec=b.cpu(), equality_mask=None)
     objective = MatchingSolverDualObjectiveFunction(matching_input_args=args, gamma=gamma, batching=batching)
     marks = {}
 

@@ -140,6 +140,8 @@ struct dualip_plan {
   int64_t n_long = 0;
   int64_t n_mid = 0;
   int64_t n_ctalong = 0;          // of the long columns, those that fit the CTA-per-column kernel's stash: [n_mid, n_mid + n_ctalong)
+  bool mid_separate = false;      // many mid columns: they take the team-per-column kernel (32 threads per column, 40 warps per SM)
+                                  // in front of the slab kernel instead of the slab kernel's own warp-per-column path
   int* mid_range = nullptr;       // n_ctas + 1: every CTA's contiguous share of the mid columns (equal cost)
   int64_t long_total = 0;         // entries of all long columns
   float* long_a = nullptr;
@@ -1696,7 +1698,7 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.long_a = p->long_a;
   k.long_c = p->long_c;
   k.long_row = p->long_row;
-  k.mid_cols = p->n_mid > 0 ? p->longcols : nullptr;
+  k.mid_cols = (p->n_mid > 0 && !p->mid_separate) ? p->longcols : nullptr;
   k.mid_range = p->mid_range;
   k.fuse = fuse ? fuse->mode : 0;
   if (fuse) {
@@ -1708,13 +1710,21 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
     memset(&k.peer, 0, sizeof(k.peer));
     memset(&k.sched, 0, sizeof(k.sched));
   }
+  if (p->n_mid > 0 && p->mid_separate) {  // many mid columns: 32 threads per column, u in a 4 KB shared-memory stash per team
+    const int team_bytes = (kLongThreads / 32) * kTeamStash * (int)sizeof(float);
+    const int blocks = (int)std::min<int64_t>((p->n_mid + 7) / 8, (int64_t)p->n_sms * 5);
+    if (p->fixed_point)
+      matching_long_cta_kernel<1, 32><<<blocks, kLongThreads, team_bytes, stream>>>(k, p->longcols, (int)p->n_mid);
+    else
+      matching_long_cta_kernel<0, 32><<<blocks, kLongThreads, team_bytes, stream>>>(k, p->longcols, (int)p->n_mid);
+  }
   if (p->n_ctalong > 0) {  // 1025 .. kLongStash entries: a CTA per column, u in shared memory
     const int stash_bytes = kLongStash * (int)sizeof(float);  // the attribute was raised at plan creation (per device)
     const int blocks = (int)std::min<int64_t>(p->n_ctalong, (int64_t)p->n_sms * 4);
     if (p->fixed_point)
-      matching_long_cta_kernel<1><<<blocks, kLongThreads, stash_bytes, stream>>>(k, p->longcols + p->n_mid, (int)p->n_ctalong);
+      matching_long_cta_kernel<1, kLongThreads><<<blocks, kLongThreads, stash_bytes, stream>>>(k, p->longcols + p->n_mid, (int)p->n_ctalong);
     else
-      matching_long_cta_kernel<0><<<blocks, kLongThreads, stash_bytes, stream>>>(k, p->longcols + p->n_mid, (int)p->n_ctalong);
+      matching_long_cta_kernel<0, kLongThreads><<<blocks, kLongThreads, stash_bytes, stream>>>(k, p->longcols + p->n_mid, (int)p->n_ctalong);
   }
   if (p->n_long > p->n_mid + p->n_ctalong) {  // longer still: warp per column, re-streamed
     const int64_t nl = p->n_long - p->n_mid - p->n_ctalong;
@@ -1958,6 +1968,12 @@ static int build_slabs(dualip_plan* p, const dualip_csc_desc* d, cudaStream_t st
         return DUALIP_ERANGE;
       }
     }
+    {
+      // few mid columns (the tail of a short-column problem): inside the slab kernel, sharing lambda and the accumulator in
+      // shared memory; many (ratings-like data): their own launch at 2.5x the occupancy.  DUALIP_MID_KERNEL=0|1 forces it.
+      const char* env_mk = getenv("DUALIP_MID_KERNEL");
+      p->mid_separate = env_mk ? atoi(env_mk) != 0 : p->n_mid > (int64_t)4 * p->n_sms * (p->threads / 32);
+    }
     BS_TRY(cudaMemcpyAsync(p->longcols, lc.data(), sizeof(LongCol) * n_long, cudaMemcpyHostToDevice, stream));
     p->long_total = tot;
     BS_TRY(cudaMalloc(&p->long_a, sizeof(float) * tot));
@@ -2075,7 +2091,7 @@ static int build_cta_ranges(dualip_plan* p) {
 // Every CTA's contiguous share of the (length-sorted) mid columns, cut to equal cost: a column costs its length plus a fixed
 // part (two warp-wide passes over its registers per search round, the reductions, the column header).
 static int build_mid_ranges(dualip_plan* p) {
-  if (p->n_mid <= 0) return DUALIP_OK;
+  if (p->n_mid <= 0 || p->mid_separate) return DUALIP_OK;
   std::vector<LongCol> lc((size_t)p->n_mid);
   if (cudaMemcpy(lc.data(), p->longcols, sizeof(LongCol) * lc.size(), cudaMemcpyDeviceToHost) != cudaSuccess) {
     set_error("reading the mid-column table failed");
@@ -2155,17 +2171,20 @@ static int choose_accumulator(dualip_plan* p, cudaStream_t stream, int keep_bits
   CA_TRY(cudaMemsetAsync(table, 0, sizeof(float) * tab, stream));
   CA_TRY(cudaMemsetAsync(long_bound, 0, sizeof(float) * m, stream));
   CA_TRY(cudaMemsetAsync(row_cnt, 0, sizeof(unsigned int) * m, stream));
-  if (p->n_slabs > 0 || p->n_mid > 0) {
+  if (p->n_slabs > 0 || (p->n_mid > 0 && !p->mid_separate)) {
     const size_t bsm = 8 * (size_t)m;  // fits: mode 0 already keeps 8*m bytes of lambda + accumulator in shared memory
     CA_TRY(cudaFuncSetAttribute((const void*)cta_row_bound_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
     cta_row_bound_kernel<unsigned short><<<p->n_ctas, p->threads, bsm, stream>>>(
-        p->data, p->hdr, p->cta_range, p->n_slabs, xmax_d, m, table, row_cnt, p->n_mid > 0 ? p->longcols : nullptr, p->mid_range,
-        p->long_a, p->long_row);
+        p->data, p->hdr, p->cta_range, p->n_slabs, xmax_d, m, table, row_cnt,
+        (p->n_mid > 0 && !p->mid_separate) ? p->longcols : nullptr, p->mid_range, p->long_a, p->long_row);
   }
-  if (p->n_long > p->n_mid) {
-    const int64_t nl = p->n_long - p->n_mid;
-    const int blocks = (int)std::min<int64_t>((nl + 7) / 8, (int64_t)p->n_sms * 8);
-    long_row_bound_kernel<<<blocks, 256, 0, stream>>>(p->longcols + p->n_mid, nl, p->long_a, p->long_row, xmax_d, long_bound, row_cnt);
+  {
+    // columns whose sums go straight to the global accumulators: the long ones, and the mid ones when they have their own launch
+    const int64_t first = p->mid_separate ? 0 : p->n_mid, nl = p->n_long - first;
+    if (nl > 0) {
+      const int blocks = (int)std::min<int64_t>((nl + 7) / 8, (int64_t)p->n_sms * 8);
+      long_row_bound_kernel<<<blocks, 256, 0, stream>>>(p->longcols + first, nl, p->long_a, p->long_row, xmax_d, long_bound, row_cnt);
+    }
   }
   bound_reduce_kernel<<<(m + 255) / 256, 256, 0, stream>>>(table, p->n_ctas, m, row_max, row_sum);
   std::vector<float> h_max(m), h_sum(m), h_long(m);
@@ -2449,7 +2468,7 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   {
     const int64_t warps_per_cta = p->threads / 32;
     const int64_t want = std::max<int64_t>(1, std::max((p->n_slabs + warps_per_cta - 1) / warps_per_cta,
-                                                       (p->n_mid + warps_per_cta - 1) / warps_per_cta));
+                                                       ((p->mid_separate ? 0 : p->n_mid) + warps_per_cta - 1) / warps_per_cta));
     if (!(env_ctas && atoi(env_ctas) > 0) && want < p->n_ctas) p->n_ctas = (int)want;
   }
   {
@@ -2507,9 +2526,9 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
     DUALIP_TRY_FAIL(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   }
   if (p->n_ctalong > 0) {
-    DUALIP_TRY_FAIL(cudaFuncSetAttribute((const void*)matching_long_cta_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DUALIP_TRY_FAIL(cudaFuncSetAttribute((const void*)matching_long_cta_kernel<0, kLongThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kLongStash * (int)sizeof(float)));
-    DUALIP_TRY_FAIL(cudaFuncSetAttribute((const void*)matching_long_cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DUALIP_TRY_FAIL(cudaFuncSetAttribute((const void*)matching_long_cta_kernel<1, kLongThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kLongStash * (int)sizeof(float)));
   }
   DUALIP_TRY_FAIL(cudaDeviceSynchronize());
@@ -2612,7 +2631,7 @@ int dualip_plan_info(const dualip_plan* p, int64_t* out, int cap) {
     return DUALIP_EINVAL;
   }
   const int64_t v[18] = {p->n_slabs, p->n_long - p->n_mid, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
-                         p->smode,   p->rows32 * kSlabW, 1 + (p->n_ctalong > 0 ? 1 : 0) + (p->n_long > p->n_mid + p->n_ctalong ? 1 : 0), (int64_t)p->owned_bytes, p->n_short, p->nnz,
+                         p->smode,   p->rows32 * kSlabW, 1 + (p->n_ctalong > 0 ? 1 : 0) + (p->n_long > p->n_mid + p->n_ctalong ? 1 : 0) + ((p->mid_separate && p->n_mid > 0) ? 1 : 0), (int64_t)p->owned_bytes, p->n_short, p->nnz,
                          p->fixed_point, p->fx_bits, (int64_t)(p->fx_relerr * 1e12), p->stage, p->row_unscale ? 1 : 0, p->n_mid};
   for (int i = 0; i < cap && i < 18; ++i) out[i] = v[i];
   return DUALIP_OK;

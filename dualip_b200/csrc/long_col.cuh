@@ -14,6 +14,11 @@ namespace dualip {
 
 constexpr int kLongThreads = 256;
 constexpr int kLongStash = 12288;  // floats of u per CTA (48 KB: four CTAs per SM); longer columns keep the warp-per-column kernel
+// The same kernel with a TEAM of 32 threads per column (eight columns per CTA, 4 KB of stash each): mid columns (up to
+// kMaxThreadDeg entries) of plans that hold MANY of them.  Inside the slab kernel such columns are a chain of dependent
+// reductions at 16 warps per SM (128 registers per thread); here nothing but a few scalars lives in registers, so 40 warps per
+// SM keep two and a half times as many columns in flight.
+constexpr int kTeamStash = 1024;   // floats of u per 32-thread team
 
 struct LongRed {  // one block-wide reduction round
   double s;
@@ -21,14 +26,17 @@ struct LongRed {  // one block-wide reduction round
   float mn, mx;
 };
 
-// All threads obtain the block-wide {sum s, sum c, min mn, max mx}.  `scratch` holds 2 x 8 entries; consecutive calls alternate
-// between the halves, so one barrier per call suffices (a thread cannot be two calls ahead of another).
-__device__ __forceinline__ LongRed long_block_reduce(LongRed v, LongRed* scratch, int& phase) {
+// All threads of a team obtain the team-wide {sum s, sum c, min mn, max mx}.  TEAM == 32: warp shuffles only.  TEAM ==
+// kLongThreads: `scratch` holds 2 x 8 entries; consecutive calls alternate between the halves, so one barrier per call
+// suffices (a thread cannot be two calls ahead of another).
+template <int TEAM>
+__device__ __forceinline__ LongRed long_team_reduce(LongRed v, LongRed* scratch, int& phase) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   v.s = warp_sum(v.s);
   v.c = __reduce_add_sync(0xffffffffu, v.c);
   v.mn = warp_min_f(v.mn);
   v.mx = warp_max(v.mx);
+  if (TEAM == 32) return v;
   LongRed* buf = scratch + phase * (kLongThreads / 32);
   if (lane == 0) buf[warp] = v;
   __syncthreads();
@@ -43,18 +51,29 @@ __device__ __forceinline__ LongRed long_block_reduce(LongRed v, LongRed* scratch
   phase ^= 1;
   return r;
 }
+template <int TEAM>
+__device__ __forceinline__ void team_sync() {
+  if (TEAM == 32)
+    __syncwarp();
+  else
+    __syncthreads();
+}
 
-template <int ACC>
-__global__ void __launch_bounds__(kLongThreads) matching_long_cta_kernel(const KArgs k, const LongCol* __restrict__ cols, int n_cols) {
+template <int ACC, int TEAM>
+__global__ void __launch_bounds__(kLongThreads, TEAM == 32 ? 5 : 1) matching_long_cta_kernel(const KArgs k, const LongCol* __restrict__ cols,
+                                                                                          int n_cols) {
   extern __shared__ __align__(16) unsigned char long_smem[];
-  float* s_u = reinterpret_cast<float*>(long_smem);  // kLongStash floats
+  constexpr int kTeams = kLongThreads / TEAM;  // columns in flight per CTA
+  // the team's stash: kLongStash floats for a whole-CTA team, kTeamStash per 32-thread team
+  float* s_u = reinterpret_cast<float*>(long_smem) + (TEAM == 32 ? (threadIdx.x / TEAM) * kTeamStash : 0);
   __shared__ LongRed s_red[2 * (kLongThreads / 32)];
   __shared__ float s_m1[kLongThreads / 32], s_m2[kLongThreads / 32];
   __shared__ int s_am[kLongThreads / 32];
   __shared__ float s_seq;
   __shared__ double s_scal[32];
   const unsigned FULL = 0xffffffffu;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x % TEAM;  // position inside the team
   int phase = 0;
   float s_run = k.s;
   if (k.sched.gamma != nullptr) {  // scheduled launch: see matching_slab_kernel
@@ -83,7 +102,7 @@ __global__ void __launch_bounds__(kLongThreads) matching_long_cta_kernel(const K
     xx = fma((double)x, (double)x, xx);
   };
 
-  for (int ci = blockIdx.x; ci < n_cols; ci += gridDim.x) {
+  for (int ci = blockIdx.x * kTeams + threadIdx.x / TEAM; ci < n_cols; ci += gridDim.x * kTeams) {
     const LongCol lc = cols[ci];
     const dualip_proj_class pc = k.classes[lc.cls];
     const int len = lc.len;
@@ -92,7 +111,7 @@ __global__ void __launch_bounds__(kLongThreads) matching_long_cta_kernel(const K
     const uint32_t* __restrict__ pr = k.long_row + lc.off;
     if (pc.kind == DUALIP_PROJ_CLAMP) {
 #pragma unroll 4
-      for (int e = tid; e < len; e += kLongThreads) {
+      for (int e = tid; e < len; e += TEAM) {
         const float a = __ldg(pa + e), c = __ldg(pcv + e);
         const uint32_t r = __ldg(pr + e);
         const float x = fminf(fmaxf(make_v(a, lam_of(r), s, c), pc.lo), pc.hi);
@@ -102,13 +121,13 @@ __global__ void __launch_bounds__(kLongThreads) matching_long_cta_kernel(const K
       continue;
     }
     // ---- simplex / simplex_eq: u into the stash; column sum, the two largest values and the position of the largest ----
-    __syncthreads();  // the previous column's stash is no longer read
+    team_sync<TEAM>();  // the previous column's stash is no longer read
     const float z = pc.z;
     double Sd = 0.0;
     float m1 = -1.f, m2 = -1.f;
     int am = 0x7fffffff;
 #pragma unroll 4
-    for (int e = tid; e < len; e += kLongThreads) {
+    for (int e = tid; e < len; e += TEAM) {
       const float a = __ldg(pa + e), c = __ldg(pcv + e);
       const uint32_t r = __ldg(pr + e);
       const float u = fmaxf(make_v(a, lam_of(r), s, c), 0.f);  // simplex.py:148
@@ -127,18 +146,22 @@ __global__ void __launch_bounds__(kLongThreads) matching_long_cta_kernel(const K
       m1 = fmaxf(m1, o1);
       m2 = fmaxf(fmaxf(m2, o2), mn);
     }
-    if (lane == 0) s_m1[warp] = m1, s_m2[warp] = m2, s_am[warp] = am;
-    LongRed r0 = long_block_reduce(LongRed{Sd, 0, 0.f, 0.f}, s_red, phase);  // its barrier also publishes s_m1 / s_m2 / s_am and s_u
+    if (TEAM != 32 && lane == 0) s_m1[warp] = m1, s_m2[warp] = m2, s_am[warp] = am;
+    LongRed r0 = long_team_reduce<TEAM>(LongRed{Sd, 0, 0.f, 0.f}, s_red, phase);  // its barrier also publishes s_m1 / s_m2 / s_am and s_u
     Sd = r0.s;
-    m1 = s_m1[0], m2 = s_m2[0], am = s_am[0];
+    if (TEAM == 32) {
+      __syncwarp();  // the team's stash is complete
+    } else {
+      m1 = s_m1[0], m2 = s_m2[0], am = s_am[0];
 #pragma unroll
-    for (int w = 1; w < kLongThreads / 32; ++w) {
-      const float o1 = s_m1[w], o2 = s_m2[w];
-      const int oa = s_am[w];
-      const float mn = fminf(m1, o1);
-      if (o1 > m1 || (o1 == m1 && oa < am)) am = oa;
-      m1 = fmaxf(m1, o1);
-      m2 = fmaxf(fmaxf(m2, o2), mn);
+      for (int w = 1; w < kLongThreads / 32; ++w) {
+        const float o1 = s_m1[w], o2 = s_m2[w];
+        const int oa = s_am[w];
+        const float mn = fminf(m1, o1);
+        if (o1 > m1 || (o1 == m1 && oa < am)) am = oa;
+        m1 = fmaxf(m1, o1);
+        m2 = fmaxf(fmaxf(m2, o2), mn);
+      }
     }
     // feasibility (simplex.py:153-155): the reference compares its fp32 entry-order sum; away from the threshold (further than
     // the worst rounding error of such a sum) the fp64 sum decides, inside the band one thread forms the sequential sum
@@ -148,13 +171,19 @@ __global__ void __launch_bounds__(kLongThreads) matching_long_cta_kernel(const K
       if (fabs(Sd - thr) > 2.2 * (double)len * 5.97e-8 * fmax(Sd, thr)) {
         feasible = Sd <= thr;
       } else {
-        if (tid == 0) {
+        if (TEAM == 32) {  // every lane forms the same sequential sum from the stash (broadcast reads)
           float S = 0.f;
           for (int e = 0; e < len; ++e) S = __fadd_rn(S, s_u[e]);
-          s_seq = S;
+          feasible = S <= pc.z_thr;
+        } else {
+          if (tid == 0) {
+            float S = 0.f;
+            for (int e = 0; e < len; ++e) S = __fadd_rn(S, s_u[e]);
+            s_seq = S;
+          }
+          __syncthreads();
+          feasible = s_seq <= pc.z_thr;
         }
-        __syncthreads();
-        feasible = s_seq <= pc.z_thr;
       }
     }
     const float m2p = fmaxf(m2, 0.f);
@@ -180,14 +209,14 @@ __global__ void __launch_bounds__(kLongThreads) matching_long_cta_kernel(const K
       int cnt = 0;
       for (int it = 0; it < 64; ++it) {
         LongRed v{0.0, 0, INFINITY, -INFINITY};
-        for (int e = tid; e < len; e += kLongThreads) {
+        for (int e = tid; e < len; e += TEAM) {
           const float u = s_u[e];
           const bool in = u > tf;
           v.c += in ? 1 : 0;
           v.s += in ? (double)u : 0.0;
           v.mn = in ? fminf(v.mn, u) : v.mn;
         }
-        v = long_block_reduce(v, s_red, phase);
+        v = long_team_reduce<TEAM>(v, s_red, phase);
         cnt = v.c;
         if (v.c == 0) break;
         const float tn = __double2float_rd((v.s - (double)z) / (double)v.c);
@@ -198,7 +227,7 @@ __global__ void __launch_bounds__(kLongThreads) matching_long_cta_kernel(const K
       float th = 0.f;
       for (int fix = 0; fix < 64; ++fix) {
         LongRed v{0.0, 0, INFINITY, -INFINITY};
-        for (int e = tid; e < len; e += kLongThreads) {
+        for (int e = tid; e < len; e += TEAM) {
           const float u = s_u[e];
           const bool in = u > tf;
           v.c += in ? 1 : 0;
@@ -206,7 +235,7 @@ __global__ void __launch_bounds__(kLongThreads) matching_long_cta_kernel(const K
           v.mn = in ? fminf(v.mn, u) : v.mn;
           v.mx = in ? v.mx : fmaxf(v.mx, u);
         }
-        v = long_block_reduce(v, s_red, phase);
+        v = long_team_reduce<TEAM>(v, s_red, phase);
         cnt = v.c;
         th = __fdiv_rn(__fsub_rn((float)v.s, z), (float)max(v.c, 1));
         bool changed = false;
@@ -226,7 +255,7 @@ __global__ void __launch_bounds__(kLongThreads) matching_long_cta_kernel(const K
       rho = max(cnt, 1);
     }
     // ---- x and the scatter: a, c and the row id are read again only where x != 0 ----
-    for (int e = tid; e < len; e += kLongThreads) {
+    for (int e = tid; e < len; e += TEAM) {
       const float u = s_u[e];
       const float x = branch == 0 ? u : (branch == 1 ? (e == am ? z : 0.f) : fmaxf(__fsub_rn(u, theta), 0.f));
       if (x != 0.f) scatter(__ldg(pa + e), __ldg(pcv + e), __ldg(pr + e), x);

@@ -153,3 +153,30 @@ def test_long_columns_cta_per_column_kernel_against_the_oracle(monkeypatch, whic
     assert old.plan_info()["launches_per_calc"] == 2
     r_old = old.calculate(lam, save_primal=True)
     assert torch.allclose(r_old.primal_var, r.primal_var, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("which", ["simplex", "mixed"])
+@pytest.mark.parametrize("gamma", [0.1, 5.0])
+def test_team_per_column_kernel_equals_the_in_kernel_path(monkeypatch, which, gamma):
+    """Plans with MANY mid columns give them their own launch (32 threads per column, u in a shared-memory stash, global
+    accumulators: matching_long_cta_kernel<ACC, 32>) instead of the slab kernel's warp-per-column path; DUALIP_MID_KERNEL
+    forces either.  Same decisions, same x, same branch / support size; sums agree to rounding."""
+    p = _problem(17)
+    n = p["ccol"].size - 1
+    lam = torch.from_numpy(p["lam"]).to(DEV)
+    monkeypatch.setenv("DUALIP_MID_KERNEL", "0")
+    inner = _objective(p, _maps(n)[which], gamma)
+    monkeypatch.setenv("DUALIP_MID_KERNEL", "1")
+    team = _objective(p, _maps(n)[which], gamma)
+    assert inner.plan_info()["launches_per_calc"] == 2 and team.plan_info()["launches_per_calc"] == 3
+    assert inner.plan_info()["n_mid_cols"] == team.plan_info()["n_mid_cols"] > 2000
+    r0 = inner.calculate(lam, save_primal=True, diagnostics=True)
+    r1 = team.calculate(lam, save_primal=True, diagnostics=True)
+    assert torch.equal(r0.primal_var, r1.primal_var) and torch.equal(r0.projection_diag, r1.projection_diag)
+    assert torch.allclose(r0.dual_gradient, r1.dual_gradient, rtol=2e-5, atol=2e-5)
+    assert abs(float(r0.scalars64[0]) - float(r1.scalars64[0])) <= 1e-6 * abs(float(r0.scalars64[0]))
+    r2 = team.calculate(lam)
+    assert torch.allclose(r2.dual_gradient, r1.dual_gradient, rtol=1e-6, atol=1e-6)
+    out = AcceleratedGradientDescent(max_iter=20, gamma=gamma, initial_step_size=1e-3, max_step_size=0.1,
+                                     iteration_callback=no_iteration_callback).maximize(team, torch.zeros(int(p["n_rows"]), device=DEV))
+    assert all(np.isfinite(out.dual_objective_log))
