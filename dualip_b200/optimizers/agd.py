@@ -54,6 +54,23 @@ def format_objective_result_summary(iteration: int, objective_result: ObjectiveR
     return " | ".join(p for p in parts if p is not None)
 
 
+def gamma_schedule(gamma0: float, n_iters: int, decay_steps: int = 0, decay_factor: float = 1.0):
+    """What the reference's loop does to gamma, unrolled (agd.py:102-109, :186-187): iteration i (1-based) runs with
+    gammas[i-1]; after it, if i % decay_steps == 0, gamma *= decay_factor (and the step cap follows: flags[i-1] = 1).
+    Returns (gammas of length n_iters + 1 -- the last entry is gamma after the final iteration -- , flags of length n_iters).
+    The products are formed one after the other in Python doubles, like the reference's `self.gamma = self.gamma * factor`."""
+    g = gamma0
+    gammas, flags = [], []
+    for i in range(1, n_iters + 1):
+        gammas.append(float(g))
+        d = 1 if (decay_steps and i % decay_steps == 0) else 0
+        flags.append(d)
+        if d:
+            g = g * decay_factor
+    gammas.append(float(g))
+    return gammas, flags
+
+
 def no_iteration_callback(iteration: int, objective_result: ObjectiveResult) -> None:
     """Pass as `iteration_callback` to run without per-iteration reporting: the fused loop then never materialises an
     ObjectiveResult per iteration (and, sharded, takes the objective's tail and the update in one launch)."""
@@ -416,16 +433,9 @@ class FusedAscentLoop:
         """gamma / beta / decay flag of every iteration, exactly as step() would pass them (agd.py:93-109)."""
         solver, n = self.solver, max(self.solver.max_iter, 1)
         g = solver.gamma if solver.gamma is not None else self.f.gamma
-        gammas, flags = [], []
         steps = solver.gamma_decay_params["decay_steps"] if self.decay else 0
         factor = float(solver.gamma_decay_params["decay_factor"]) if self.decay else 1.0
-        for i in range(1, n + 1):
-            gammas.append(float(g))
-            d = 1 if (self.decay and i % steps == 0) else 0
-            flags.append(d)
-            if d:
-                g = g * factor
-        gammas.append(float(g))
+        gammas, flags = gamma_schedule(g, n, steps, factor)
         self._gamma_sched = gammas  # [k] = gamma before iteration k+1; [n] = after the last
         beta = (ctypes.c_float * n)(*self.beta[:n])
         with torch.cuda.device(self.device):

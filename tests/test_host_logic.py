@@ -395,3 +395,24 @@ def test_vectorised_input_validation():
     with pytest.raises(InputValidationError, match="all-zero column"):
         check_no_zero_row_or_col(dense)
     assert issubclass(InputValidationError, ValueError)
+
+
+def test_gamma_schedule_equals_the_reference_loop():
+    """The device-resident schedule of the graph-replayed loop (gamma per iteration, step-cap flags) against the reference's
+    own bookkeeping: AcceleratedGradientDescent._update_gamma called once per iteration (agd.py:102-109,186-187)."""
+    from dualip_b200.optimizers.agd import AcceleratedGradientDescent, gamma_schedule
+
+    for gamma0, steps, factor, n in ((1e-3, 35, 0.7, 200), (0.1, 1, 0.5, 12), (2.0, 7, 0.9, 7), (5e-2, 1000, 0.1, 50)):
+        solver = AcceleratedGradientDescent(max_iter=n, gamma=gamma0, gamma_decay_type="step",
+                                            gamma_decay_params={"decay_steps": steps, "decay_factor": factor})
+        seen, caps = [], []
+        for i in range(1, n + 1):
+            seen.append(solver.gamma)
+            before = solver.max_step_size
+            solver._update_gamma(i, 0.5)  # the step size only feeds the cap
+            caps.append(1 if solver.max_step_size != before else 0)
+        gammas, flags = gamma_schedule(gamma0, n, steps, factor)
+        assert gammas[:n] == seen and gammas[n] == solver.gamma  # bit-identical doubles
+        assert flags == caps
+    gammas, flags = gamma_schedule(3e-3, 5)
+    assert gammas == [3e-3] * 6 and flags == [0] * 5
