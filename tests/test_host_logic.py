@@ -409,7 +409,7 @@ def test_gamma_schedule_equals_the_reference_loop():
         for i in range(1, n + 1):
             seen.append(solver.gamma)
             before = solver.max_step_size
-            solver._update_gamma(i, 0.5)  # the step size only feeds the cap
+            solver._update_gamma(i, 0.5 + 1e-3 * i)  # the step size only feeds the cap (varied, so that every change shows)
             caps.append(1 if solver.max_step_size != before else 0)
         gammas, flags = gamma_schedule(gamma0, n, steps, factor)
         assert gammas[:n] == seen and gammas[n] == solver.gamma  # bit-identical doubles
