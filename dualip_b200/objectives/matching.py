@@ -1,6 +1,8 @@
 """Matching objective: same class names, constructor signatures and `calculate` keywords as the reference
 (src/dualip/objectives/matching.py), with the body of `calculate` replaced by one call into the C-ABI
-(include/dualip_b200.h: dualip_matching_calc / dualip_matching_partial + dualip_matching_epilogue).
+(include/dualip_b200.h: dualip_matching_calc; sharded: dualip_matching_partial + all-reduce + dualip_matching_epilogue, or
+dualip_matching_calc_peer_host for a host-resident dual).  The Maximizer drives the same plan through
+dualip_matching_ascent_step[_peer / _scheduled] (evaluation + step in one launch).
 
 CUDA-only: tensors must live on a CUDA device and be float32.  There is no CPU fallback.
 """

@@ -1,10 +1,15 @@
 """Maximizer: Nesterov-accelerated projected gradient ascent on the dual.
 
 Same class name, constructor and `maximize(f, initial_value, rank=0) -> SolverResult` as the reference
-(src/dualip/optimizers/agd.py:66-229).  Two loops:
+(src/dualip/optimizers/agd.py:66-229).  Three loops:
 
-* fused (CUDA matching objectives): iterate, history ring, step-size rule and logs live on the device
-  (csrc/agd.cu); one iteration = the objective's kernel(s) + one update kernel, with no host synchronisation;
+* fused (CUDA objectives, device-resident dual): iterate, history ring, step-size rule and logs live on the device
+  (csrc/agd_step.cuh).  Matching objectives take evaluation AND step in ONE launch per iteration (the slab kernel's last CTA
+  steps; sharded: it also exchanges the partial sums through peer memory), and once the plan has settled whole chunks of
+  iterations replay as one CUDA graph (device-resident gamma / beta schedule).  Other objectives (generic LP, fairness rows,
+  user-registered projections, per-iteration callbacks) launch their kernels plus one update kernel.  No host synchronisation.
+* host-buffer (float32 CPU dual, native matching objective): one native call per iteration, dualip_matching_step_host
+  (lambda up, fused kernel, gradient + scalars down, host-side step).
 * generic (any object with `calculate` / `equality_mask`): host-driven, the reference's semantics op for op.
 """
 from __future__ import annotations
