@@ -166,6 +166,10 @@ struct dualip_plan {
   float* row_unscale = nullptr;  // m floats 2^-k_r, or null: rows are stored scaled by 2^k_r (power-of-two row equilibration)
   double* acc_scal = nullptr;  // [c.x, ||x||^2], zero between calls
   unsigned int* counter = nullptr;
+  unsigned int* grid_bar = nullptr;  // grid barrier of the all-CTA tail: {arrive counter, generation}
+  double* tail_part = nullptr;       // n_ctas x kTailPart doubles
+  int* grid_status = nullptr;
+  int grid_tail = 1;                 // DUALIP_GRID_TAIL=0: the last CTA runs the tail alone
   float* lambda_stage = nullptr;  // m floats, for *_calc_host
   float* grad_stage = nullptr;
   dualip_scalars* scal_stage = nullptr;
@@ -364,6 +368,11 @@ struct KArgs {
   // device-resident schedule at index *agd.pushes, so the kernel arguments are the same for every iteration and a sequence
   // of launches can be captured once in a CUDA graph and replayed (dualip_ascent_graph_*).  sched.gamma == null: off.
   SchedArgs sched;
+  // grid-wide tail (grid_tail.cuh): all CTAs share the m-length tail, the exchange and the step.  0: the last CTA does it.
+  int grid_tail;
+  unsigned int* grid_bar;   // {arrive counter, generation}
+  double* tail_part;        // gridDim.x x kTailPart doubles
+  int* grid_status;         // set to 2 if a grid barrier timed out
 };
 
 template <bool ROW16>
@@ -413,6 +422,7 @@ __device__ __forceinline__ int pad_len_of(const KArgs& k, int cls, int d) {
 #include "slab_fast.cuh"
 #include "mid_col.cuh"
 #include "long_col.cuh"
+#include "grid_tail.cuh"
 namespace dualip {
 
 // Generic-path loads of N consecutive entries k0 .. k0+N-1 of this lane's column (N = 8/4: whole 4-entry chunks,
@@ -1291,15 +1301,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     }
   }
   stamp(3);
-  // ---- last CTA to finish runs the m-length tail and leaves the accumulators zeroed ----
   __threadfence();
-  __syncthreads();
-  if (tid == 0) s_ticket = atomicAdd(k.counter, 1u);
-  __syncthreads();
-  if (s_ticket != gridDim.x - 1) return;
-  __threadfence();
-  const double cxv = __ldcg(&k.acc_scal[0]);
-  const double xxv = __ldcg(&k.acc_scal[1]);
   auto sum_load = [&](int i) -> float {
     const double un = k.row_unscale ? (double)__ldg(k.row_unscale + i) : 1.0;  // exact: a power of two
     if (ACC == 1) {
@@ -1317,14 +1319,33 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     }
   };
   const bool scheduled = k.sched.gamma != nullptr;
-  // (read again rather than kept in registers across the main loop; the counter moves only inside agd_step_body, behind a
-  // CTA barrier that every thread reaches after this point)
+  // (read again rather than kept in registers across the main loop; the counter moves only at the very end of the tail, behind
+  // barriers that every thread reaches after this point)
   long long sched_it = 0;
   double gamma_run = k.gamma;
   if (scheduled) {
     sched_it = __ldcg(k.agd.pushes);
     gamma_run = __ldg(k.sched.gamma + (sched_it < (long long)k.sched.n ? sched_it : (long long)k.sched.n - 1));
   }
+  if (k.grid_tail) {
+    // ---- all CTAs share the tail, the exchange and the step (grid_tail.cuh) ----
+    const StepDyn dyn = scheduled ? step_dyn_sched(k.agd, k.sched, sched_it) : step_dyn_of(k.agd);
+    const unsigned long long seq_g = scheduled ? (unsigned long long)(k.sched.seq_base + sched_it + 1) : k.peer.seq;
+    if (k.fuse == 2)
+      grid_tail<true>(k, sum_load, sum_clear, dyn, gamma_run, seq_g);
+    else
+      grid_tail<false>(k, sum_load, sum_clear, dyn, gamma_run, seq_g);
+    stamp(4);
+    return;
+  }
+  // ---- last CTA to finish runs the m-length tail and leaves the accumulators zeroed ----
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(k.counter, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  const double cxv = __ldcg(&k.acc_scal[0]);
+  const double xxv = __ldcg(&k.acc_scal[1]);
   if (k.do_epilogue) {
     cta_epilogue(sum_load, sum_clear, cxv, xxv, k.lambda, k.b, m, gamma_run, k.grad_out, k.scalars_out, dscratch, fscratch);
     if (k.fuse == 1) {
@@ -1701,6 +1722,12 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.mid_cols = (p->n_mid > 0 && !p->mid_separate) ? p->longcols : nullptr;
   k.mid_range = p->mid_range;
   k.fuse = fuse ? fuse->mode : 0;
+  // the all-CTA tail needs every CTA of the grid resident at once (one CTA per SM) and, sharded, the push exchange
+  k.grid_tail = (fuse && p->grid_tail && p->n_ctas <= p->n_sms && x_out == nullptr && diag == nullptr &&
+                 (fuse->mode == 1 || (fuse->mode == 2 && fuse->peer.push != 0))) ? 1 : 0;
+  k.grid_bar = p->grid_bar;
+  k.tail_part = p->tail_part;
+  k.grid_status = p->grid_status;
   if (fuse) {
     k.agd = fuse->agd;
     k.peer = fuse->peer;
@@ -2332,6 +2359,9 @@ void dualip_plan_destroy(dualip_plan* p) {
   cudaFree(p->acc_hi);
   cudaFree(p->acc_scal);
   cudaFree(p->counter);
+  cudaFree(p->grid_bar);
+  cudaFree(p->tail_part);
+  cudaFree(p->grid_status);
   cudaFree(p->lambda_stage);
   cudaFree(p->grad_stage);
   cudaFree(p->scal_stage);
@@ -2508,6 +2538,16 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   DUALIP_TRY_FAIL(cudaMemset(p->acc_scal, 0, sizeof(double) * 2));
   DUALIP_TRY_FAIL(cudaMalloc(&p->counter, sizeof(unsigned int)));
   DUALIP_TRY_FAIL(cudaMemset(p->counter, 0, sizeof(unsigned int)));
+  DUALIP_TRY_FAIL(cudaMalloc(&p->grid_bar, 2 * sizeof(unsigned int)));
+  DUALIP_TRY_FAIL(cudaMemset(p->grid_bar, 0, 2 * sizeof(unsigned int)));
+  DUALIP_TRY_FAIL(cudaMalloc(&p->tail_part, sizeof(double) * kTailPart * (size_t)std::max(p->n_ctas, 1)));
+  DUALIP_TRY_FAIL(cudaMalloc(&p->grid_status, sizeof(int)));
+  DUALIP_TRY_FAIL(cudaMemset(p->grid_status, 0, sizeof(int)));
+  // the all-CTA tail pays two to four grid barriers (~3 us each): a gain once the m-length passes of a single CTA cost more than
+  // that (measured: +17 % at m = 26 744, neutral at m = 10 000 on one and two GPUs, -9 % at m = 1 000); DUALIP_GRID_TAIL=0|1
+  // forces it
+  p->grid_tail = p->m >= 16384 ? 1 : 0;
+  if (const char* gt = getenv("DUALIP_GRID_TAIL")) p->grid_tail = atoi(gt) != 0 ? 1 : 0;
   DUALIP_TRY_FAIL(cudaMalloc(&p->lambda_stage, sizeof(float) * (m_pad + 4)));
   DUALIP_TRY_FAIL(cudaMalloc(&p->grad_stage, sizeof(float) * (m_pad + 4)));
   DUALIP_TRY_FAIL(cudaMalloc(&p->scal_stage, sizeof(dualip_scalars)));

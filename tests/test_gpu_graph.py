@@ -197,3 +197,32 @@ def test_host_buffer_loop_one_native_call_per_iteration(monkeypatch, decay):
     assert b.dual_val.device.type == "cpu" and b.objective_result.dual_gradient.device.type == "cpu"
     quiet = AcceleratedGradientDescent(iteration_callback=no_iteration_callback, **kw).maximize(_objective(p, _mixed_map(n), 2e-2), lam0)
     assert torch.equal(quiet.dual_val, b.dual_val) and quiet.objective_result is not None
+
+
+@pytest.mark.parametrize("decay", [False, True])
+def test_all_cta_tail_equals_the_last_cta_tail(monkeypatch, decay):
+    """grid_tail.cuh: every CTA takes a slice of the m-length tail and of the accelerated step, with grid-wide barriers in
+    between (default for m >= 16384) against the tail run by the last CTA alone.  Element-wise arithmetic is identical; only the
+    order of the double-precision partial sums differs, so the logs agree to rounding and the iterates to a few ulps.  Also
+    through CUDA-graph replay (barrier state persists across the captured launches)."""
+    monkeypatch.setenv("DUALIP_REBALANCE", "0")
+    p = random_problem(19, 9000, 700, 8.0)
+    n = p["ccol"].size - 1
+    kw = dict(max_iter=45, gamma=2e-2, initial_step_size=1e-3, max_step_size=0.1, iteration_callback=no_iteration_callback)
+    if decay:
+        kw.update(gamma_decay_type="step", gamma_decay_params={"decay_steps": 7, "decay_factor": 0.7})
+    lam0 = torch.zeros(700, device=DEV)
+    outs = {}
+    for tag, env, graph in (("last", "0", "0"), ("grid", "1", "0"), ("grid_graph", "1", "1")):
+        monkeypatch.setenv("DUALIP_GRID_TAIL", env)
+        monkeypatch.setenv("DUALIP_GRAPH", graph)
+        monkeypatch.setenv("DUALIP_GRAPH_CHUNK", "8")
+        obj = _objective(p, _mixed_map(n), 2e-2)
+        assert obj.plan_info()["n_ctas"] > 1
+        outs[tag] = AcceleratedGradientDescent(**kw).maximize(obj, lam0)
+    a, b, c = outs["last"], outs["grid"], outs["grid_graph"]
+    assert np.allclose(a.dual_objective_log, b.dual_objective_log, rtol=1e-9)
+    assert np.allclose(a.step_size_log, b.step_size_log, rtol=1e-6)
+    assert torch.allclose(a.dual_val, b.dual_val, rtol=1e-5, atol=1e-7)
+    assert b.dual_objective_log == c.dual_objective_log and torch.equal(b.dual_val, c.dual_val), "graph replay of the all-CTA tail"
+    assert torch.allclose(a.objective_result.dual_gradient, b.objective_result.dual_gradient, rtol=1e-5, atol=1e-6)
