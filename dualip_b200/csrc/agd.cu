@@ -18,7 +18,8 @@ namespace dualip {
 
 template <bool FROM_PARTIAL>
 __global__ void __launch_bounds__(1024) agd_step_kernel(const AgdStepArgs A) {
-  agd_step_body<FROM_PARTIAL>(A, step_dyn_of(A));
+  __shared__ TailScratch s_tail;
+  agd_step_body<FROM_PARTIAL>(A, step_dyn_of(A), s_tail);
 }
 
 // ceil((m+2) / 4096) CTAs of 1024 threads.  CTA 0 tells every peer that this rank's partial sums (written by the preceding
@@ -28,6 +29,7 @@ __global__ void __launch_bounds__(1024) agd_step_kernel(const AgdStepArgs A) {
 // objective's tail and the accelerated update on the reduced vector.
 __global__ void __launch_bounds__(1024) agd_step_peer_kernel(const AgdStepArgs A, const PeerArgs P) {
   __shared__ int s_last;
+  __shared__ TailScratch s_tail;
   const int tid = threadIdx.x;
   const int m2 = A.m + 2;
   if (tid < P.world) {
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(1024) agd_step_peer_kernel(const AgdStepArgs A
   } else {
     __syncthreads();  // P.sum is read below by other threads of this CTA
   }
-  agd_step_body<true>(A, step_dyn_of(A));
+  agd_step_body<true>(A, step_dyn_of(A), s_tail);
 }
 
 }  // namespace dualip

@@ -59,8 +59,18 @@ __device__ __forceinline__ StepDyn step_dyn_sched(const AgdStepArgs& A, const Sc
   return StepDyn{S.beta[i], (int)S.decay[i], (int)it, S.gamma[i], A.log_obj != nullptr && it < (long long)A.log_cap};
 }
 
+// Shared-memory scratch of the m-length tail / step code.  ONE object per kernel, handed to every helper: static __shared__
+// arrays inside templated device functions would be replicated per instantiation, and the slab kernel's dynamic shared
+// memory is sized up to the device limit minus a fixed allowance for its static part.
+struct TailScratch {
+  double red[5][32];
+  double tot[8];
+  double step;
+  float mx[32];
+};
+
 template <bool FROM_PARTIAL>
-__device__ __forceinline__ void agd_step_body(const AgdStepArgs& A, const StepDyn& D) {
+__device__ __forceinline__ void agd_step_body(const AgdStepArgs& A, const StepDyn& D, TailScratch& T) {
   float* __restrict__ x = A.x;
   float* __restrict__ y = A.y;
   float* __restrict__ gh = A.gh;
@@ -80,9 +90,9 @@ __device__ __forceinline__ void agd_step_body(const AgdStepArgs& A, const StepDy
   const float* __restrict__ b = A.b;
   float* grad_out = A.grad_out;
   dualip_scalars* __restrict__ scal_out = A.scal_out;
-  __shared__ double s_red[5][32];
-  __shared__ float s_mx[32];
-  __shared__ double s_step;
+  double (&s_red)[5][32] = T.red;
+  float (&s_mx)[32] = T.mx;
+  double& s_step = T.step;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
   const long long t = *pushes;  // index of the entry pushed now

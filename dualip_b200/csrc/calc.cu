@@ -475,7 +475,7 @@ __device__ __forceinline__ void load_batch(const float* __restrict__ pa0, const 
 template <typename SumFn, typename ClearFn>
 __device__ __forceinline__ void cta_epilogue(SumFn sum_load, ClearFn sum_clear, double cxv, double xxv, const float* lambda, const float* b, int m,
                                              double gamma, float* grad_out, dualip_scalars* out, double* dscratch,
-                                             float* fscratch) {
+                                             float* fscratch, TailScratch& T) {
   double lg = 0.0, sp = 0.0, g2 = 0.0;
   float mx = -INFINITY;
   const int nt = blockDim.x;
@@ -511,7 +511,7 @@ __device__ __forceinline__ void cta_epilogue(SumFn sum_load, ClearFn sum_clear, 
   sp = warp_sum(sp);
   g2 = warp_sum(g2);
   mx = warp_max(mx);
-  __shared__ double s_red[3][32];
+  double (&s_red)[5][32] = T.red;
   __syncthreads();
   if (lane == 0) {
     s_red[0][warp] = lg;
@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       (reinterpret_cast<uintptr_t>(s_stash) + 127) & ~(uintptr_t)127);  // kStageBytes per warp (register path)
   __shared__ unsigned int s_ticket;
   __shared__ int s_nseg;
+  __shared__ TailScratch s_tail;  // the one static scratch of the tail code (cta_epilogue, agd_step_body, grid_tail)
 
   const unsigned FULL = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1332,9 +1333,13 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
     const StepDyn dyn = scheduled ? step_dyn_sched(k.agd, k.sched, sched_it) : step_dyn_of(k.agd);
     const unsigned long long seq_g = scheduled ? (unsigned long long)(k.sched.seq_base + sched_it + 1) : k.peer.seq;
     if (k.fuse == 2)
-      grid_tail<true>(k, sum_load, sum_clear, dyn, gamma_run, seq_g);
+      grid_tail<true, true>(k, sum_load, sum_clear, dyn, gamma_run, seq_g, s_tail);
+    else if (k.fuse == 1)
+      grid_tail<false, true>(k, sum_load, sum_clear, dyn, gamma_run, seq_g, s_tail);
+    else if (k.fuse == 3)
+      grid_tail<true, false>(k, sum_load, sum_clear, dyn, gamma_run, seq_g, s_tail);
     else
-      grid_tail<false>(k, sum_load, sum_clear, dyn, gamma_run, seq_g);
+      grid_tail<false, false>(k, sum_load, sum_clear, dyn, gamma_run, seq_g, s_tail);
     stamp(4);
     return;
   }
@@ -1347,10 +1352,10 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   const double cxv = __ldcg(&k.acc_scal[0]);
   const double xxv = __ldcg(&k.acc_scal[1]);
   if (k.do_epilogue) {
-    cta_epilogue(sum_load, sum_clear, cxv, xxv, k.lambda, k.b, m, gamma_run, k.grad_out, k.scalars_out, dscratch, fscratch);
+    cta_epilogue(sum_load, sum_clear, cxv, xxv, k.lambda, k.b, m, gamma_run, k.grad_out, k.scalars_out, dscratch, fscratch, s_tail);
     if (k.fuse == 1) {
       __syncthreads();  // grad_out / scalars_out written above are read by other threads of this CTA
-      agd_step_body<false>(k.agd, scheduled ? step_dyn_sched(k.agd, k.sched, sched_it) : step_dyn_of(k.agd));
+      agd_step_body<false>(k.agd, scheduled ? step_dyn_sched(k.agd, k.sched, sched_it) : step_dyn_of(k.agd), s_tail);
     }
   } else {
     // sharded + scheduled: the exchange step number follows the device-side iteration count, and so does the slot
@@ -1395,13 +1400,13 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
       else
         peer_exchange_cta(k.peer, m + 2, seq);
       if (k.fuse == 2) {
-        agd_step_body<true>(k.agd, scheduled ? step_dyn_sched(k.agd, k.sched, sched_it) : step_dyn_of(k.agd));
+        agd_step_body<true>(k.agd, scheduled ? step_dyn_sched(k.agd, k.sched, sched_it) : step_dyn_of(k.agd), s_tail);
       } else {
         // sharded evaluation for a caller that keeps the iterate itself (host-buffer path): the m-length tail on the summed
         // vector, no optimizer step
         const float* sum = k.peer.sum;
         cta_epilogue([&](int i) { return sum[i]; }, [](int) {}, (double)sum[m], (double)sum[m + 1], k.lambda, k.b, m, gamma_run,
-                     k.grad_out, k.scalars_out, dscratch, fscratch);
+                     k.grad_out, k.scalars_out, dscratch, fscratch, s_tail);
       }
     }
   }
@@ -1554,9 +1559,10 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(const float* sum, int m,
                                                         double gamma, float* grad_out, dualip_scalars* out) {
   __shared__ double dscratch[32];
   __shared__ float fscratch[32];
+  __shared__ TailScratch s_tail;
   const double cxv = (double)sum[m], xxv = (double)sum[m + 1];
   cta_epilogue([&](int i) { return __ldcg(sum + i); }, [](int) {}, cxv, xxv, lambda, b, m, gamma, grad_out, out, dscratch,
-               fscratch);
+               fscratch, s_tail);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1723,8 +1729,11 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   k.mid_range = p->mid_range;
   k.fuse = fuse ? fuse->mode : 0;
   // the all-CTA tail needs every CTA of the grid resident at once (one CTA per SM) and, sharded, the push exchange
-  k.grid_tail = (fuse && p->grid_tail && p->n_ctas <= p->n_sms && x_out == nullptr && diag == nullptr &&
-                 (fuse->mode == 1 || (fuse->mode == 2 && fuse->peer.push != 0))) ? 1 : 0;
+  {
+    const int mode = fuse ? fuse->mode : 0;
+    const bool ok_mode = (mode == 0 && do_epilogue) || mode == 1 || ((mode == 2 || mode == 3) && fuse->peer.push != 0);
+    k.grid_tail = (p->grid_tail && p->n_ctas <= p->n_sms && x_out == nullptr && diag == nullptr && ok_mode) ? 1 : 0;
+  }
   k.grid_bar = p->grid_bar;
   k.tail_part = p->tail_part;
   k.grid_status = p->grid_status;

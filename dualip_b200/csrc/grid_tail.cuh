@@ -47,33 +47,36 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int n, 
   __syncthreads();
 }
 
-template <bool SHARDED, typename SumFn, typename ClearFn>
+// STEP false: evaluation only (dualip_matching_calc / dualip_matching_calc_peer: the host-buffer path) -- the tail without
+// the optimizer's part; the evaluation point is k.lambda and the outputs are k.grad_out / k.scalars_out.
+template <bool SHARDED, bool STEP, typename SumFn, typename ClearFn>
 __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearFn sum_clear, const StepDyn D, double gamma,
-                                          unsigned long long seq) {
-  __shared__ double s_red[5][32];
-  __shared__ float s_mx[32];
-  __shared__ double s_tot[6];
-  __shared__ double s_step;
+                                          unsigned long long seq, TailScratch& T) {
+  double (&s_red)[5][32] = T.red;
+  float (&s_mx)[32] = T.mx;
+  double (&s_tot)[8] = T.tot;
+  double& s_step = T.step;
   const AgdStepArgs& A = k.agd;
   const unsigned FULL = 0xffffffffu;
   const int tid = threadIdx.x, nt = blockDim.x, nb = gridDim.x, bid = blockIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
-  const int m = k.m, H = A.H;
+  const int m = k.m, H = STEP ? A.H : 2;  // (evaluation only: the optimizer arguments are not set)
   const int S = (m + nb - 1) / nb;
   const int r0 = min(m, bid * S), r1 = min(m, r0 + S);
   int* status = SHARDED ? k.peer.status : k.grid_status;
   // optimizer state that CTA 0 changes at the very end: read by everyone before the first barrier
-  const long long t = __ldcg(A.pushes);
+  const long long t = STEP ? __ldcg(A.pushes) : 0;
   const int slot = (int)(t % H), prev = (int)((t + H - 1) % H);
-  const bool have_prev = t > 0;
-  const double max_step = __ldcg(&A.dstate[0]), init_step = __ldcg(&A.dstate[1]);
+  const bool have_prev = STEP && t > 0;
+  const double max_step = STEP ? __ldcg(&A.dstate[0]) : 0.0, init_step = STEP ? __ldcg(&A.dstate[1]) : 0.0;
   float* __restrict__ x = A.x;
   float* __restrict__ y = A.y;
   float* __restrict__ gh = A.gh;
   float* __restrict__ yh = A.yh;
-  float* grad_out = SHARDED ? A.grad_out : k.grad_out;
-  dualip_scalars* scal_out = SHARDED ? A.scal_out : k.scalars_out;
-  const float* __restrict__ b = SHARDED ? A.b : k.b;
+  const float* __restrict__ lam_p = STEP ? A.x : k.lambda;  // the evaluation point
+  float* grad_out = (SHARDED && STEP) ? A.grad_out : k.grad_out;
+  dualip_scalars* scal_out = (SHARDED && STEP) ? A.scal_out : k.scalars_out;
+  const float* __restrict__ b = (SHARDED && STEP) ? A.b : k.b;
 
   grid_barrier(k.grid_bar, nb, status);  // B1: the accumulators hold this rank's complete sums
   const double cx_local = __ldcg(&k.acc_scal[0]), xx_local = __ldcg(&k.acc_scal[1]);
@@ -147,19 +150,22 @@ __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearF
     }
     const float g = b ? __fsub_rn(tot, __ldg(b + i)) : tot;
     grad_out[i] = g;
-    const float lam = x[i], yv = y[i];
+    const float lam = lam_p[i];
     lg = fma((double)lam, (double)g, lg);
     sp += (double)fmaxf(g, 0.f);
     g2 = fma((double)g, (double)g, g2);
     mx = fmaxf(mx, g);
-    if (have_prev) {
-      const float dg = __fsub_rn(gh[(size_t)prev * m + i], g);
-      const float dy = __fsub_rn(yh[(size_t)prev * m + i], yv);
-      dg2 = fma((double)dg, (double)dg, dg2);
-      dy2 = fma((double)dy, (double)dy, dy2);
+    if (STEP) {
+      const float yv = y[i];
+      if (have_prev) {
+        const float dg = __fsub_rn(gh[(size_t)prev * m + i], g);
+        const float dy = __fsub_rn(yh[(size_t)prev * m + i], yv);
+        dg2 = fma((double)dg, (double)dg, dg2);
+        dy2 = fma((double)dy, (double)dy, dy2);
+      }
+      gh[(size_t)slot * m + i] = g;
+      yh[(size_t)slot * m + i] = yv;
     }
-    gh[(size_t)slot * m + i] = g;
-    yh[(size_t)slot * m + i] = yv;
   }
   lg = warp_sum(lg), sp = warp_sum(sp), g2 = warp_sum(g2), dg2 = warp_sum(dg2), dy2 = warp_sum(dy2);
   mx = warp_max(mx);
@@ -210,36 +216,45 @@ __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearF
     r.sum_pos_slack = sp;
     r.x_sq_norm = xxv;
     r.grad_sq_norm = g2;
-    const float rnew = have_prev ? __fdiv_rn((float)sqrt(dg2), (float)sqrt(dy2)) : 0.f;
-    // step size (agd_utils.py:44-62): Python max() over the ratios in chronological order; the newest one is rnew
-    const long long n_pairs = t < (long long)(H - 1) ? t : (long long)(H - 1);
-    double step = init_step;
-    if (n_pairs >= H - 1) {
-      const long long j0 = t - (H - 1);
-      float lmax = (j0 == t - 1) ? rnew : A.ratios[j0 % (H - 1)];
-      for (long long j = j0 + 1; j < t; ++j) {
-        const float v = (j == t - 1) ? rnew : A.ratios[j % (H - 1)];
-        if (v > lmax) lmax = v;
+    if (!STEP) {
+      if (bid == 0) {
+        *scal_out = r;
+        k.acc_scal[0] = 0.0;
+        k.acc_scal[1] = 0.0;
       }
-      if (!(isnan(lmax) || isinf(lmax))) {
-        const double cand = (lmax != 0.f) ? 1.0 / (double)lmax : max_step;
-        step = cand < max_step ? cand : max_step;
+    } else {
+      const float rnew = have_prev ? __fdiv_rn((float)sqrt(dg2), (float)sqrt(dy2)) : 0.f;
+      // step size (agd_utils.py:44-62): Python max() over the ratios in chronological order; the newest one is rnew
+      const long long n_pairs = t < (long long)(H - 1) ? t : (long long)(H - 1);
+      double step = init_step;
+      if (n_pairs >= H - 1) {
+        const long long j0 = t - (H - 1);
+        float lmax = (j0 == t - 1) ? rnew : A.ratios[j0 % (H - 1)];
+        for (long long j = j0 + 1; j < t; ++j) {
+          const float v = (j == t - 1) ? rnew : A.ratios[j % (H - 1)];
+          if (v > lmax) lmax = v;
+        }
+        if (!(isnan(lmax) || isinf(lmax))) {
+          const double cand = (lmax != 0.f) ? 1.0 / (double)lmax : max_step;
+          step = cand < max_step ? cand : max_step;
+        }
       }
-    }
-    s_step = step;
-    if (bid == 0) {  // one writer for everything that is not sliced
-      *scal_out = r;
-      if (have_prev) A.ratios[(t - 1) % (H - 1)] = rnew;
-      if (D.log) {
-        A.log_obj[D.iter_index] = r.dual_objective;
-        A.log_step[D.iter_index] = step;
+      s_step = step;
+      if (bid == 0) {  // one writer for everything that is not sliced
+        *scal_out = r;
+        if (have_prev) A.ratios[(t - 1) % (H - 1)] = rnew;
+        if (D.log) {
+          A.log_obj[D.iter_index] = r.dual_objective;
+          A.log_step[D.iter_index] = step;
+        }
+        if (D.decay_now) A.dstate[0] = step * A.decay_factor;  // agd.py:107
+        *A.pushes = t + 1;
+        k.acc_scal[0] = 0.0;
+        k.acc_scal[1] = 0.0;
       }
-      if (D.decay_now) A.dstate[0] = step * A.decay_factor;  // agd.py:107
-      *A.pushes = t + 1;
-      k.acc_scal[0] = 0.0;
-      k.acc_scal[1] = 0.0;
     }
   }
+  if (!STEP) return;
   __syncthreads();
   // ---- ascent step, projection on the dual cone, momentum on this CTA's rows (agd.py:181-185, :13-21) ----
   const float step32 = (float)s_step;

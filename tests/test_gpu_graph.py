@@ -226,3 +226,13 @@ def test_all_cta_tail_equals_the_last_cta_tail(monkeypatch, decay):
     assert torch.allclose(a.dual_val, b.dual_val, rtol=1e-5, atol=1e-7)
     assert b.dual_objective_log == c.dual_objective_log and torch.equal(b.dual_val, c.dual_val), "graph replay of the all-CTA tail"
     assert torch.allclose(a.objective_result.dual_gradient, b.objective_result.dual_gradient, rtol=1e-5, atol=1e-6)
+    # evaluation only (dualip_matching_calc, device and host buffers): the all-CTA tail without the optimizer's part
+    lam = a.dual_val
+    res = {}
+    for env in ("0", "1"):
+        monkeypatch.setenv("DUALIP_GRID_TAIL", env)
+        obj = _objective(p, _mixed_map(n), 2e-2)
+        res[env] = (obj.calculate(lam), obj.calculate(lam.cpu()))
+    for k in (0, 1):
+        assert torch.equal(res["0"][k].dual_gradient, res["1"][k].dual_gradient)
+        assert abs(float(res["0"][k].scalars64[0]) - float(res["1"][k].scalars64[0])) <= 1e-12 * abs(float(res["0"][k].scalars64[0]))

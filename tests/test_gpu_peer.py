@@ -169,13 +169,14 @@ def test_peer_wait_is_bounded(monkeypatch):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("push", ["1", "0"])
-def test_sharded_evaluation_through_peer_memory_without_a_step(world, push, monkeypatch):
+@pytest.mark.parametrize("push,grid", [("1", "0"), ("0", "0"), ("1", "1")])
+def test_sharded_evaluation_through_peer_memory_without_a_step(world, push, grid, monkeypatch):
     """dualip_matching_calc_peer: shard kernel + exchange + m-length tail in one launch, no optimizer step (the host-buffer
     path of the sharded objective, reference matching.py:247-307).  Every rank obtains the same bits, and they equal the
     unsharded evaluation up to the order of the shard sums; a second call reuses the other slot parity."""
     monkeypatch.setenv("DUALIP_PEER_TIMEOUT_MS", "3000")
     monkeypatch.setenv("DUALIP_PEER_PUSH", push)
+    monkeypatch.setenv("DUALIP_GRID_TAIL", grid)  # "1": every CTA takes a slice of the exchange and of the tail (grid_tail.cuh)
     lib = _native.lib()
     p = random_problem(31, 5003, 200, 8.0, scale_c=10.0, lam_scale=0.5)
     n, m, gamma = p["n_cols"], p["n_rows"], 2e-2
