@@ -1243,8 +1243,10 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   cx = block_sum(cx, dscratch);
   xx = block_sum(xx, dscratch);
   if (tid == 0) {
-    if (cx != 0.0) atomicAdd(&k.acc_scal[0], cx);
-    if (xx != 0.0) atomicAdd(&k.acc_scal[1], xx);
+    // one slot per CTA, added up in CTA order by the tail: the objective's scalars are reproducible bit for bit, like the
+    // fixed-point gradient (a floating-point atomic per CTA would add them in arrival order)
+    k.tail_part[(size_t)blockIdx.x * kTailPart + 6] = cx;
+    k.tail_part[(size_t)blockIdx.x * kTailPart + 7] = xx;
   }
   __syncthreads();
   if (ACC == 1) {
@@ -1349,8 +1351,8 @@ __global__ void __launch_bounds__(THREADS, MINB) matching_slab_kernel(const KArg
   __syncthreads();
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();
-  const double cxv = __ldcg(&k.acc_scal[0]);
-  const double xxv = __ldcg(&k.acc_scal[1]);
+  double cxv, xxv;
+  load_scalar_sums(k, s_tail, cxv, xxv);
   if (k.do_epilogue) {
     cta_epilogue(sum_load, sum_clear, cxv, xxv, k.lambda, k.b, m, gamma_run, k.grad_out, k.scalars_out, dscratch, fscratch, s_tail);
     if (k.fuse == 1) {

@@ -49,6 +49,23 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int n, 
 
 // STEP false: evaluation only (dualip_matching_calc / dualip_matching_calc_peer: the host-buffer path) -- the tail without
 // the optimizer's part; the evaluation point is k.lambda and the outputs are k.grad_out / k.scalars_out.
+// c.x and ||x||^2 of this launch: the slab kernel's per-CTA slots added in CTA order (warp 0 / warp 1: lanes stride over the
+// CTAs, then a fixed shuffle tree) on top of what the column kernels launched before it left in acc_scal.  Every thread of the
+// calling CTA gets the result; all CTAs that call it compute the same bits.
+__device__ __forceinline__ void load_scalar_sums(const KArgs& k, TailScratch& T, double& cxv, double& xxv) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < 2) {
+    double acc = 0.0;
+    for (int c = lane; c < (int)gridDim.x; c += 32) acc += __ldcg(k.tail_part + (size_t)c * kTailPart + 6 + warp);
+    acc = warp_sum(acc);
+    if (lane == 0) T.tot[6 + warp] = acc + __ldcg(&k.acc_scal[warp]);
+  }
+  __syncthreads();
+  cxv = T.tot[6];
+  xxv = T.tot[7];
+  __syncthreads();
+}
+
 template <bool SHARDED, bool STEP, typename SumFn, typename ClearFn>
 __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearFn sum_clear, const StepDyn D, double gamma,
                                           unsigned long long seq, TailScratch& T) {
@@ -79,7 +96,8 @@ __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearF
   const float* __restrict__ b = (SHARDED && STEP) ? A.b : k.b;
 
   grid_barrier(k.grid_bar, nb, status);  // B1: the accumulators hold this rank's complete sums
-  const double cx_local = __ldcg(&k.acc_scal[0]), xx_local = __ldcg(&k.acc_scal[1]);
+  double cx_local, xx_local;
+  load_scalar_sums(k, T, cx_local, xx_local);
   double cxv = cx_local, xxv = xx_local;
   if (SHARDED) {
     const PeerArgs& P = k.peer;
