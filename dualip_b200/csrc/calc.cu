@@ -169,7 +169,10 @@ struct dualip_plan {
   unsigned int* grid_bar = nullptr;  // grid barrier of the all-CTA tail: {arrive counter, generation}
   double* tail_part = nullptr;       // n_ctas x kTailPart doubles
   int* grid_status = nullptr;
-  int grid_tail = 1;                 // DUALIP_GRID_TAIL=0: the last CTA runs the tail alone
+  int* grid_status_host = nullptr;      // the same word in mapped host memory (written by the kernel on a time-out only)
+  int* grid_status_host_dev = nullptr;  // its device-side address
+  int grid_tail = 1;                 // all-CTA tail for this plan's own launches (size rule, or forced by DUALIP_GRID_TAIL=0|1)
+  int grid_tail_auto = 1;            // 1: not forced; sharded launches may still turn it on from the world size
   float* lambda_stage = nullptr;  // m floats, for *_calc_host
   float* grad_stage = nullptr;
   dualip_scalars* scal_stage = nullptr;
@@ -373,6 +376,7 @@ struct KArgs {
   unsigned int* grid_bar;   // {arrive counter, generation}
   double* tail_part;        // gridDim.x x kTailPart doubles
   int* grid_status;         // set to 2 if a grid barrier timed out
+  int* grid_status_host;    // the same, in mapped host memory
 };
 
 template <bool ROW16>
@@ -1734,11 +1738,16 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
   {
     const int mode = fuse ? fuse->mode : 0;
     const bool ok_mode = (mode == 0 && do_epilogue) || mode == 1 || ((mode == 2 || mode == 3) && fuse->peer.push != 0);
-    k.grid_tail = (p->grid_tail && p->n_ctas <= p->n_sms && x_out == nullptr && diag == nullptr && ok_mode) ? 1 : 0;
+    // sharded, the single CTA's tail also grows with the world size (it stores its sums into W windows and adds W slots): at
+    // 8 ranks and m = 10 000 sharing it is worth 6.8 % of the step (2935 -> 3135 it/s, A/B/A/B on one box), at 2 ranks nothing
+    const bool wide_world = (mode == 2 || mode == 3) && fuse->peer.world >= 4 && p->m >= 8192;
+    const bool want = p->grid_tail || (p->grid_tail_auto && wide_world);
+    k.grid_tail = (want && p->n_ctas <= p->n_sms && x_out == nullptr && diag == nullptr && ok_mode) ? 1 : 0;
   }
   k.grid_bar = p->grid_bar;
   k.tail_part = p->tail_part;
   k.grid_status = p->grid_status;
+  k.grid_status_host = p->grid_status_host_dev;
   if (fuse) {
     k.agd = fuse->agd;
     k.peer = fuse->peer;
@@ -2373,6 +2382,7 @@ void dualip_plan_destroy(dualip_plan* p) {
   cudaFree(p->grid_bar);
   cudaFree(p->tail_part);
   cudaFree(p->grid_status);
+  if (p->grid_status_host) cudaFreeHost(p->grid_status_host);
   cudaFree(p->lambda_stage);
   cudaFree(p->grad_stage);
   cudaFree(p->scal_stage);
@@ -2554,11 +2564,18 @@ int dualip_plan_create(dualip_plan** out, const dualip_csc_desc* d) {
   DUALIP_TRY_FAIL(cudaMalloc(&p->tail_part, sizeof(double) * kTailPart * (size_t)std::max(p->n_ctas, 1)));
   DUALIP_TRY_FAIL(cudaMalloc(&p->grid_status, sizeof(int)));
   DUALIP_TRY_FAIL(cudaMemset(p->grid_status, 0, sizeof(int)));
+  DUALIP_TRY_FAIL(cudaHostAlloc(reinterpret_cast<void**>(&p->grid_status_host), sizeof(int), cudaHostAllocMapped));
+  *p->grid_status_host = 0;
+  DUALIP_TRY_FAIL(cudaHostGetDevicePointer(reinterpret_cast<void**>(&p->grid_status_host_dev), p->grid_status_host, 0));
   // the all-CTA tail pays two to four grid barriers (~3 us each): a gain once the m-length passes of a single CTA cost more than
   // that (measured: +17 % at m = 26 744, neutral at m = 10 000 on one and two GPUs, -9 % at m = 1 000); DUALIP_GRID_TAIL=0|1
   // forces it
   p->grid_tail = p->m >= 16384 ? 1 : 0;
-  if (const char* gt = getenv("DUALIP_GRID_TAIL")) p->grid_tail = atoi(gt) != 0 ? 1 : 0;
+  p->grid_tail_auto = 1;
+  if (const char* gt = getenv("DUALIP_GRID_TAIL")) {
+    p->grid_tail = atoi(gt) != 0 ? 1 : 0;
+    p->grid_tail_auto = 0;
+  }
   DUALIP_TRY_FAIL(cudaMalloc(&p->lambda_stage, sizeof(float) * (m_pad + 4)));
   DUALIP_TRY_FAIL(cudaMalloc(&p->grad_stage, sizeof(float) * (m_pad + 4)));
   DUALIP_TRY_FAIL(cudaMalloc(&p->scal_stage, sizeof(dualip_scalars)));
@@ -2681,10 +2698,12 @@ int dualip_plan_info(const dualip_plan* p, int64_t* out, int cap) {
     set_error("null argument");
     return DUALIP_EINVAL;
   }
-  const int64_t v[18] = {p->n_slabs, p->n_long - p->n_mid, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
+  const int64_t v[20] = {p->n_slabs, p->n_long - p->n_mid, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
                          p->smode,   p->rows32 * kSlabW, 1 + (p->n_ctalong > 0 ? 1 : 0) + (p->n_long > p->n_mid + p->n_ctalong ? 1 : 0) + ((p->mid_separate && p->n_mid > 0) ? 1 : 0), (int64_t)p->owned_bytes, p->n_short, p->nnz,
-                         p->fixed_point, p->fx_bits, (int64_t)(p->fx_relerr * 1e12), p->stage, p->row_unscale ? 1 : 0, p->n_mid};
-  for (int i = 0; i < cap && i < 18; ++i) out[i] = v[i];
+                         p->fixed_point, p->fx_bits, (int64_t)(p->fx_relerr * 1e12), p->stage, p->row_unscale ? 1 : 0, p->n_mid,
+                         (p->grid_tail && p->n_ctas <= p->n_sms) ? 1 : 0,
+                         p->grid_status_host ? (int64_t)*reinterpret_cast<volatile int*>(p->grid_status_host) : 0};
+  for (int i = 0; i < cap && i < 20; ++i) out[i] = v[i];
   return DUALIP_OK;
 }
 
@@ -2984,6 +3003,10 @@ int dualip_matching_calc_host(dualip_plan* p, const float* lambda_host, const fl
   DUALIP_CUDA_TRY(cudaMemcpyAsync(grad_out_host, p->grad_stage, sizeof(float) * p->m, cudaMemcpyDeviceToHost, st));
   DUALIP_CUDA_TRY(cudaMemcpyAsync(scalars_out_host, p->scal_stage, sizeof(dualip_scalars), cudaMemcpyDeviceToHost, st));
   DUALIP_CUDA_TRY(cudaStreamSynchronize(st));
+  if (p->grid_status_host && *reinterpret_cast<volatile int*>(p->grid_status_host) != 0) {
+    set_error("all-CTA tail: a grid-wide barrier timed out (the CTAs of the launch were not co-resident)");
+    return DUALIP_ECUDA;
+  }
   return DUALIP_OK;
 }
 

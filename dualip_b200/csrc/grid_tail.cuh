@@ -23,21 +23,25 @@ namespace dualip {
 
 constexpr int kTailPart = 8;  // doubles per CTA in the partials table: lg, sp, g2, dg2, dy2, mx
 
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int n, int* status) {
+// status / status_host: the same failure word in device memory (read here, so that after one time-out the later barriers of
+// the run do not wait again) and in mapped host memory (written on a time-out only; the host reads it without a sync).
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int n, int* status, int* status_host) {
   __syncthreads();
   if (threadIdx.x == 0 && n > 1) {
     volatile unsigned int* gen = bar + 1;
     const unsigned int g = *gen;
+    const int failed = status ? *reinterpret_cast<volatile int*>(status) : 0;
     __threadfence();
     if (atomicAdd(bar, 1u) == n - 1) {
       bar[0] = 0u;
       __threadfence();
       atomicAdd(bar + 1, 1u);
-    } else {
+    } else if (!failed) {
       const unsigned long long t0 = global_timer_ns();
       while (*gen == g) {
         if (global_timer_ns() - t0 > 4000000000ull) {  // 4 s: a CTA of this grid never arrived (not co-resident?)
           if (status) *reinterpret_cast<volatile int*>(status) = 2;
+          if (status_host) *reinterpret_cast<volatile int*>(status_host) = 2;
           break;
         }
       }
@@ -81,6 +85,7 @@ __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearF
   const int S = (m + nb - 1) / nb;
   const int r0 = min(m, bid * S), r1 = min(m, r0 + S);
   int* status = SHARDED ? k.peer.status : k.grid_status;
+  int* status_host = SHARDED ? k.peer.status_host : k.grid_status_host;
   // optimizer state that CTA 0 changes at the very end: read by everyone before the first barrier
   const long long t = STEP ? __ldcg(A.pushes) : 0;
   const int slot = (int)(t % H), prev = (int)((t + H - 1) % H);
@@ -95,7 +100,7 @@ __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearF
   dualip_scalars* scal_out = (SHARDED && STEP) ? A.scal_out : k.scalars_out;
   const float* __restrict__ b = (SHARDED && STEP) ? A.b : k.b;
 
-  grid_barrier(k.grid_bar, nb, status);  // B1: the accumulators hold this rank's complete sums
+  grid_barrier(k.grid_bar, nb, status, status_host);  // B1: the accumulators hold this rank's complete sums
   double cx_local, xx_local;
   load_scalar_sums(k, T, cx_local, xx_local);
   double cxv = cx_local, xxv = xx_local;
@@ -118,7 +123,7 @@ __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearF
         }
     }
     __threadfence_system();
-    grid_barrier(k.grid_bar, nb, status);  // B2: every CTA's stores into the peers' windows are performed
+    grid_barrier(k.grid_bar, nb, status, status_host);  // B2: every CTA's stores into the peers' windows are performed
     if (bid == 0) {
       if (tid < P.world) {
         st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.win[tid]) + P.rank, seq);
@@ -134,7 +139,7 @@ __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearF
         asm volatile("fence.acq_rel.sys;" ::: "memory");
       }
     }
-    grid_barrier(k.grid_bar, nb, status);  // B3: every peer's sums are in this rank's window
+    grid_barrier(k.grid_bar, nb, status, status_host);  // B3: every peer's sums are in this rank's window
     asm volatile("fence.acq_rel.sys;" ::: "memory");
     if (tid == 0) {  // the two scalars, added in rank order like the rows
       float c0 = 0.f, c1 = 0.f;
@@ -205,7 +210,7 @@ __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearF
     }
   }
   __threadfence();
-  grid_barrier(k.grid_bar, nb, status);  // B_last: every CTA's partials are in the table
+  grid_barrier(k.grid_bar, nb, status, status_host);  // B_last: every CTA's partials are in the table
 
   // ---- totals, in the same fixed order on every CTA (and on every rank) ----
   if (warp < 6) {

@@ -289,12 +289,23 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
 
     # -- introspection -------------------------------------------------------------------------------------
     def plan_info(self) -> dict:
-        buf = (ctypes.c_int64 * 18)()
-        _native.check(_native.lib().dualip_plan_info(self._plan, buf, 18))
+        buf = (ctypes.c_int64 * 20)()
+        _native.check(_native.lib().dualip_plan_info(self._plan, buf, 20))
         names = ["n_slabs", "n_long_cols", "n_ctas", "threads", "smem_bytes", "row_bits", "smem_mode", "slab_elems",
                  "launches_per_calc", "owned_bytes", "n_slab_cols", "nnz", "fixed_point", "fixed_point_bits",
-                 "fixed_point_relerr_e12", "staged_degree", "row_scaled", "n_mid_cols"]
+                 "fixed_point_relerr_e12", "staged_degree", "row_scaled", "n_mid_cols", "grid_tail", "grid_barrier_status"]
         return dict(zip(names, list(buf)))
+
+    def check_grid_barrier(self) -> None:
+        """Raises if a grid-wide barrier of the all-CTA tail (csrc/grid_tail.cuh) ever timed out on this plan: the CTAs of a
+        launch were not co-resident for seconds, and what that launch produced is invalid.  Reads a word in mapped host memory
+        (no synchronisation); call it after the stream has been synchronised."""
+        buf = (ctypes.c_int64 * 20)()
+        _native.check(_native.lib().dualip_plan_info(self._plan, buf, 20))
+        if buf[19]:
+            raise RuntimeError("dualip_b200: a grid-wide barrier of the fused kernel timed out (status "
+                               f"{int(buf[19])}): its CTAs were not co-resident; results of this run are invalid "
+                               "(DUALIP_GRID_TAIL=0 selects the single-CTA tail)")
 
     def algorithmic_bytes(self, save_primal: bool = False) -> int:
         """B_alg of SURVEY.md §8(d): fp32 a + fp32 c + int32 row per nnz, int32 ccol per column, read lambda and b and

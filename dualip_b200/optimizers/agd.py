@@ -601,8 +601,8 @@ class FusedAscentLoop:
         """A rank did not arrive within the time-out: this run is invalid and the windows are unusable from now on."""
         self.f._peer_failed = True
         self.f._peer = None
-        raise RuntimeError("peer exchange: a rank did not arrive within the time-out (ranks out of step?); results of this run "
-                           "are invalid.  DUALIP_PEER_EXCHANGE=0 selects the NCCL path")
+        raise RuntimeError("peer exchange: a rank (status 1) or a CTA of this rank's own grid (status 2) did not arrive within the "
+                           "time-out (ranks out of step?); results of this run are invalid.  DUALIP_PEER_EXCHANGE=0 selects the NCCL path")
 
     def _x_tensor(self, stream) -> torch.Tensor:
         """The evaluation point as a tensor (a copy of the native state's x), for the tensor-op part of block entries."""
@@ -625,6 +625,8 @@ class FusedAscentLoop:
             _native.check(self.lib.dualip_agd_read_log(self.handle, n, obj_log, step_log, stream), "dualip_agd_read_log")
             y = self.current_dual()
             torch.cuda.synchronize(self.device)
+            if self.peer is None and hasattr(self._tune, "check_grid_barrier"):
+                self._tune.check_grid_barrier()  # all-CTA tail: a grid-wide barrier that timed out invalidates the run
             if self.peer is not None:
                 timed_out = self.peer.status()
                 if dist.is_available() and dist.is_initialized() and self.peer.world == dist.get_world_size():

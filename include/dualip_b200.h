@@ -124,7 +124,12 @@ int dualip_plan_rebalance(dualip_plan* plan, void* stream);
  * [15] longest column whose slab is staged through shared memory by the TMA engine (0: plain vector loads)
  * [16] 1 if the rows are stored scaled by per-row powers of two (fixed-point resolution per row; results unchanged)
  * [17] n_mid_cols: columns of 21..1024 entries kept column-contiguous and processed a warp per column inside the same
- *      launch ([1] counts only the columns beyond 1024 entries, which take the separate long-column kernel) */
+ *      launch ([1] counts only the columns beyond 1024 entries, which take the separate long-column kernel)
+ * [18] 1 if this plan's own launches share the m-length tail among all CTAs (m >= 16384 or DUALIP_GRID_TAIL=1; sharded
+ *      launches of 4 or more ranks also do so from m >= 8192 unless DUALIP_GRID_TAIL=0)
+ * [19] 0, or 2 once a grid-wide barrier of the all-CTA tail timed out (the CTAs of a launch were not co-resident, e.g. another
+ *      process held SMs for seconds): results of that launch are invalid.  Read from mapped host memory, no synchronisation;
+ *      sharded launches report the same event through dualip_peer_status. */
 int dualip_plan_info(const dualip_plan* plan, int64_t* out, int cap);
 
 /* One evaluation of the dual at lambda on this shard, epilogue included (single device).

@@ -218,8 +218,10 @@ def test_all_cta_tail_equals_the_last_cta_tail(monkeypatch, decay):
         monkeypatch.setenv("DUALIP_GRAPH", graph)
         monkeypatch.setenv("DUALIP_GRAPH_CHUNK", "8")
         obj = _objective(p, _mixed_map(n), 2e-2)
-        assert obj.plan_info()["n_ctas"] > 1
+        assert obj.plan_info()["n_ctas"] > 1 and obj.plan_info()["grid_tail"] == int(env)
         outs[tag] = AcceleratedGradientDescent(**kw).maximize(obj, lam0)
+        assert obj.plan_info()["grid_barrier_status"] == 0  # (2 after a grid-wide barrier timed out: maximize() would raise)
+        obj.check_grid_barrier()
     a, b, c = outs["last"], outs["grid"], outs["grid_graph"]
     assert np.allclose(a.dual_objective_log, b.dual_objective_log, rtol=1e-9)
     assert np.allclose(a.step_size_log, b.step_size_log, rtol=1e-6)
