@@ -138,14 +138,37 @@ _lib = None
 _lock = threading.Lock()
 
 
+def _source_digest() -> str:
+    """sha256 over the CUDA sources, the public header and the Makefile (names and contents)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC_DIR, n) for n in os.listdir(CSRC_DIR)
+                   if n.endswith((".cu", ".cuh", ".inc")) or n == "Makefile")
+    files.append(os.path.join(os.path.dirname(CSRC_DIR), "..", "include", "dualip_b200.h"))
+    for path in files:
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def build(verbose: bool = False) -> str:
-    """Compile the CUDA sources for sm_100a into dualip_b200/_lib/ (nvcc cross-compiles without a GPU)."""
+    """Compile the CUDA sources for sm_100a into dualip_b200/_lib/ (nvcc cross-compiles without a GPU).  The library is up to
+    date when the digest of the sources recorded beside it matches: a copied tree (file times lost, e.g. the snapshot on a GPU
+    box) is not recompiled -- calc.cu alone takes minutes."""
+    digest = _source_digest()
+    stamp = os.path.join(os.path.dirname(LIB_PATH), "SOURCE_DIGEST")
+    if os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return LIB_PATH
     res = subprocess.run(["make", "-j4", "-C", CSRC_DIR], capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)
         print(res.stderr)
     if res.returncode != 0:
         raise RuntimeError("building libdualip_b200.so failed")
+    with open(stamp, "w") as fh:
+        fh.write(digest + "\n")
     return LIB_PATH
 
 
