@@ -57,3 +57,32 @@ def test_sass_is_sm100a_and_uses_bulk_async_copy():
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", _native.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "UBLKRED" in sass and "SYNCS" in sass
+
+
+def test_build_is_up_to_date_by_source_digest(monkeypatch, tmp_path):
+    """build() compares a digest of the sources with the one recorded beside the library, not file times: a copied tree
+    (the snapshot on a GPU box) must not recompile, an edited source must."""
+    import subprocess
+
+    stamp = os.path.join(os.path.dirname(_native.LIB_PATH), "SOURCE_DIGEST")
+    if not os.path.exists(stamp):
+        pytest.skip("library was built by make directly (no digest recorded)")
+    assert open(stamp).read().strip() == _native._source_digest(), "libdualip_b200.so is stale: run __graft_entry__.build()"
+
+    def no_make(*a, **k):
+        raise AssertionError("make must not run when the digest matches")
+
+    monkeypatch.setattr(subprocess, "run", no_make)
+    assert _native.build() == _native.LIB_PATH
+    # a changed source changes the digest
+    csrc = tmp_path / "pkg" / "csrc"  # the header sits at <package>/../include, as in the repository
+    csrc.mkdir(parents=True)
+    (tmp_path / "include").mkdir()
+    for name in os.listdir(_native.CSRC_DIR):
+        if name.endswith((".cu", ".cuh", ".inc")) or name == "Makefile":
+            (csrc / name).write_bytes(open(os.path.join(_native.CSRC_DIR, name), "rb").read())
+    (tmp_path / "include" / "dualip_b200.h").write_bytes(open(os.path.join(ROOT, "include", "dualip_b200.h"), "rb").read())
+    monkeypatch.setattr(_native, "CSRC_DIR", str(csrc))
+    same = _native._source_digest()
+    (csrc / "lp.cu").write_bytes((csrc / "lp.cu").read_bytes() + b"\n// edited\n")
+    assert _native._source_digest() != same
