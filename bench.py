@@ -108,14 +108,20 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+NCU_TRAFFIC_FILES = ("profiles/r2/ncu_traffic.json", "profiles/r1_ncu_traffic.json")  # newest capture first
+
+
 def ncu_traffic_bytes(workload_id: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this workload (profiles/r1_ncu_traffic.json), or None if there is none."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as fh:
-            return float(json.load(fh)[workload_id]["traffic_bytes_per_launch"])
-    except Exception:
-        return None
+    """(dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, file it came from) from the committed
+    `ncu --set full` capture of this workload, or (None, None) if there is none."""
+    for rel in NCU_TRAFFIC_FILES:
+        try:
+            with open(os.path.join(ROOT, rel)) as fh:
+                entry = json.load(fh)[workload_id]
+            return float(entry["traffic_bytes_per_launch"]), entry.get("source", rel)
+        except Exception:
+            continue
+    return None, None
 
 
 def mixed_projection_map(n_local: int, col_start: int, device):
@@ -402,6 +408,12 @@ def run_native(args):
 
     if rank == 0:
         it_per_s = K / (ms_total * 1e-3)
+        if args.ncu_traffic_bytes is not None:
+            traffic, traffic_src = args.ncu_traffic_bytes, "--ncu-traffic-bytes"
+        elif world == 1 and args.entities == WORKLOADS[args.workload][0]:
+            traffic, traffic_src = ncu_traffic_bytes(args.workload)
+        else:
+            traffic, traffic_src = None, None
         line = {
             "metric": "dual-ascent iterations/sec", "value": it_per_s, "unit": "iterations/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -421,14 +433,14 @@ def run_native(args):
             "gpu_launches": launches_per_step * K,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.ncu_traffic_bytes if args.ncu_traffic_bytes is not None
-                         else (ncu_traffic_bytes(args.workload) if world == 1 and args.entities == WORKLOADS[args.workload][0] else None),
+                         "traffic": traffic,
                          "kernel": "matching_slab_kernel", "kernel_ms": kernel_ms,
                          "kernel_ms_min": min(kernel_times), "kernel_ms_max": max(kernel_times),
                          "algorithmic_bytes": b_alg, "peak_source": peak_src,
                          "note": ("rank-0 shard; " if world > 1 else "") + "average over the K launches of the timed region "
                                  "(the kernel's cost depends on the iterate: how many simplex columns take the sorted scan); "
-                                 "traffic: ncu --set full capture of this workload (profiles/r1_ncu_c3_full_summary.txt)"},
+                                 + (f"traffic: ncu --set full capture of this workload ({traffic_src})" if traffic is not None
+                                    else "traffic: no ncu capture of this configuration")},
             "final_dual_objective": result.dual_objective,
             "setup": {"generate_s": info["gen_s"], "plan_s": info["plan_s"], "plan": info["plan"]},
         }
