@@ -173,6 +173,7 @@ struct dualip_plan {
   int* grid_status_host_dev = nullptr;  // its device-side address
   int grid_tail = 1;                 // all-CTA tail for this plan's own launches (size rule, or forced by DUALIP_GRID_TAIL=0|1)
   int grid_tail_auto = 1;            // 1: not forced; sharded launches may still turn it on from the world size
+  int last_grid_tail = 0;            // what the most recent launch of the slab kernel used (introspection)
   float* lambda_stage = nullptr;  // m floats, for *_calc_host
   float* grad_stage = nullptr;
   dualip_scalars* scal_stage = nullptr;
@@ -1743,6 +1744,7 @@ static int launch_eval(dualip_plan* p, const float* lambda, const float* b, doub
     const bool wide_world = (mode == 2 || mode == 3) && fuse->peer.world >= 4 && p->m >= 8192;
     const bool want = p->grid_tail || (p->grid_tail_auto && wide_world);
     k.grid_tail = (want && p->n_ctas <= p->n_sms && x_out == nullptr && diag == nullptr && ok_mode) ? 1 : 0;
+    p->last_grid_tail = k.grid_tail;
   }
   k.grid_bar = p->grid_bar;
   k.tail_part = p->tail_part;
@@ -2698,12 +2700,13 @@ int dualip_plan_info(const dualip_plan* p, int64_t* out, int cap) {
     set_error("null argument");
     return DUALIP_EINVAL;
   }
-  const int64_t v[20] = {p->n_slabs, p->n_long - p->n_mid, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
+  const int64_t v[21] = {p->n_slabs, p->n_long - p->n_mid, p->n_ctas, p->threads, (int64_t)p->smem_bytes, p->row_bits,
                          p->smode,   p->rows32 * kSlabW, 1 + (p->n_ctalong > 0 ? 1 : 0) + (p->n_long > p->n_mid + p->n_ctalong ? 1 : 0) + ((p->mid_separate && p->n_mid > 0) ? 1 : 0), (int64_t)p->owned_bytes, p->n_short, p->nnz,
                          p->fixed_point, p->fx_bits, (int64_t)(p->fx_relerr * 1e12), p->stage, p->row_unscale ? 1 : 0, p->n_mid,
                          (p->grid_tail && p->n_ctas <= p->n_sms) ? 1 : 0,
-                         p->grid_status_host ? (int64_t)*reinterpret_cast<volatile int*>(p->grid_status_host) : 0};
-  for (int i = 0; i < cap && i < 20; ++i) out[i] = v[i];
+                         p->grid_status_host ? (int64_t)*reinterpret_cast<volatile int*>(p->grid_status_host) : 0,
+                         p->last_grid_tail};
+  for (int i = 0; i < cap && i < 21; ++i) out[i] = v[i];
   return DUALIP_OK;
 }
 

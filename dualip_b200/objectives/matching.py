@@ -289,11 +289,12 @@ class MatchingSolverDualObjectiveFunction(BaseObjective):
 
     # -- introspection -------------------------------------------------------------------------------------
     def plan_info(self) -> dict:
-        buf = (ctypes.c_int64 * 20)()
-        _native.check(_native.lib().dualip_plan_info(self._plan, buf, 20))
+        buf = (ctypes.c_int64 * 21)()
+        _native.check(_native.lib().dualip_plan_info(self._plan, buf, 21))
         names = ["n_slabs", "n_long_cols", "n_ctas", "threads", "smem_bytes", "row_bits", "smem_mode", "slab_elems",
                  "launches_per_calc", "owned_bytes", "n_slab_cols", "nnz", "fixed_point", "fixed_point_bits",
-                 "fixed_point_relerr_e12", "staged_degree", "row_scaled", "n_mid_cols", "grid_tail", "grid_barrier_status"]
+                 "fixed_point_relerr_e12", "staged_degree", "row_scaled", "n_mid_cols", "grid_tail", "grid_barrier_status",
+                 "last_launch_grid_tail"]
         return dict(zip(names, list(buf)))
 
     def check_grid_barrier(self) -> None:

@@ -129,7 +129,8 @@ int dualip_plan_rebalance(dualip_plan* plan, void* stream);
  *      launches of 4 or more ranks also do so from m >= 8192 unless DUALIP_GRID_TAIL=0)
  * [19] 0, or 2 once a grid-wide barrier of the all-CTA tail timed out (the CTAs of a launch were not co-resident, e.g. another
  *      process held SMs for seconds): results of that launch are invalid.  Read from mapped host memory, no synchronisation;
- *      sharded launches report the same event through dualip_peer_status. */
+ *      sharded launches report the same event through dualip_peer_status.
+ * [20] 1 if the most recent launch of the hot kernel on this plan used the all-CTA tail */
 int dualip_plan_info(const dualip_plan* plan, int64_t* out, int cap);
 
 /* One evaluation of the dual at lambda on this shard, epilogue included (single device).

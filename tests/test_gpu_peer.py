@@ -209,3 +209,86 @@ def test_sharded_evaluation_through_peer_memory_without_a_step(world, push, grid
         assert abs(float(scals[0][0]) - float(ref.scalars64[0])) <= 1e-6 * abs(float(ref.scalars64[0]))
     for e in ex:
         e.close()
+
+
+@pytest.mark.parametrize("world,shared_tail", [(2, 0), (4, 1)])
+def test_sharded_launches_of_four_or_more_ranks_share_the_tail(world, shared_tail, monkeypatch):
+    """Size rule of the all-CTA tail in sharded launches (csrc/calc.cu launch_eval): from m = 8192 on, launches of 4 or more
+    ranks let every CTA store a slice of the sums into the peers' windows and add a slice of the W slots (measured on 8 GPUs:
+    2935 -> 3135 it/s); 2 ranks keep the last-CTA tail.  Both for the evaluation-only launch of the host-buffer path and for the
+    fused step, against the unsharded evaluation and against the same run with the rule switched off.  DUALIP_CTAS=32 keeps
+    the `world` grids co-resident on the one GPU of this test (the grid-wide barriers need that; one process per GPU has it
+    by construction)."""
+    monkeypatch.setenv("DUALIP_PEER_TIMEOUT_MS", "3000")
+    monkeypatch.setenv("DUALIP_CTAS", "32")
+    monkeypatch.setenv("DUALIP_REBALANCE", "0")
+    monkeypatch.delenv("DUALIP_GRID_TAIL", raising=False)
+    lib = _native.lib()
+    p = random_problem(37, 6000, 8200, 8.0, scale_c=10.0, lam_scale=0.5)
+    n, m, gamma, iters = p["n_cols"], p["n_rows"], 2e-2, 12
+    A, C = _csc(p)
+    b = torch.from_numpy(p["b"]).to(DEV)
+    pm = create_projection_map("simplex", {"z": 1.0}, n)
+    whole = MatchingSolverDualObjectiveFunction(MatchingInputArgs(A, C, pm, b), gamma)
+    a_s, c_s, index_map = split_tensors_to_devices(A, C, [DEV] * world)
+    beta = AcceleratedGradientDescent(max_iter=iters, gamma=gamma).beta_seq.tolist()
+
+    def shards():
+        return [MatchingSolverDualObjectiveFunction(
+            MatchingInputArgs(a_s[k], c_s[k], global_to_local_projection_map(pm, index_map[k]), None), gamma) for k in range(world)]
+
+    def exchanges():
+        ex = [PeerExchange(m, k, world, torch.device(DEV)) for k in range(world)]
+        PeerExchange.connect_local(ex)
+        return ex
+
+    # evaluation only: dualip_matching_calc_peer
+    objs, ex = shards(), exchanges()
+    assert all(o.plan_info()["n_ctas"] <= 32 and o.plan_info()["grid_tail"] == 0 for o in objs)
+    streams = [torch.cuda.Stream(device=DEV) for _ in range(world)]
+    grads = [torch.empty(m, device=DEV) for _ in range(world)]
+    scals = [torch.zeros(N_SCAL, dtype=torch.float64, device=DEV) for _ in range(world)]
+    lam = torch.from_numpy(p["lam"]).to(DEV)
+    torch.cuda.synchronize()
+    for _ in range(2):
+        for k in range(world):
+            with torch.cuda.stream(streams[k]):
+                _native.check(lib.dualip_matching_calc_peer(objs[k]._plan, ex[k].handle, lam.data_ptr(), b.data_ptr(), gamma,
+                                                            grads[k].data_ptr(), scals[k].data_ptr(), streams[k].cuda_stream))
+        torch.cuda.synchronize()
+    assert [e.status() for e in ex] == [0] * world
+    assert [o.plan_info()["last_launch_grid_tail"] for o in objs] == [shared_tail] * world
+    ref = whole.calculate(lam)
+    assert whole.plan_info()["last_launch_grid_tail"] == 0
+    for k in range(world):
+        assert torch.equal(grads[k], grads[0]) and torch.equal(scals[k], scals[0]), "ranks must obtain identical bits"
+    assert torch.allclose(grads[0], ref.dual_gradient, rtol=1e-5, atol=1e-5)
+    assert abs(float(scals[0][0]) - float(ref.scalars64[0])) <= 1e-6 * abs(float(ref.scalars64[0]))
+    for e in ex:
+        e.close()
+
+    # fused step: dualip_matching_ascent_step_peer, rule on (default) and off
+    runs = {}
+    for tag in ("rule", "off"):
+        if tag == "off":
+            monkeypatch.setenv("DUALIP_GRID_TAIL", "0")
+        ranks, ex = [_Rank(o, m, 1e-3, 0.1) for o in shards()], exchanges()
+        torch.cuda.synchronize()
+        for i in range(iters):
+            for k, r in enumerate(ranks):
+                with torch.cuda.stream(r.stream):
+                    r.obj.launch_ascent_step_peer(r.agd, ex[k].handle, b.data_ptr(), gamma, r.grad.data_ptr(), r.scal.data_ptr(),
+                                                  beta[i], 0, 1.0, i)
+        torch.cuda.synchronize()
+        assert [e.status() for e in ex] == [0] * world
+        assert [r.obj.plan_info()["last_launch_grid_tail"] for r in ranks] == [shared_tail if tag == "rule" else 0] * world
+        logs, duals = [r.logs(iters) for r in ranks], [r.dual() for r in ranks]
+        for k in range(1, world):
+            assert np.array_equal(logs[k][0], logs[0][0]) and torch.equal(duals[k], duals[0]), "replicas must stay bit-identical"
+        runs[tag] = (logs[0], duals[0])
+        for r in ranks:
+            lib.dualip_agd_destroy(r.agd)
+        for e in ex:
+            e.close()
+    assert np.allclose(runs["rule"][0][0], runs["off"][0][0], rtol=1e-9) and np.allclose(runs["rule"][0][1], runs["off"][0][1], rtol=1e-6)
+    assert torch.allclose(runs["rule"][1], runs["off"][1], rtol=1e-5, atol=1e-7)
