@@ -13,7 +13,7 @@ _SUBMODULES = [
     "types", "run_solver", "objectives", "objectives.base", "objectives.matching", "objectives.miplib", "objectives.matching_fairness",
     "projections", "projections.base",
     "projections.box", "projections.cone", "projections.simplex", "optimizers", "optimizers.agd", "optimizers.agd_utils",
-    "utils", "utils.dist_utils", "utils.sparse_utils", "utils.mlflow_utils", "preprocessing", "preprocessing.precondition",
+    "utils", "utils.dist_utils", "utils.sparse_utils", "utils.mlflow_utils", "utils.step_size_utility", "preprocessing", "preprocessing.precondition",
     "preprocessing.input_validation",
 ]
 

@@ -216,6 +216,40 @@ def test_step_size_rule():
     assert calculate_step_size(torch.tensor([1.0]), torch.tensor([0.0]), gh, dh) == 1e-5
 
 
+def test_numpy_step_size_utility_follows_the_tensor_rule_and_the_reference_module():
+    """utils/step_size_utility.py (numpy iterates): same steps as optimizers/agd_utils.py on the same sequence, and -- where
+    the reference tree is present -- as the reference's own module (src/dualip/utils/step_size_utility.py)."""
+    import importlib.util
+    import os
+
+    import numpy as np
+
+    from dualip_b200.utils import step_size_utility as S
+
+    rng = np.random.default_rng(3)
+    seq = [(rng.standard_normal(40), rng.standard_normal(40)) for _ in range(22)]
+    seq[17] = (seq[16][0].copy(), seq[16][1].copy())  # a repeated pair: 0/0 = NaN estimate -> initial step while it is in the ring
+    ref_path = "/root/reference/src/dualip/utils/step_size_utility.py"
+    R = None
+    if os.path.exists(ref_path):
+        spec = importlib.util.spec_from_file_location("_ref_step_size_utility", ref_path)
+        R = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(R)
+    gh, dh, gt, dt, gr, dr = [], [], [], [], [], []
+    steps = []
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for g, d in seq:
+            s_np = S.calculate_step_size(g, d, gh, dh, 15, 1e-5, 0.1)
+            s_t = calculate_step_size(torch.from_numpy(g), torch.from_numpy(d), gt, dt, 15, 1e-5, 0.1)
+            assert s_np == pytest.approx(s_t, rel=1e-12)
+            if R is not None:
+                assert s_np == R.calculate_step_size(g, d, gr, dr, 15, 1e-5, 0.1)
+            steps.append(s_np)
+    assert len(gh) == len(dh) == 15 and steps[:14] == [1e-5] * 14 and steps[14] != 1e-5 and steps[17] == 1e-5
+    assert S.estimate_lipschitz_constant(np.zeros(1), np.full(1, 2.0), np.zeros(1), np.ones(1)) == 2.0
+    assert S.step_size_from_lipschitz_constants([0.0] * 14, 15, 1e-5, 0.1) == 0.1
+
+
 def test_run_solver_argument_errors():
     A = torch.eye(3).to_sparse_csc()
     args = MatchingInputArgs(A, A, create_projection_map("simplex", {"z": 1.0}, 3), torch.ones(3))
