@@ -227,8 +227,9 @@ def test_numpy_step_size_utility_follows_the_tensor_rule_and_the_reference_modul
     from dualip_b200.utils import step_size_utility as S
 
     rng = np.random.default_rng(3)
-    seq = [(rng.standard_normal(40), rng.standard_normal(40)) for _ in range(22)]
-    seq[17] = (seq[16][0].copy(), seq[16][1].copy())  # a repeated pair: 0/0 = NaN estimate -> initial step while it is in the ring
+    seq = [(rng.standard_normal(40), rng.standard_normal(40)) for _ in range(33)]
+    # a repeated pair gives a 0/0 = NaN estimate: Python's max() skips it unless it is the FIRST of the ring (agd_utils.py:58-60)
+    seq[17] = (seq[16][0].copy(), seq[16][1].copy())
     ref_path = "/root/reference/src/dualip/utils/step_size_utility.py"
     R = None
     if os.path.exists(ref_path):
@@ -245,7 +246,8 @@ def test_numpy_step_size_utility_follows_the_tensor_rule_and_the_reference_modul
             if R is not None:
                 assert s_np == R.calculate_step_size(g, d, gr, dr, 15, 1e-5, 0.1)
             steps.append(s_np)
-    assert len(gh) == len(dh) == 15 and steps[:14] == [1e-5] * 14 and steps[14] != 1e-5 and steps[17] == 1e-5
+    assert len(gh) == len(dh) == 15 and steps[:14] == [1e-5] * 14 and steps[14] == 0.1 and steps[17] == 0.1
+    assert steps[30] == 1e-5 and steps[31] == 0.1  # the NaN estimate heads the ring exactly once
     assert S.estimate_lipschitz_constant(np.zeros(1), np.full(1, 2.0), np.zeros(1), np.ones(1)) == 2.0
     assert S.step_size_from_lipschitz_constants([0.0] * 14, 15, 1e-5, 0.1) == 0.1
 
