@@ -25,7 +25,10 @@ constexpr int kTailPart = 8;  // doubles per CTA in the partials table: lg, sp, 
 
 // status / status_host: the same failure word in device memory (read here, so that after one time-out the later barriers of
 // the run do not wait again) and in mapped host memory (written on a time-out only; the host reads it without a sync).
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int n, int* status, int* status_host) {
+// timeout_ns: 4 s for a grid on its own; a sharded grid also waits (in B3) for CTA 0's wait on the peers, which is bounded by
+// the exchange's own time-out, so its barriers allow that much more.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int n, int* status, int* status_host,
+                                             unsigned long long timeout_ns) {
   __syncthreads();
   if (threadIdx.x == 0 && n > 1) {
     volatile unsigned int* gen = bar + 1;
@@ -39,7 +42,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int n, 
     } else if (!failed) {
       const unsigned long long t0 = global_timer_ns();
       while (*gen == g) {
-        if (global_timer_ns() - t0 > 4000000000ull) {  // 4 s: a CTA of this grid never arrived (not co-resident?)
+        if (global_timer_ns() - t0 > timeout_ns) {  // a CTA of this grid never arrived (not co-resident?)
           if (status) *reinterpret_cast<volatile int*>(status) = 2;
           if (status_host) *reinterpret_cast<volatile int*>(status_host) = 2;
           break;
@@ -86,6 +89,7 @@ __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearF
   const int r0 = min(m, bid * S), r1 = min(m, r0 + S);
   int* status = SHARDED ? k.peer.status : k.grid_status;
   int* status_host = SHARDED ? k.peer.status_host : k.grid_status_host;
+  const unsigned long long bar_timeout = 4000000000ull + (SHARDED ? k.peer.timeout_ns : 0ull);
   // optimizer state that CTA 0 changes at the very end: read by everyone before the first barrier
   const long long t = STEP ? __ldcg(A.pushes) : 0;
   const int slot = (int)(t % H), prev = (int)((t + H - 1) % H);
@@ -100,7 +104,7 @@ __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearF
   dualip_scalars* scal_out = (SHARDED && STEP) ? A.scal_out : k.scalars_out;
   const float* __restrict__ b = (SHARDED && STEP) ? A.b : k.b;
 
-  grid_barrier(k.grid_bar, nb, status, status_host);  // B1: the accumulators hold this rank's complete sums
+  grid_barrier(k.grid_bar, nb, status, status_host, bar_timeout);  // B1: the accumulators hold this rank's complete sums
   double cx_local, xx_local;
   load_scalar_sums(k, T, cx_local, xx_local);
   double cxv = cx_local, xxv = xx_local;
@@ -123,7 +127,7 @@ __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearF
         }
     }
     __threadfence_system();
-    grid_barrier(k.grid_bar, nb, status, status_host);  // B2: every CTA's stores into the peers' windows are performed
+    grid_barrier(k.grid_bar, nb, status, status_host, bar_timeout);  // B2: every CTA's stores into the peers' windows are performed
     if (bid == 0) {
       if (tid < P.world) {
         st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.win[tid]) + P.rank, seq);
@@ -139,7 +143,7 @@ __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearF
         asm volatile("fence.acq_rel.sys;" ::: "memory");
       }
     }
-    grid_barrier(k.grid_bar, nb, status, status_host);  // B3: every peer's sums are in this rank's window
+    grid_barrier(k.grid_bar, nb, status, status_host, bar_timeout);  // B3: every peer's sums are in this rank's window
     asm volatile("fence.acq_rel.sys;" ::: "memory");
     if (tid == 0) {  // the two scalars, added in rank order like the rows
       float c0 = 0.f, c1 = 0.f;
@@ -210,7 +214,7 @@ __device__ __forceinline__ void grid_tail(const KArgs& k, SumFn sum_load, ClearF
     }
   }
   __threadfence();
-  grid_barrier(k.grid_bar, nb, status, status_host);  // B_last: every CTA's partials are in the table
+  grid_barrier(k.grid_bar, nb, status, status_host, bar_timeout);  // B_last: every CTA's partials are in the table
 
   // ---- totals, in the same fixed order on every CTA (and on every rank) ----
   if (warp < 6) {
